@@ -1,0 +1,145 @@
+/* sfd2_b200.h - C ABI of libsfd2_b200.so: the B200 (sm_100a) implementation of the
+ * SFD2 feature-extraction + mutual-NN matching hot path.
+ *
+ * The reference (feixue94/sfd2) is pure Python/PyTorch and has no FFI of its own;
+ * each entry point below names the reference Python interface it replaces
+ * (paths relative to the reference root).  The Python drop-ins in sfd2_b200/
+ * (extractor.py, matchers.py) bind these symbols with ctypes - see INTEGRATION.md
+ * for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative sfd2_status on failure and
+ *    never throws; sfd2_last_error() gives the message for the calling thread;
+ *  - the CALLER owns every buffer; the library owns its packed weights and a
+ *    workspace that is (re)sized when the image size grows;
+ *  - *_dev entry points take DEVICE pointers and are asynchronous on `stream`
+ *    (a cudaStream_t passed as void*; NULL = default stream): no hidden
+ *    synchronisation, no allocation once the workspace exists;
+ *  - *_host entry points take HOST pointers, do the H2D/D2H copies themselves and
+ *    return when the results are in the host buffers;
+ *  - outputs have fixed capacity (topk rows per image) plus a count per image;
+ *  - a context is bound to one device and must not be used from two threads at once.
+ */
+#ifndef SFD2_B200_H
+#define SFD2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SFD2_API __attribute__((visibility("default")))
+#else
+#define SFD2_API
+#endif
+
+#define SFD2_ABI_VERSION 1
+#define SFD2_DESC_DIM 128
+
+typedef struct sfd2_ctx sfd2_ctx;
+
+typedef enum {
+  SFD2_OK = 0,
+  SFD2_ERR_ARG = -1,       /* bad argument / unsupported shape            */
+  SFD2_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed          */
+  SFD2_ERR_WEIGHTS = -3,   /* malformed weight blob                        */
+  SFD2_ERR_OVERFLOW = -4,  /* more NMS candidates than the workspace holds */
+  SFD2_ERR_NOMEM = -5
+} sfd2_status;
+
+/* precision of the convolution stack */
+typedef enum {
+  SFD2_PREC_FP32 = 0,     /* CUDA-core fp32 FMA (reference-grade, slow)                          */
+  SFD2_PREC_TC_EXACT = 1, /* tcgen05 fp16 x3 split (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi), fp32 acc */
+  SFD2_PREC_TC_FAST = 2   /* tcgen05 fp16 x1, fp32 accumulate                                    */
+} sfd2_precision;
+
+/* image element type for sfd2_extract_* */
+typedef enum {
+  SFD2_IMG_F32_NCHW = 0, /* float32 [n,3,h,w] RGB in [0,1]  (what ImageDataset yields)  */
+  SFD2_IMG_U8_NHWC = 1   /* uint8   [n,h,w,3] RGB; divided by 255 on the device         */
+} sfd2_img_dtype;
+
+typedef struct {
+  float conf_th;      /* nets/extractor.py:143 conf_thresh (0.001 in every preset)      */
+  int32_t nms_radius; /* nets/extractor.py:145 nms_dist = 4 (only 4 is implemented)     */
+  int32_t border;     /* nets/extractor.py:146 border_remove = 4                        */
+  int32_t topk;       /* extract_localization.py max_keypoints; rows of every output    */
+  int32_t precision;  /* sfd2_precision                                                 */
+  int32_t use_stability; /* extract_localization.py:30 use_stability                    */
+} sfd2_extract_params;
+
+typedef struct {
+  int32_t do_mutual_check;  /* hloc/matchers/nearest_neighbor.py:31                      */
+  float distance_threshold; /* :30 ; <= 0 means None                                     */
+  float ratio_threshold;    /* :29 ; <= 0 means None                                     */
+  int32_t precision;        /* sfd2_precision (FP32 = CUDA cores, TC_* = tcgen05)        */
+} sfd2_match_params;
+
+SFD2_API int sfd2_abi_version(void);
+SFD2_API const char* sfd2_last_error(void);
+
+/* Replaces get_model(...)[0] + model.cuda()  (extract_localization.py:208-218,227).
+ * `blob` is the folded weight blob made by sfd2_b200/weights.py (host memory). */
+SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx** out);
+SFD2_API int sfd2_destroy(sfd2_ctx* ctx);
+
+/* Replaces extract_resnet_return(model, img, conf_th, mask=None, topK, scales=[1.0])
+ * (nets/extractor.py:97-337): normalise -> ResSegNetV2.det (nets/sfd2.py:313-354)
+ * -> x stability -> simple_nms(4) -> >conf_th -> border -> sort -> bilinear
+ * descriptor sampling + L2 -> top-K.
+ *   img      [n] images of dtype `img_dtype`, h x w each
+ *   kpts     float32 [n, topk, 2]  (x, y) pixel indices, score-descending
+ *   scores   float32 [n, topk]
+ *   desc     float32 [n, topk, 128] unit-norm rows
+ *   counts   int32   [n] valid rows per image (<= topk); rows beyond are zero */
+SFD2_API int sfd2_extract_dev(sfd2_ctx* ctx, const void* img_dev, int img_dtype, int n, int h, int w,
+                     const sfd2_extract_params* p, float* kpts_dev, float* scores_dev,
+                     float* desc_dev, int32_t* counts_dev, void* stream);
+SFD2_API int sfd2_extract_host(sfd2_ctx* ctx, const void* img_host, int img_dtype, int n, int h, int w,
+                      const sfd2_extract_params* p, float* kpts_host, float* scores_host,
+                      float* desc_host, int32_t* counts_host);
+
+/* Replaces NearestNeighbor._forward (hloc/matchers/nearest_neighbor.py:38-57) and
+ * Matcher.mutual_nn_matcher (it_loc/matcher.py:122-130).
+ *   d0 float32 [n0, d] row-major, d1 float32 [n1, d]   (d = 128)
+ *   matches0 int32 [n0]  index into d1 or -1
+ *   sim0     float32 [n0] raw max cosine of every row (callers map to (s+1)/2)  */
+SFD2_API int sfd2_match_dev(sfd2_ctx* ctx, const float* d0_dev, int n0, const float* d1_dev, int n1, int d,
+                   const sfd2_match_params* p, int32_t* matches0_dev, float* sim0_dev, void* stream);
+SFD2_API int sfd2_match_host(sfd2_ctx* ctx, const float* d0_host, int n0, const float* d1_host, int n1, int d,
+                    const sfd2_match_params* p, int32_t* matches0_host, float* sim0_host);
+/* Many independent pairs in one call (hloc/match_features.py:90 pair loop;
+ * it_loc/localize_cv2.py:705 one query against <= 50 db images).  Pair i uses rows
+ * [off0[i], off0[i+1]) of d0 and [off1[i], off1[i+1]) of d1; outputs are indexed
+ * like d0 and matches are relative to off1[i].  Offsets are HOST arrays. */
+SFD2_API int sfd2_match_batched_dev(sfd2_ctx* ctx, const float* d0_dev, const int32_t* off0_host,
+                           const float* d1_dev, const int32_t* off1_host, int npairs, int d,
+                           const sfd2_match_params* p, int32_t* matches0_dev, float* sim0_dev,
+                           void* stream);
+
+/* Test / profiling hooks (not part of the reference surface). */
+/* Copy an intermediate of the LAST extracted image to host as float32:
+ * "heat" [h,w], "nms" [h,w], "score" [h8*8? see DESIGN.md], "desc_map" [h4,w4,128],
+ * "sta_logits" [h4,w4,3], "out4" [h4,w4,256], "conv1a".."conv3b" NHWC.  Returns the
+ * number of floats written or a negative status. */
+SFD2_API long long sfd2_debug_fetch(sfd2_ctx* ctx, const char* name, float* out_host, long long capacity);
+/* Number of kernels this library launched on behalf of ctx since creation. */
+SFD2_API long long sfd2_launch_count(sfd2_ctx* ctx);
+/* Standalone NMS + selection on a caller-supplied heat-map (device fp32 [h,w]):
+ * the part of the path that is compare-only and therefore bit-exact. */
+SFD2_API int sfd2_nms_select_dev(sfd2_ctx* ctx, const float* heat_dev, int h, int w,
+                        const sfd2_extract_params* p, float* kpts_dev, float* scores_dev,
+                        int32_t* count_dev, float* nms_out_dev /* may be NULL */, void* stream);
+/* Standalone conv layer on tcgen05 for unit tests: see sfd2_b200/csrc/api.cu. */
+SFD2_API int sfd2_debug_conv(sfd2_ctx* ctx, const float* x_host, int h, int w, int cin, const float* w_host,
+                    const float* b_host, int cout, int ksize, int stride, int groups, int relu,
+                    int precision, float* y_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFD2_B200_H */

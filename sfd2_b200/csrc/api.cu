@@ -1,0 +1,584 @@
+// C ABI of libsfd2_b200.so (see include/sfd2_b200.h): context, weight blob parsing, workspace
+// management and the per-image kernel schedule of the extract path, plus the matcher entry points.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+
+#include "common.cuh"
+
+namespace sfd2 {
+
+static thread_local char g_err[1024] = "";
+thread_local long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+}  // namespace sfd2
+
+using namespace sfd2;
+
+// ---- weight blob (written by sfd2_b200/weights.py) -------------------------------------------
+//   char magic[8] = "SFD2W001"; uint32 n_layers; uint32 reserved;
+//   n_layers x { char name[16]; int32 cin, cout, k, stride, groups, relu; uint64 w_off, b_off; }
+//   float data (offsets in bytes from the start of the blob; weights OIHW, BN already folded)
+#pragma pack(push, 1)
+struct BlobLayer {
+  char name[16];
+  int32_t cin, cout, k, stride, groups, relu;
+  uint64_t w_off, b_off;
+};
+#pragma pack(pop)
+
+enum ActId { A1A, A1B, A2A, A2B, A3A, A3B, T1, T2, BA, BB, PA, DA, NUM_ACTS };
+
+struct sfd2_ctx {
+  int device = 0, num_sms = 148;
+  std::vector<Layer> layers;
+  std::map<std::string, int> lidx;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  // extract workspace (sized for one image of wsH x wsW)
+  int wsH = 0, wsW = 0;
+  bool have_f32 = false, have_tc = false;
+  Act acts[NUM_ACTS];
+  CUtensorMap maps[NUM_ACTS][4];
+  int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
+  float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
+  unsigned long long *cand = nullptr, *scratch = nullptr;
+  int cap = 0;
+  int *counter = nullptr, *status = nullptr;
+  int debug_flags = 0;
+  int last_prec = -1;
+  // host-API staging
+  void* img_dev = nullptr; size_t img_cap = 0;
+  float *kp_dev = nullptr, *sc_dev = nullptr, *de_dev = nullptr; int32_t* cnt_dev = nullptr; size_t out_cap = 0;
+  // matcher workspace
+  unsigned long long *row_key = nullptr, *col_key = nullptr; size_t key_cap = 0;
+  __half* mhalf = nullptr; size_t mhalf_cap = 0;
+  float *m_d0 = nullptr, *m_d1 = nullptr; size_t m_d0_cap = 0, m_d1_cap = 0;
+  int32_t* m_out = nullptr; float* m_sim = nullptr; size_t m_out_cap = 0;
+  long long launches = 0;
+
+  const Layer& L(const char* n) const { return layers[lidx.at(n)]; }
+};
+
+static const char* kLayerNames[] = {"conv1a", "conv1b", "conv2a", "conv2b", "conv3a", "conv3b", "rb0c1", "rb0c2",
+                                    "rb0c3", "rb1c1", "rb1c2", "rb1c3", "rb2c1", "rb2c2", "rb2c3", "convPa0",
+                                    "headP", "convDa0", "headD", "sta"};
+
+static int upload_simt(Layer& L) {
+  const int taps = L.k * L.k, cpg = L.cin / L.groups;
+  const int cp = round_up(L.cout, 64);
+  L.cout_pad = cp;
+  std::vector<float> w((size_t)taps * cpg * cp, 0.f), b(cp < 128 ? 128 : cp, 0.f);
+  for (int o = 0; o < L.cout; ++o)
+    for (int r = 0; r < cpg; ++r)
+      for (int t = 0; t < taps; ++t) w[((size_t)t * cpg + r) * cp + o] = L.w[((size_t)o * cpg + r) * taps + t];
+  for (int o = 0; o < L.cout; ++o) b[o] = L.b[o];
+  SFD2_CUDA(cudaMalloc(&L.w_simt, w.size() * sizeof(float)));
+  SFD2_CUDA(cudaMalloc(&L.b_dev, b.size() * sizeof(float)));
+  SFD2_CUDA(cudaMemcpy(L.w_simt, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  SFD2_CUDA(cudaMemcpy(L.b_dev, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return SFD2_OK;
+}
+
+static void free_layer(Layer& L) {
+  cudaFree(L.w_simt); cudaFree(L.b_dev); cudaFree(L.w_hi); cudaFree(L.w_lo);
+  L.w_simt = L.b_dev = nullptr; L.w_hi = L.w_lo = nullptr;
+}
+
+static void free_workspace(sfd2_ctx* c) {
+  for (int i = 0; i < NUM_ACTS; ++i) {
+    cudaFree(c->acts[i].f32); cudaFree(c->acts[i].hi); cudaFree(c->acts[i].lo);
+    c->acts[i] = Act();
+  }
+  cudaFree(c->logits); cudaFree(c->semi); cudaFree(c->descmap); cudaFree(c->sta); cudaFree(c->heat); cudaFree(c->nmsdbg);
+  cudaFree(c->cand); cudaFree(c->scratch); cudaFree(c->counter); cudaFree(c->status);
+  c->logits = c->semi = c->descmap = c->sta = c->heat = c->nmsdbg = nullptr;
+  c->cand = c->scratch = nullptr; c->counter = c->status = nullptr;
+  c->wsH = c->wsW = 0; c->have_f32 = c->have_tc = false;
+}
+
+static int ensure_workspace(sfd2_ctx* c, int H, int W, int prec) {
+  if (c->wsH != H || c->wsW != W) {
+    free_workspace(c);
+    c->wsH = H; c->wsW = W;
+    c->H2 = conv_out(H, 2); c->W2 = conv_out(W, 2);
+    c->H4 = conv_out(c->H2, 2); c->W4 = conv_out(c->W2, 2);
+    c->H8 = conv_out(c->H4, 2); c->W8 = conv_out(c->W4, 2);
+    const int dims[NUM_ACTS][3] = {{H, W, 64}, {c->H2, c->W2, 64}, {c->H2, c->W2, 128}, {c->H4, c->W4, 128},
+                                   {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H4, c->W4, 256},
+                                   {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H8, c->W8, 256}, {c->H4, c->W4, 256}};
+    for (int i = 0; i < NUM_ACTS; ++i) {
+      Act& a = c->acts[i];
+      a.H = dims[i][0]; a.W = dims[i][1]; a.C = dims[i][2];
+      a.Hp = round_up(a.H, 2); a.Wp = round_up(a.W, 2);
+    }
+    const size_t n8 = (size_t)c->H8 * c->W8, n4 = (size_t)c->H4 * c->W4;
+    SFD2_CUDA(cudaMalloc(&c->logits, n8 * 80 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->semi, n8 * 64 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->descmap, n4 * 128 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->sta, n4 * 3 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->heat, (size_t)H * W * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->nmsdbg, (size_t)H * W * sizeof(float)));
+    // NMS survivors are >= 5 px apart except on exact plateaus: H*W/16 leaves 1.5x headroom.
+    c->cap = (int)(((size_t)H * W) / 16) + 4096;
+    int cap2 = 1;
+    while (cap2 < c->cap) cap2 <<= 1;
+    SFD2_CUDA(cudaMalloc(&c->cand, (size_t)c->cap * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->scratch, (size_t)cap2 * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->counter, sizeof(int)));
+    SFD2_CUDA(cudaMalloc(&c->status, sizeof(int)));
+    SFD2_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+  }
+  const bool want_tc = (prec != SFD2_PREC_FP32);
+  if (!want_tc && !c->have_f32) {
+    for (int i = 0; i < NUM_ACTS; ++i) {
+      Act& a = c->acts[i];
+      SFD2_CUDA(cudaMalloc(&a.f32, a.elems() * sizeof(float)));
+      SFD2_CUDA(cudaMemset(a.f32, 0, a.elems() * sizeof(float)));
+    }
+    c->have_f32 = true;
+  }
+  if (want_tc && !c->have_tc) {
+    for (int i = 0; i < NUM_ACTS; ++i) {
+      Act& a = c->acts[i];
+      SFD2_CUDA(cudaMalloc(&a.hi, a.elems() * sizeof(__half)));
+      SFD2_CUDA(cudaMalloc(&a.lo, a.elems() * sizeof(__half)));
+      SFD2_CUDA(cudaMemset(a.hi, 0, a.elems() * sizeof(__half)));
+      SFD2_CUDA(cudaMemset(a.lo, 0, a.elems() * sizeof(__half)));
+      int rc = tc_make_act_maps(a, a.hi, &c->maps[i][0], &c->maps[i][2]);
+      if (rc) return rc;
+      rc = tc_make_act_maps(a, a.lo, &c->maps[i][1], &c->maps[i][3]);
+      if (rc) return rc;
+      a.tm = c->maps[i];
+    }
+    c->have_tc = true;
+  }
+  return SFD2_OK;
+}
+
+// one image through network + post-processing, all on `st`
+static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W, const sfd2_extract_params* p,
+                       float* kpts, float* scores, float* desc, int32_t* count, cudaStream_t st) {
+  const int prec = p->precision;
+  const bool tc = prec != SFD2_PREC_FP32;
+  const int split = (prec == SFD2_PREC_TC_EXACT) ? 3 : 1;
+  Act* A = c->acts;
+  int rc;
+#define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
+  RUN(launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, st));
+  auto conv = [&](const char* name, int in, int out, int res) -> int {
+    const Layer& L = c->L(name);
+    if (tc) return launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, split, c->num_sms, st);
+    return launch_conv_simt(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, st);
+  };
+  RUN(conv("conv1b", A1A, A1B, -1));
+  RUN(conv("conv2a", A1B, A2A, -1));
+  RUN(conv("conv2b", A2A, A2B, -1));
+  RUN(conv("conv3a", A2B, A3A, -1));
+  RUN(conv("conv3b", A3A, A3B, -1));
+  RUN(conv("rb0c1", A3B, T1, -1)); RUN(conv("rb0c2", T1, T2, -1)); RUN(conv("rb0c3", T2, BA, A3B));
+  RUN(conv("rb1c1", BA, T1, -1));  RUN(conv("rb1c2", T1, T2, -1)); RUN(conv("rb1c3", T2, BB, BA));
+  RUN(conv("rb2c1", BB, T1, -1));  RUN(conv("rb2c2", T1, T2, -1)); RUN(conv("rb2c3", T2, BA, BB));
+  RUN(conv("convPa0", BA, PA, -1));
+  RUN(conv("convDa0", BA, DA, -1));
+  // heads: fp32 outputs
+  Act logit_act; logit_act.f32 = c->logits; logit_act.H = c->H8; logit_act.W = c->W8; logit_act.Wp = c->W8; logit_act.Hp = c->H8; logit_act.C = 80;
+  Act desc_act;  desc_act.f32 = c->descmap; desc_act.H = c->H4; desc_act.W = c->W4; desc_act.Wp = c->W4; desc_act.Hp = c->H4; desc_act.C = 128;
+  if (tc) {
+    RUN(launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, c->logits, split, c->num_sms, st));
+    RUN(launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, c->descmap, split, c->num_sms, st));
+  } else {
+    RUN(launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
+    RUN(launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
+  }
+  RUN(launch_softmax65(c->logits, c->H8 * c->W8, c->semi, st));
+  RUN(launch_l2norm128(c->descmap, c->H4 * c->W4, st));
+  if (p->use_stability) RUN(launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), c->sta, st));
+  RUN(launch_heat(c->semi, c->H8, c->W8, c->sta, c->H4, c->W4, p->use_stability, c->heat, H, W, st));
+  RUN(launch_nms(c->heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? c->nmsdbg : nullptr, c->cand, c->cap,
+                 c->counter, st));
+  RUN(launch_select(c->cand, c->cap, c->counter, W, p->topk, kpts, scores, count, c->status, c->scratch, st));
+  RUN(launch_sample(c->descmap, c->H4, c->W4, H, W, kpts, count, p->topk, desc, st));
+#undef RUN
+  return SFD2_OK;
+}
+
+static int check_params(const sfd2_extract_params* p, int n, int h, int w) {
+  SFD2_CHECK(p != nullptr, SFD2_ERR_ARG, "params is NULL");
+  SFD2_CHECK(n >= 1 && h >= 16 && w >= 16, SFD2_ERR_ARG, "bad image batch %d x %d x %d (min 16x16)", n, h, w);
+  SFD2_CHECK(p->nms_radius == 4, SFD2_ERR_ARG, "only nms_radius == 4 is implemented (got %d)", p->nms_radius);
+  SFD2_CHECK(p->topk >= 1, SFD2_ERR_ARG, "topk must be >= 1 (capacity of the output buffers)");
+  SFD2_CHECK(p->precision >= 0 && p->precision <= 2, SFD2_ERR_ARG, "bad precision %d", p->precision);
+  SFD2_CHECK(p->border >= 0, SFD2_ERR_ARG, "bad border");
+  return SFD2_OK;
+}
+
+extern "C" {
+
+SFD2_API int sfd2_abi_version(void) { return SFD2_ABI_VERSION; }
+SFD2_API const char* sfd2_last_error(void) { return g_err; }
+
+SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx** out) {
+  SFD2_CHECK(blob && out, SFD2_ERR_ARG, "sfd2_create: NULL argument");
+  *out = nullptr;
+  SFD2_CHECK(nbytes >= 16 && memcmp(blob, "SFD2W001", 8) == 0, SFD2_ERR_WEIGHTS, "bad weight blob magic");
+  const uint8_t* base = static_cast<const uint8_t*>(blob);
+  uint32_t nl;
+  memcpy(&nl, base + 8, 4);
+  SFD2_CHECK(nl > 0 && nl < 64 && 16 + (size_t)nl * sizeof(BlobLayer) <= nbytes, SFD2_ERR_WEIGHTS, "bad layer count %u", nl);
+  SFD2_CUDA(cudaSetDevice(device));
+  sfd2_ctx* c = new sfd2_ctx();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; set_error("cudaGetDeviceProperties failed"); return SFD2_ERR_CUDA; }
+  c->num_sms = prop.multiProcessorCount;
+  if (prop.major != 10) { delete c; set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return SFD2_ERR_CUDA; }
+  for (uint32_t i = 0; i < nl; ++i) {
+    BlobLayer bl;
+    memcpy(&bl, base + 16 + (size_t)i * sizeof(BlobLayer), sizeof(BlobLayer));
+    Layer L;
+    L.name = std::string(bl.name, strnlen(bl.name, 16));
+    L.cin = bl.cin; L.cout = bl.cout; L.k = bl.k; L.stride = bl.stride; L.groups = bl.groups; L.relu = bl.relu;
+    const size_t wn = (size_t)L.cout * (L.cin / (L.groups > 0 ? L.groups : 1)) * L.k * L.k;
+    if (L.groups < 1 || bl.w_off + wn * 4 > nbytes || bl.b_off + (size_t)L.cout * 4 > nbytes) {
+      delete c; set_error("layer %s out of blob bounds", L.name.c_str()); return SFD2_ERR_WEIGHTS;
+    }
+    L.w.resize(wn); L.b.resize(L.cout);
+    memcpy(L.w.data(), base + bl.w_off, wn * 4);
+    memcpy(L.b.data(), base + bl.b_off, (size_t)L.cout * 4);
+    c->lidx[L.name] = (int)c->layers.size();
+    c->layers.push_back(std::move(L));
+  }
+  for (const char* n : kLayerNames)
+    if (!c->lidx.count(n)) { delete c; set_error("weight blob lacks layer %s", n); return SFD2_ERR_WEIGHTS; }
+  for (Layer& L : c->layers) {
+    int rc = upload_simt(L);
+    if (!rc && L.cin % 64 == 0 && L.cout > 3) rc = tc_encode_weights(L);
+    if (rc) { sfd2_destroy(c); return rc; }
+  }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { sfd2_destroy(c); set_error("stream create failed"); return SFD2_ERR_CUDA; }
+  *out = c;
+  return SFD2_OK;
+}
+
+SFD2_API int sfd2_destroy(sfd2_ctx* c) {
+  if (!c) return SFD2_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_workspace(c);
+  for (Layer& L : c->layers) free_layer(L);
+  cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
+  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
+  cudaFree(c->m_out); cudaFree(c->m_sim);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SFD2_OK;
+}
+
+SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
+                     float* kpts, float* scores, float* desc, int32_t* counts, void* stream) {
+  SFD2_CHECK(c && img && kpts && scores && desc && counts, SFD2_ERR_ARG, "sfd2_extract_dev: NULL argument");
+  int rc = check_params(p, n, h, w);
+  if (rc) return rc;
+  SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "bad image dtype %d", img_dtype);
+  SFD2_CUDA(cudaSetDevice(c->device));
+  rc = ensure_workspace(c, h, w, p->precision);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t img_stride = (size_t)h * w * 3 * (img_dtype == SFD2_IMG_F32_NCHW ? 4 : 1);
+  const long long before = g_launches;
+  for (int i = 0; i < n; ++i) {
+    rc = extract_one(c, static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
+                     kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
+                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, st);
+    if (rc) return rc;
+  }
+  c->launches += g_launches - before;
+  c->last_prec = p->precision;
+  return SFD2_OK;
+}
+
+SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
+                      float* kpts, float* scores, float* desc, int32_t* counts) {
+  SFD2_CHECK(c && img && kpts && scores && desc && counts, SFD2_ERR_ARG, "sfd2_extract_host: NULL argument");
+  int rc = check_params(p, n, h, w);
+  if (rc) return rc;
+  SFD2_CUDA(cudaSetDevice(c->device));
+  const size_t img_bytes = (size_t)n * h * w * 3 * (img_dtype == SFD2_IMG_F32_NCHW ? 4 : 1);
+  if (img_bytes > c->img_cap) {
+    cudaFree(c->img_dev); c->img_dev = nullptr; c->img_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->img_dev, img_bytes));
+    c->img_cap = img_bytes;
+  }
+  const size_t rows = (size_t)n * p->topk;
+  if (rows > c->out_cap) {
+    cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
+    c->kp_dev = c->sc_dev = c->de_dev = nullptr; c->cnt_dev = nullptr; c->out_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->kp_dev, rows * 2 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->sc_dev, rows * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->de_dev, rows * SFD2_DESC_DIM * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&c->cnt_dev, (rows + 1) * sizeof(int32_t)));
+    c->out_cap = rows;
+  }
+  cudaStream_t st = c->stream;
+  SFD2_CUDA(cudaMemcpyAsync(c->img_dev, img, img_bytes, cudaMemcpyHostToDevice, st));
+  SFD2_CUDA(cudaMemsetAsync(c->kp_dev, 0, rows * 2 * sizeof(float), st));
+  SFD2_CUDA(cudaMemsetAsync(c->sc_dev, 0, rows * sizeof(float), st));
+  rc = sfd2_extract_dev(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st);
+  if (rc) return rc;
+  SFD2_CUDA(cudaMemcpyAsync(kpts, c->kp_dev, rows * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaMemcpyAsync(scores, c->sc_dev, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaMemcpyAsync(desc, c->de_dev, rows * SFD2_DESC_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaMemcpyAsync(counts, c->cnt_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  int status = 0;
+  SFD2_CUDA(cudaMemcpyAsync(&status, c->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaStreamSynchronize(st));
+  if (status != 0) {
+    cudaMemset(c->status, 0, sizeof(int));
+    set_error("NMS produced more candidates than the workspace holds (cap %d); results truncated", c->cap);
+    return SFD2_ERR_OVERFLOW;
+  }
+  return SFD2_OK;
+}
+
+static int ensure_match_ws(sfd2_ctx* c, int n0, int n1) {
+  const size_t need = (size_t)(n0 > n1 ? n0 : n1) + 128;
+  if (need > c->key_cap) {
+    cudaFree(c->row_key); cudaFree(c->col_key); c->row_key = c->col_key = nullptr; c->key_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->row_key, need * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->col_key, need * sizeof(unsigned long long)));
+    c->key_cap = need;
+  }
+  const size_t hneed = 2 * ((size_t)round_up(n0 > 0 ? n0 : 1, 128) + round_up(n1 > 0 ? n1 : 1, 128)) * 128;
+  if (hneed > c->mhalf_cap) {
+    cudaFree(c->mhalf); c->mhalf = nullptr; c->mhalf_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->mhalf, hneed * sizeof(__half)));
+    c->mhalf_cap = hneed;
+  }
+  return SFD2_OK;
+}
+
+static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
+                     int32_t* matches0, float* sim0, cudaStream_t st) {
+  int rc;
+  if (p->precision == SFD2_PREC_FP32)
+    rc = launch_match_simt(d0, n0, d1, n1, d, c->row_key, c->col_key, st);
+  else
+    rc = launch_match_tc(d0, n0, d1, n1, d, p->precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->mhalf, c->row_key,
+                         c->col_key, c->num_sms, st);
+  if (rc) return rc;
+  return launch_match_finish(c->row_key, c->col_key, n0, n1, p->do_mutual_check, p->distance_threshold, matches0, sim0, st);
+}
+
+SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
+                   int32_t* matches0, float* sim0, void* stream) {
+  SFD2_CHECK(c && p && (n0 == 0 || (d0 && matches0 && sim0)) && (n1 == 0 || d1), SFD2_ERR_ARG, "sfd2_match_dev: NULL argument");
+  SFD2_CHECK(n0 >= 0 && n1 >= 0 && d >= 1, SFD2_ERR_ARG, "sfd2_match_dev: bad shape %d x %d x %d", n0, n1, d);
+  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio_threshold is not implemented yet");
+  SFD2_CHECK(p->precision >= 0 && p->precision <= 2, SFD2_ERR_ARG, "bad precision %d", p->precision);
+  SFD2_CUDA(cudaSetDevice(c->device));
+  int rc = ensure_match_ws(c, n0, n1);
+  if (rc) return rc;
+  const long long before = g_launches;
+  rc = match_one(c, d0, n0, d1, n1, d, p, matches0, sim0, static_cast<cudaStream_t>(stream));
+  c->launches += g_launches - before;
+  return rc;
+}
+
+SFD2_API int sfd2_match_batched_dev(sfd2_ctx* c, const float* d0, const int32_t* off0, const float* d1, const int32_t* off1,
+                           int npairs, int d, const sfd2_match_params* p, int32_t* matches0, float* sim0, void* stream) {
+  SFD2_CHECK(c && p && off0 && off1 && npairs >= 0, SFD2_ERR_ARG, "sfd2_match_batched_dev: bad argument");
+  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio_threshold is not implemented yet");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  int mx0 = 0, mx1 = 0;
+  for (int i = 0; i < npairs; ++i) {
+    SFD2_CHECK(off0[i + 1] >= off0[i] && off1[i + 1] >= off1[i], SFD2_ERR_ARG, "offsets must be non-decreasing");
+    mx0 = std::max(mx0, off0[i + 1] - off0[i]);
+    mx1 = std::max(mx1, off1[i + 1] - off1[i]);
+  }
+  int rc = ensure_match_ws(c, mx0, mx1);
+  if (rc) return rc;
+  const long long before = g_launches;
+  for (int i = 0; i < npairs && !rc; ++i)
+    rc = match_one(c, d0 + (size_t)off0[i] * d, off0[i + 1] - off0[i], d1 + (size_t)off1[i] * d, off1[i + 1] - off1[i],
+                   d, p, matches0 + off0[i], sim0 + off0[i], static_cast<cudaStream_t>(stream));
+  c->launches += g_launches - before;
+  return rc;
+}
+
+SFD2_API int sfd2_match_host(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
+                    int32_t* matches0, float* sim0) {
+  SFD2_CHECK(c && p, SFD2_ERR_ARG, "sfd2_match_host: NULL argument");
+  SFD2_CHECK(n0 >= 0 && n1 >= 0 && d >= 1, SFD2_ERR_ARG, "sfd2_match_host: bad shape");
+  if (n0 == 0) return SFD2_OK;
+  SFD2_CUDA(cudaSetDevice(c->device));
+  const size_t b0 = (size_t)n0 * d * sizeof(float), b1 = (size_t)(n1 > 0 ? n1 : 1) * d * sizeof(float);
+  if (b0 > c->m_d0_cap) { cudaFree(c->m_d0); c->m_d0 = nullptr; c->m_d0_cap = 0; SFD2_CUDA(cudaMalloc(&c->m_d0, b0)); c->m_d0_cap = b0; }
+  if (b1 > c->m_d1_cap) { cudaFree(c->m_d1); c->m_d1 = nullptr; c->m_d1_cap = 0; SFD2_CUDA(cudaMalloc(&c->m_d1, b1)); c->m_d1_cap = b1; }
+  if ((size_t)n0 > c->m_out_cap) {
+    cudaFree(c->m_out); cudaFree(c->m_sim); c->m_out = nullptr; c->m_sim = nullptr; c->m_out_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->m_out, (size_t)n0 * sizeof(int32_t)));
+    SFD2_CUDA(cudaMalloc(&c->m_sim, (size_t)n0 * sizeof(float)));
+    c->m_out_cap = n0;
+  }
+  cudaStream_t st = c->stream;
+  SFD2_CUDA(cudaMemcpyAsync(c->m_d0, d0, b0, cudaMemcpyHostToDevice, st));
+  if (n1 > 0) SFD2_CUDA(cudaMemcpyAsync(c->m_d1, d1, (size_t)n1 * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = sfd2_match_dev(c, c->m_d0, n0, c->m_d1, n1, d, p, c->m_out, c->m_sim, st);
+  if (rc) return rc;
+  SFD2_CUDA(cudaMemcpyAsync(matches0, c->m_out, (size_t)n0 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaMemcpyAsync(sim0, c->m_sim, (size_t)n0 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  SFD2_CUDA(cudaStreamSynchronize(st));
+  return SFD2_OK;
+}
+
+SFD2_API long long sfd2_launch_count(sfd2_ctx* c) { return c ? c->launches : -1; }
+
+SFD2_API int sfd2_nms_select_dev(sfd2_ctx* c, const float* heat, int h, int w, const sfd2_extract_params* p, float* kpts,
+                        float* scores, int32_t* count, float* nms_out, void* stream) {
+  SFD2_CHECK(c && heat && p && kpts && scores && count, SFD2_ERR_ARG, "sfd2_nms_select_dev: NULL argument");
+  SFD2_CHECK(h >= 1 && w >= 1 && p->topk >= 1 && p->nms_radius == 4, SFD2_ERR_ARG, "sfd2_nms_select_dev: bad argument");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  // private workspace sized for this map (the extract workspace may belong to another size)
+  const int cap = (int)(((size_t)h * w) / 16) + 4096;
+  int cap2 = 1;
+  while (cap2 < cap) cap2 <<= 1;
+  unsigned long long *cand = nullptr, *scratch = nullptr;
+  int *counter = nullptr, *status = nullptr;
+  SFD2_CUDA(cudaMalloc(&cand, (size_t)cap * 8));
+  SFD2_CUDA(cudaMalloc(&scratch, (size_t)cap2 * 8));
+  SFD2_CUDA(cudaMalloc(&counter, 4));
+  SFD2_CUDA(cudaMalloc(&status, 4));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SFD2_CUDA(cudaMemsetAsync(status, 0, 4, st));
+  const long long before = g_launches;
+  int rc = launch_nms(heat, h, w, p->conf_th, p->border, nms_out, cand, cap, counter, st);
+  if (!rc) rc = launch_select(cand, cap, counter, w, p->topk, kpts, scores, count, status, scratch, st);
+  c->launches += g_launches - before;
+  int hstatus = 0;
+  cudaMemcpyAsync(&hstatus, status, 4, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  cudaFree(cand); cudaFree(scratch); cudaFree(counter); cudaFree(status);
+  if (!rc && hstatus) { set_error("candidate overflow (cap %d)", cap); rc = SFD2_ERR_OVERFLOW; }
+  return rc;
+}
+
+// name -> intermediate of the last image.  Activations are returned as dense [H][W][C] fp32.
+SFD2_API long long sfd2_debug_fetch(sfd2_ctx* c, const char* name, float* out, long long capacity) {
+  if (!c || !name) { set_error("sfd2_debug_fetch: NULL argument"); return SFD2_ERR_ARG; }
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  const std::string n(name);
+  if (n == "enable_nms_out") { c->debug_flags |= 1; return 0; }
+  if (c->wsH == 0) { set_error("no image has been extracted yet"); return SFD2_ERR_ARG; }
+  const float* src = nullptr;
+  long long cnt = 0;
+  if (n == "heat") { src = c->heat; cnt = (long long)c->wsH * c->wsW; }
+  else if (n == "nms") { src = c->nmsdbg; cnt = (long long)c->wsH * c->wsW; }
+  else if (n == "semi") { src = c->semi; cnt = (long long)c->H8 * c->W8 * 64; }
+  else if (n == "logits") { src = c->logits; cnt = (long long)c->H8 * c->W8 * 80; }
+  else if (n == "desc_map") { src = c->descmap; cnt = (long long)c->H4 * c->W4 * 128; }
+  else if (n == "sta_logits") { src = c->sta; cnt = (long long)c->H4 * c->W4 * 3; }
+  if (src) {
+    if (cnt > capacity) { set_error("buffer too small: need %lld floats", cnt); return SFD2_ERR_ARG; }
+    if (cudaMemcpy(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return SFD2_ERR_CUDA; }
+    return cnt;
+  }
+  static const std::map<std::string, int> ids = {{"conv1a", A1A}, {"conv1b", A1B}, {"conv2a", A2A}, {"conv2b", A2B},
+                                                 {"conv3a", A3A}, {"conv3b", A3B}, {"t1", T1}, {"t2", T2},
+                                                 {"out4", BA}, {"rb1", BB}, {"convPa0", PA}, {"convDa0", DA}};
+  auto it = ids.find(n);
+  if (it == ids.end()) { set_error("unknown intermediate '%s'", name); return SFD2_ERR_ARG; }
+  const Act& a = c->acts[it->second];
+  cnt = (long long)a.H * a.W * a.C;
+  if (cnt > capacity) { set_error("buffer too small: need %lld floats", cnt); return SFD2_ERR_ARG; }
+  const bool tc = (c->last_prec != SFD2_PREC_FP32);
+  const size_t ne = a.elems();
+  if (!tc) {
+    std::vector<float> tmp(ne);
+    if (cudaMemcpy(tmp.data(), a.f32, ne * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return SFD2_ERR_CUDA; }
+    for (int y = 0; y < a.H; ++y)
+      memcpy(out + (size_t)y * a.W * a.C, tmp.data() + (size_t)y * a.Wp * a.C, (size_t)a.W * a.C * 4);
+  } else {
+    std::vector<__half> hi(ne), lo(ne);
+    if (cudaMemcpy(hi.data(), a.hi, ne * 2, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(lo.data(), a.lo, ne * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return SFD2_ERR_CUDA; }
+    const bool use_lo = (c->last_prec == SFD2_PREC_TC_EXACT);
+    for (int y = 0; y < a.H; ++y)
+      for (size_t i = 0; i < (size_t)a.W * a.C; ++i) {
+        const size_t s = (size_t)y * a.Wp * a.C + i;
+        out[(size_t)y * a.W * a.C + i] = __half2float(hi[s]) + (use_lo ? __half2float(lo[s]) : 0.f);
+      }
+  }
+  return cnt;
+}
+
+// One convolution layer in isolation (unit tests): x NHWC fp32 [h][w][cin] on the host, weights OIHW,
+// y NHWC fp32 [ho][wo][cout] on the host.  precision selects the CUDA-core or tcgen05 kernel.
+SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin, const float* wt, const float* bs, int cout,
+                    int ksize, int stride, int groups, int relu, int precision, float* y) {
+  SFD2_CHECK(c && x && wt && bs && y, SFD2_ERR_ARG, "sfd2_debug_conv: NULL argument");
+  SFD2_CHECK((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && (groups == 1 || groups == 32), SFD2_ERR_ARG, "sfd2_debug_conv: unsupported conv");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  Layer L;
+  L.name = "dbg"; L.cin = cin; L.cout = cout; L.k = ksize; L.stride = stride; L.groups = groups; L.relu = relu;
+  const size_t wn = (size_t)cout * (cin / groups) * ksize * ksize;
+  L.w.assign(wt, wt + wn); L.b.assign(bs, bs + cout);
+  int rc = upload_simt(L);
+  const bool tc = precision != SFD2_PREC_FP32;
+  if (!rc && tc) rc = tc_encode_weights(L);
+  Act in, out;
+  in.H = h; in.W = w; in.C = cin; in.Hp = round_up(h, 2); in.Wp = round_up(w, 2);
+  out.H = conv_out(h, stride); out.W = conv_out(w, stride); out.C = cout; out.Hp = round_up(out.H, 2); out.Wp = round_up(out.W, 2);
+  const int outC_f32 = round_up(cout, 16);
+  CUtensorMap maps[4];
+  float* yf = nullptr;
+  std::vector<float> xin(in.elems(), 0.f);
+  for (int yy = 0; yy < h; ++yy) memcpy(xin.data() + (size_t)yy * in.Wp * cin, x + (size_t)yy * w * cin, (size_t)w * cin * 4);
+  auto cleanup = [&]() { cudaFree(in.f32); cudaFree(in.hi); cudaFree(in.lo); cudaFree(out.f32); cudaFree(yf); free_layer(L); };
+#define DBG_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { set_error("%s -> %s", #call, cudaGetErrorString(e_)); cleanup(); return SFD2_ERR_CUDA; } } while (0)
+  if (rc) { cleanup(); return rc; }
+  const long long before = g_launches;
+  if (!tc) {
+    DBG_CUDA(cudaMalloc(&in.f32, in.elems() * 4));
+    DBG_CUDA(cudaMemcpy(in.f32, xin.data(), in.elems() * 4, cudaMemcpyHostToDevice));
+    out.Wp = out.W; out.Hp = out.H;
+    DBG_CUDA(cudaMalloc(&out.f32, out.elems() * 4));
+    rc = launch_conv_simt(in, L, out, nullptr, nullptr);
+    if (!rc) { DBG_CUDA(cudaDeviceSynchronize()); DBG_CUDA(cudaMemcpy(y, out.f32, out.elems() * 4, cudaMemcpyDeviceToHost)); }
+  } else {
+    std::vector<__half> hi(in.elems()), lo(in.elems());
+    for (size_t i = 0; i < in.elems(); ++i) { hi[i] = __float2half_rn(xin[i]); lo[i] = __float2half_rn(xin[i] - __half2float(hi[i])); }
+    DBG_CUDA(cudaMalloc(&in.hi, in.elems() * 2));
+    DBG_CUDA(cudaMalloc(&in.lo, in.elems() * 2));
+    DBG_CUDA(cudaMemcpy(in.hi, hi.data(), in.elems() * 2, cudaMemcpyHostToDevice));
+    DBG_CUDA(cudaMemcpy(in.lo, lo.data(), in.elems() * 2, cudaMemcpyHostToDevice));
+    rc = tc_make_act_maps(in, in.hi, &maps[0], &maps[2]);
+    if (!rc) rc = tc_make_act_maps(in, in.lo, &maps[1], &maps[3]);
+    in.tm = maps;
+    Act o2 = out; o2.Wp = out.W; o2.Hp = out.H; o2.C = outC_f32;
+    DBG_CUDA(cudaMalloc(&yf, o2.elems() * 4));
+    if (!rc) rc = launch_conv_tc(in, L, o2, nullptr, yf, precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->num_sms, nullptr);
+    if (!rc) {
+      DBG_CUDA(cudaDeviceSynchronize());
+      std::vector<float> tmp(o2.elems());
+      DBG_CUDA(cudaMemcpy(tmp.data(), yf, o2.elems() * 4, cudaMemcpyDeviceToHost));
+      for (size_t pix = 0; pix < (size_t)out.H * out.W; ++pix)
+        memcpy(y + pix * cout, tmp.data() + pix * outC_f32, (size_t)cout * 4);
+    }
+  }
+#undef DBG_CUDA
+  c->launches += g_launches - before;
+  cleanup();
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+// Mutual-NN matcher on tcgen05: sim = D0 * D1^T as a K-major x K-major GEMM (K = 128) whose
+// epilogue reduces every 128 x 128 accumulator tile straight into the per-row / per-column
+// arg-max keys of match.cu - the similarity matrix never exists in HBM.
+//
+// Operands are the fp16 hi/lo split of the fp32 descriptors (unit-norm rows, so hi+lo carries
+// ~22 bits): split==3 issues d0_hi*d1_hi + d0_hi*d1_lo + d0_lo*d1_hi into one fp32 accumulator,
+// which reproduces the fp32 reference arg-max on real SFD2 descriptors;
+// split==1 is the single-pass fp16 variant.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sfd2 {
+
+using namespace ptx;
+
+__device__ __forceinline__ unsigned m_ord_f32(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ unsigned long long m_key(float sim, int idx) {
+  return ((unsigned long long)m_ord_f32(sim) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
+}
+
+// fp32 rows [n][128] -> fp16 hi / lo rows [n_pad][128] (rows >= n are zero)
+__global__ void split_rows_kernel(const float* __restrict__ src, int n, int n_pad, __half* __restrict__ hi,
+                                  __half* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+  if (idx >= n_pad * 32) return;
+  const int r = idx >> 5;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < n) v = __ldg(reinterpret_cast<const float4*>(src) + idx);
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(x[j]);
+    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
+}
+
+constexpr int TM_TILE = 128;
+constexpr int TM_OP_BYTES = 128 * 128;  // 128 rows x 64 fp16
+constexpr int TM_THREADS = 192;
+constexpr int TM_MAX_STAGES = 6;
+
+struct TcMatchArgs {
+  int n0, n1, tiles_m, tiles_n, split, stages, stage_bytes;
+  unsigned long long* row_key;
+  unsigned long long* col_key;
+};
+
+__global__ void __launch_bounds__(TM_THREADS, 1)
+tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                const __grid_constant__ TcMatchArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* xpose = reinterpret_cast<float*>(smem + (size_t)a.stages * a.stage_bytes);  // 4 warps x 32 x 33 floats
+  uint64_t* full = reinterpret_cast<uint64_t*>(xpose + 4 * 32 * 33);
+  uint64_t* empty = full + TM_MAX_STAGES;
+  uint64_t* tfull = empty + TM_MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA_hi);
+    prefetch_tmap(&tmB_hi);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int num_tiles = a.tiles_m * a.tiles_n;
+  const int nops = (a.split == 3) ? 2 : 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int r0 = (tile / a.tiles_n) * TM_TILE, c0 = (tile % a.tiles_n) * TM_TILE;
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
+          uint8_t* sb = sa + nops * TM_OP_BYTES;
+          mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
+          tma_load_2d(sa, &tmA_hi, &full[stage], kb * 64, r0);
+          tma_load_2d(sb, &tmB_hi, &full[stage], kb * 64, c0);
+          if (a.split == 3) {
+            tma_load_2d(sa + TM_OP_BYTES, &tmA_lo, &full[stage], kb * 64, r0);
+            tma_load_2d(sb + TM_OP_BYTES, &tmB_lo, &full[stage], kb * 64, c0);
+          }
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(128, 128);
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, bphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
+          const uint32_t sb = sa + nops * TM_OP_BYTES;
+          const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
+          const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + TM_OP_BYTES);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+#pragma unroll 1
+          for (int pass = 0; pass < a.split; ++pass) {
+            const uint64_t da = (pass == 2) ? da_lo : da_hi;
+            const uint64_t db = (pass == 1) ? db_lo : db_hi;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(dcol, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb == 0 && pass == 0 && k == 0) ? 0u : 1u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+        if (++buf == 2) { buf = 0; bphase ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* xp = xpose + q * 32 * 33;
+    int buf = 0;
+    uint32_t bphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int r0 = (tile / a.tiles_n) * TM_TILE, c0 = (tile % a.tiles_n) * TM_TILE;
+      const int i = r0 + q * 32 + lane;
+      mbar_wait(&tfull[buf], bphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+      unsigned long long rbest = 0ull;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        const int jbase = c0 + ch * 32;
+        // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (jbase + j < a.n1) {
+            const unsigned long long k = m_key(__uint_as_float(v[j]), jbase + j);
+            rbest = (k > rbest) ? k : rbest;
+          }
+        }
+        // column arg-max over this warp's 32 rows: transpose through smem, one column per lane
+#pragma unroll
+        for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int rows_valid = min(32, a.n0 - (r0 + q * 32));
+        float best = 0.f;
+        int besti = -1;
+        for (int r = 0; r < rows_valid; ++r) {
+          const float s = xp[r * 33 + lane];
+          if (besti < 0 || s > best) { best = s; besti = r; }
+        }
+        __syncwarp();
+        if (besti >= 0 && jbase + lane < a.n1) atomicMax(a.col_key + jbase + lane, m_key(best, r0 + q * 32 + besti));
+      }
+      if (i < a.n0 && rbest) atomicMax(a.row_key + i, rbest);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (++buf == 2) { buf = 0; bphase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ws_half must hold 2 * (n0_pad + n1_pad) * 128 halves (n*_pad = n* rounded up to 128)
+int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int split, __half* ws_half,
+                    unsigned long long* row_key, unsigned long long* col_key, int num_sms, cudaStream_t st) {
+  SFD2_CHECK(d == 128, SFD2_ERR_ARG, "match_tc: descriptor dim must be 128 (got %d)", d);
+  SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)(n0 > 0 ? n0 : 1), st));
+  SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)(n1 > 0 ? n1 : 1), st));
+  if (n0 <= 0 || n1 <= 0) return SFD2_OK;
+  const int n0p = round_up(n0, TM_TILE), n1p = round_up(n1, TM_TILE);
+  __half* a_hi = ws_half;
+  __half* a_lo = a_hi + (size_t)n0p * 128;
+  __half* b_hi = a_lo + (size_t)n0p * 128;
+  __half* b_lo = b_hi + (size_t)n1p * 128;
+  split_rows_kernel<<<cdiv(n0p * 32, 256), 256, 0, st>>>(d0, n0, n0p, a_hi, a_lo);
+  split_rows_kernel<<<cdiv(n1p * 32, 256), 256, 0, st>>>(d1, n1, n1p, b_hi, b_lo);
+  g_launches += 2;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
+  const uint64_t strides[1] = {256};
+  {
+    const uint64_t dims[2] = {128, (uint64_t)n0p};
+    int rc = make_tmap_f16(&tA_hi, a_hi, 2, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_f16(&tA_lo, a_lo, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[2] = {128, (uint64_t)n1p};
+    int rc = make_tmap_f16(&tB_hi, b_hi, 2, dims, strides, box);
+    if (rc) return rc;
+    rc = make_tmap_f16(&tB_lo, b_lo, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  TcMatchArgs a{};
+  a.n0 = n0; a.n1 = n1; a.tiles_m = n0p / TM_TILE; a.tiles_n = n1p / TM_TILE; a.split = split;
+  a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
+  a.stages = (split == 3) ? 3 : 6;
+  a.row_key = row_key; a.col_key = col_key;
+  const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = a.tiles_m * a.tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+  ++g_launches;
+  SFD2_CUDA(cudaGetLastError());
+  return SFD2_OK;
+}
+
+}  // namespace sfd2

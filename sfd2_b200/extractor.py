@@ -1,0 +1,188 @@
+"""Drop-ins for the reference's extraction interface (same names, arguments, outputs):
+
+  get_model(model_name, weight_path, use_stability)  <- extract_localization.py:208-218
+  extract_resnet_return(model, img, conf_th, mask, topK, scales=...)  <- nets/extractor.py:97-337
+  ResSegNetV2(outdim, require_stability)  <- nets/sfd2.py:259 (inference surface only)
+
+The network, NMS / top-K and descriptor sampling all run in libsfd2_b200.so; this
+module only marshals arguments and packs the float64 numpy dict the hloc / it_loc
+scripts expect.  No compute happens in Python and there is no CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .weights import blob_from_checkpoint, fold_layers, pack_blob
+
+__all__ = ["ResSegNetV2", "get_model", "extract_resnet_return", "Extractor"]
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class ResSegNetV2(torch.nn.Module):
+    """Stands where nets.sfd2.ResSegNetV2 stands in the extraction scripts: accepts
+    .eval(), .cuda(), .load_state_dict(ckpt['model'], strict=False); the forward
+    pass itself lives on the device inside the native context.
+
+    precision: 'exact' (tcgen05 fp16x3 split, parity default), 'fast' (tcgen05
+    fp16x1) or 'fp32' (CUDA-core reference mode)."""
+
+    def __init__(self, outdim=128, require_feature=False, require_stability=False, ms_detector=True,
+                 precision="exact"):
+        super().__init__()
+        if outdim != 128:
+            raise ValueError("only outdim=128 is supported (the shipped checkpoint)")
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {list(_lib.PREC)}")
+        self.outdim = outdim
+        self.require_stability = bool(require_stability)
+        self.precision = precision
+        self._blob = None
+        self._ctx = None
+
+    # -- weights -------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=False):
+        sd = {k: (v.detach().cpu().double().numpy() if torch.is_tensor(v) else np.asarray(v, np.float64))
+              for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
+        self._blob = pack_blob(fold_layers(sd))
+        self._ctx = None
+        return "<All keys matched successfully>"
+
+    def load_checkpoint(self, path):
+        self._blob = blob_from_checkpoint(path)
+        self._ctx = None
+        return self
+
+    # -- device --------------------------------------------------------------------------
+    def cuda(self, device=None):
+        if self._blob is None:
+            raise _lib.Sfd2Error("load weights before .cuda()")
+        if not torch.cuda.is_available():
+            raise _lib.Sfd2Error("no CUDA device: sfd2_b200 has no CPU path")
+        dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        if self._ctx is None or self._ctx.device != dev:
+            self._ctx = _lib.Context(self._blob, dev)
+        return self
+
+    def to(self, device=None, *a, **k):
+        if device is not None and torch.device(device).type == "cuda":
+            return self.cuda(device)
+        return self
+
+    @property
+    def ctx(self) -> "_lib.Context":
+        if self._ctx is None:
+            self.cuda()
+        return self._ctx
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("training forward is out of scope; use extract_resnet_return / Extractor")
+
+    # -- test hook -----------------------------------------------------------------------
+    def debug_fetch(self, name: str, shape) -> np.ndarray:
+        out = np.empty(int(np.prod(shape)), np.float32)
+        n = _lib.lib().sfd2_debug_fetch(self.ctx.handle, name.encode(), _np_ptr(out), out.size)
+        if n < 0:
+            _lib.check(int(n), f"sfd2_debug_fetch({name})")
+        return out[:n].reshape(shape)
+
+
+def get_model(model_name, weight_path, use_stability=False, precision="exact"):
+    """extract_localization.get_model: -> (model, extractor)."""
+    if model_name != "ressegnetv2":
+        raise ValueError(f"model '{model_name}' is outside the hot path (only 'ressegnetv2')")
+    model = ResSegNetV2(outdim=128, require_stability=use_stability, precision=precision).eval()
+    model.load_checkpoint(weight_path)
+    return model, extract_resnet_return
+
+
+def _params(model, conf_th, topk, border=4):
+    return _lib.ExtractParams(conf_th=float(conf_th), nms_radius=4, border=border, topk=int(topk),
+                              precision=_lib.PREC[model.precision], use_stability=int(model.require_stability))
+
+
+def _pack(kp, sc, de, n):
+    return {"keypoints": np.array(kp[:n], dtype=float),
+            "descriptors": np.array(de[:n], dtype=float),
+            "scores": np.array(sc[:n], dtype=float)}
+
+
+def extract_resnet_return(model, img, conf_th=0.001, mask=None, topK=-1, **kwargs):
+    """nets/extractor.py:97: img float [1,3,H,W] (or [3,H,W]) RGB in [0,1], CPU or CUDA tensor.
+    Returns {"keypoints": f64[K,2] (x,y), "descriptors": f64[K,128], "scores": f64[K]},
+    score-descending (ties by pixel index).  0 keypoints -> empty arrays (the reference
+    crashes there)."""
+    if mask is not None:
+        raise NotImplementedError("the reference's mask/label branch is unreachable (labels undefined, :314)")
+    scales = list(kwargs.get("scales", [1.0]))
+    if scales != [1.0]:
+        raise NotImplementedError("multi-scale extraction is not implemented yet (all shipped presets use [1.0])")
+    img = torch.as_tensor(img)
+    if img.dtype != torch.float32:
+        img = img.float()
+    img = img.reshape(-1, *img.shape[-2:])
+    if img.shape[0] != 3:
+        raise ValueError(f"expected a 3-channel image, got {tuple(img.shape)}")
+    H, W = int(img.shape[1]), int(img.shape[2])
+    ctx = model.ctx
+    cap = int(topK) if topK and topK > 0 else (H * W) // 16 + 4096
+    p = _params(model, conf_th, cap)
+    lib = _lib.lib()
+    if img.is_cuda:
+        img = img.contiguous()
+        dev = img.device
+        kp = torch.zeros(cap, 2, dtype=torch.float32, device=dev)
+        sc = torch.zeros(cap, dtype=torch.float32, device=dev)
+        de = torch.empty(cap, _lib.DESC_DIM, dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.sfd2_extract_dev(ctx.handle, img.data_ptr(), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
+                                        kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
+                   "sfd2_extract_dev")
+        n = int(cnt.item())
+        return _pack(kp.cpu().numpy(), sc.cpu().numpy(), de.cpu().numpy(), n)
+    a = np.ascontiguousarray(img.numpy())
+    kp = np.zeros((cap, 2), np.float32)
+    sc = np.zeros((cap,), np.float32)
+    de = np.zeros((cap, _lib.DESC_DIM), np.float32)
+    cnt = np.zeros((1,), np.int32)
+    _lib.check(lib.sfd2_extract_host(ctx.handle, _np_ptr(a), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
+                                     _np_ptr(kp), _np_ptr(sc), _np_ptr(de), _np_ptr(cnt)), "sfd2_extract_host")
+    return _pack(kp, sc, de, int(cnt[0]))
+
+
+class Extractor:
+    """Batched, device-resident front end for throughput work (bench / dataset sweeps):
+    images stay in HBM, outputs are fixed-capacity torch tensors plus counts."""
+
+    def __init__(self, weight_path, use_stability=True, precision="exact", topk=4096, conf_th=0.001, device=None):
+        self.model = ResSegNetV2(require_stability=use_stability, precision=precision).load_checkpoint(weight_path)
+        self.model.cuda(device)
+        self.topk, self.conf_th = int(topk), float(conf_th)
+
+    def __call__(self, images: torch.Tensor):
+        """images: CUDA float32 [n,3,H,W] in [0,1] or CUDA uint8 [n,H,W,3]."""
+        if not images.is_cuda:
+            raise ValueError("Extractor takes device-resident batches; use extract_resnet_return for host images")
+        images = images.contiguous()
+        if images.dtype == torch.uint8:
+            n, H, W, _ = images.shape
+            dt = _lib.IMG_U8_NHWC
+        else:
+            n, _, H, W = images.shape
+            dt = _lib.IMG_F32_NCHW
+        dev = images.device
+        kp = torch.zeros(n, self.topk, 2, dtype=torch.float32, device=dev)
+        sc = torch.zeros(n, self.topk, dtype=torch.float32, device=dev)
+        de = torch.empty(n, self.topk, _lib.DESC_DIM, dtype=torch.float32, device=dev)
+        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        p = _params(self.model, self.conf_th, self.topk)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(_lib.lib().sfd2_extract_dev(self.model.ctx.handle, images.data_ptr(), dt, n, H, W, C.byref(p),
+                                               kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
+                   "sfd2_extract_dev")
+        return {"keypoints": kp, "scores": sc, "descriptors": de, "counts": cnt}

@@ -1,0 +1,189 @@
+"""Drop-ins for the reference's two mutual-nearest-neighbour matchers:
+
+  NearestNeighbor  <- hloc/matchers/nearest_neighbor.py:27-57 (BaseModel plugin, torch in/out)
+  Matcher          <- it_loc/matcher.py:85-119 (numpy in/out, mode 'nnm')
+  BaseModel        <- hloc/utils/base_model.py:7-37 (so the plugin also works standalone)
+
+Both run the same native kernel (csrc/match.cu, csrc/tc_match.cu): similarity GEMM
+with the row / column arg-max fused into its epilogue, then the mutual check.
+"""
+import ctypes as C
+from copy import copy
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["BaseModel", "NearestNeighbor", "NearestNeighborMixin", "Matcher", "confs", "match_batched"]
+
+_BLOB = None
+_CTX = {}
+
+
+def _ctx(device_index: int) -> "_lib.Context":
+    """The matcher needs no network weights; it shares a context per device built from a
+    minimal (zero) weight blob so that workspace + stream management stay in one place."""
+    global _BLOB
+    if device_index not in _CTX:
+        if _BLOB is None:
+            from .weights import LAYER_ORDER, pack_blob
+            shapes = {"conv1a": (64, 3, 3, 1, 1), "conv1b": (64, 64, 3, 2, 1), "conv2a": (128, 64, 3, 1, 1),
+                      "conv2b": (128, 128, 3, 2, 1), "conv3a": (256, 128, 3, 1, 1), "conv3b": (256, 256, 3, 1, 1),
+                      "convPa0": (256, 256, 3, 2, 1), "headP": (65, 256, 3, 1, 1), "convDa0": (256, 256, 3, 1, 1),
+                      "headD": (128, 256, 3, 1, 1), "sta": (3, 256, 1, 1, 1)}
+            for i in range(3):
+                shapes[f"rb{i}c1"] = (256, 256, 1, 1, 1)
+                shapes[f"rb{i}c2"] = (256, 8, 3, 1, 32)
+                shapes[f"rb{i}c3"] = (256, 256, 1, 1, 1)
+            layers = {n: dict(w=np.zeros((shapes[n][0], shapes[n][1], shapes[n][2], shapes[n][2]), np.float32),
+                              b=np.zeros(shapes[n][0], np.float32), stride=shapes[n][3], groups=shapes[n][4], relu=0)
+                      for n in LAYER_ORDER}
+            _BLOB = pack_blob(layers)
+        _CTX[device_index] = _lib.Context(_BLOB, device_index)
+    return _CTX[device_index]
+
+
+def _mparams(mutual, dist_th, ratio_th, precision):
+    return _lib.MatchParams(do_mutual_check=int(bool(mutual)),
+                            distance_threshold=float(dist_th) if dist_th else 0.0,
+                            ratio_threshold=float(ratio_th) if ratio_th else 0.0,
+                            precision=_lib.PREC[precision])
+
+
+def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, ratio_th=None, precision="exact"):
+    """d0 [N,D], d1 [M,D] CUDA float32 row-major -> (matches0 int32 [N], sim0 float32 [N]) on the device."""
+    assert d0.is_cuda and d1.is_cuda and d0.dtype == torch.float32 and d1.dtype == torch.float32
+    d0, d1 = d0.contiguous(), d1.contiguous()
+    n0, d = d0.shape
+    n1 = d1.shape[0]
+    dev = d0.device
+    m0 = torch.full((n0,), -1, dtype=torch.int32, device=dev)
+    s0 = torch.zeros((n0,), dtype=torch.float32, device=dev)
+    if n0 == 0:
+        return m0, s0
+    p = _mparams(mutual, dist_th, ratio_th, precision)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().sfd2_match_dev(_ctx(dev.index or 0).handle, d0.data_ptr(), n0, d1.data_ptr(), n1, d,
+                                         C.byref(p), m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_dev")
+    return m0, s0
+
+
+def match_batched(d0: torch.Tensor, off0, d1: torch.Tensor, off1, mutual=True, dist_th=None, precision="exact"):
+    """Many pairs in one native call; off0/off1 are python/numpy int sequences of length npairs+1."""
+    d0, d1 = d0.contiguous(), d1.contiguous()
+    o0 = np.ascontiguousarray(off0, np.int32)
+    o1 = np.ascontiguousarray(off1, np.int32)
+    npairs = len(o0) - 1
+    dev = d0.device
+    m0 = torch.full((d0.shape[0],), -1, dtype=torch.int32, device=dev)
+    s0 = torch.zeros((d0.shape[0],), dtype=torch.float32, device=dev)
+    p = _mparams(mutual, dist_th, None, precision)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().sfd2_match_batched_dev(_ctx(dev.index or 0).handle, d0.data_ptr(),
+                                                 o0.ctypes.data_as(C.c_void_p), d1.data_ptr(),
+                                                 o1.ctypes.data_as(C.c_void_p), npairs, d0.shape[1], C.byref(p),
+                                                 m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_batched_dev")
+    return m0, s0
+
+
+class BaseModel(torch.nn.Module):
+    """hloc/utils/base_model.py:7-37 (same contract: default_conf merge, _init, forward -> _forward)."""
+    default_conf = {}
+    required_data_keys = []
+
+    def __init__(self, conf):
+        super().__init__()
+        self.conf = conf = {**self.default_conf, **conf}
+        self.required_data_keys = copy(self.required_data_keys)
+        self._init(conf)
+
+    def forward(self, data):
+        for key in self.required_data_keys:
+            assert key in data, "Missing key {} in data".format(key)
+        return self._forward(data)
+
+    def _init(self, conf):
+        raise NotImplementedError
+
+    def _forward(self, data):
+        raise NotImplementedError
+
+
+class NearestNeighborMixin:
+    """The plugin body, independent of which BaseModel it is mixed with - so a reference
+    checkout can define `class NearestNeighbor(NearestNeighborMixin, BaseModel)` inside
+    hloc/matchers/<name>.py and dynamic_load (base_model.py:40-50) will pick it up."""
+    default_conf = {
+        "ratio_threshold": None,
+        "distance_threshold": None,
+        "do_mutual_check": True,
+        "precision": "exact",
+    }
+    required_inputs = ["descriptors0", "descriptors1"]
+
+    def _init(self, conf):
+        if conf.get("ratio_threshold"):
+            raise NotImplementedError("ratio_threshold needs top-2 in the epilogue: not implemented yet")
+
+    def _forward(self, data):
+        d0, d1 = data["descriptors0"], data["descriptors1"]      # [B, D, N], [B, D, M]
+        if not d0.is_cuda:
+            raise _lib.Sfd2Error("NearestNeighbor: descriptors must be CUDA tensors (no CPU path)")
+        B = d0.shape[0]
+        ms, ss = [], []
+        for b in range(B):
+            a = d0[b].float().t().contiguous()
+            c = d1[b].float().t().contiguous()
+            m0, s0 = match_dev(a, c, self.conf["do_mutual_check"], self.conf["distance_threshold"], None,
+                               self.conf.get("precision", "exact"))
+            scores = (s0 + 1) / 2                                 # nearest_neighbor.py:15
+            if self.conf["distance_threshold"]:
+                ok = (2 * (1 - s0)) <= self.conf["distance_threshold"] ** 2
+                scores = torch.where(ok, scores, scores.new_tensor(0))
+            ms.append(m0.long())
+            ss.append(scores)
+        return {"matches0": torch.stack(ms), "matching_scores0": torch.stack(ss)}
+
+
+class NearestNeighbor(NearestNeighborMixin, BaseModel):
+    pass
+
+
+confs = {   # it_loc/matcher.py:24-82, the entries on the hot path
+    "NNM": {"output": "NNM", "model": {"name": "nnm", "do_mutual_check": True, "distance_threshold": None}},
+    "ONN": {"output": "ONN", "model": {"name": "nn", "do_mutual_check": False, "distance_threshold": None}},
+}
+
+
+class Matcher(torch.nn.Module):
+    """it_loc/matcher.py:85-119: numpy [N,D] / [M,D] in (any float dtype), numpy out;
+    matching_scores0 is the RAW max cosine of every row.  Mode 'nnm' only (hot path)."""
+
+    def __init__(self, conf, precision="exact"):
+        super().__init__()
+        self.conf = conf
+        self.mode = conf["model"]["name"]
+        self.precision = precision
+        if self.mode not in ("nnm", "nn"):
+            raise NotImplementedError(f"matcher mode '{self.mode}' is outside the hot path")
+
+    def cuda(self, device=None):
+        return self
+
+    def forward(self, data):
+        d0 = np.ascontiguousarray(data["descriptors0"], dtype=np.float32)
+        d1 = np.ascontiguousarray(data["descriptors1"], dtype=np.float32)
+        n0 = d0.shape[0]
+        n1 = d1.shape[0]
+        d = d0.shape[1] if d0.ndim == 2 else _lib.DESC_DIM
+        m0 = np.full((n0,), -1, np.int32)
+        s0 = np.zeros((n0,), np.float32)
+        if n0 > 0:
+            p = _mparams(self.mode == "nnm", None, None, self.precision)
+            dev = torch.cuda.current_device()
+            _lib.check(_lib.lib().sfd2_match_host(_ctx(dev).handle, d0.ctypes.data_as(C.c_void_p), n0,
+                                                  d1.ctypes.data_as(C.c_void_p), n1, d, C.byref(p),
+                                                  m0.ctypes.data_as(C.c_void_p), s0.ctypes.data_as(C.c_void_p)),
+                       "sfd2_match_host")
+        return {"matches0": m0.astype(int), "matching_scores0": s0}
