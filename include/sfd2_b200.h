@@ -129,6 +129,11 @@ SFD2_API int sfd2_match_batched_dev(sfd2_ctx* ctx, const float* d0_dev, const in
 SFD2_API long long sfd2_debug_fetch(sfd2_ctx* ctx, const char* name, float* out_host, long long capacity);
 /* Number of kernels this library launched on behalf of ctx since creation. */
 SFD2_API long long sfd2_launch_count(sfd2_ctx* ctx);
+/* Per-launch CUDA-event timing on the launching stream (bench.py's roofline numbers):
+ * sfd2_profile(ctx, 1) starts recording; sfd2_profile_read synchronises and writes
+ * "label\tlaunches\ttotal_ms\n" lines for everything recorded since the last read. */
+SFD2_API int sfd2_profile(sfd2_ctx* ctx, int enable);
+SFD2_API long long sfd2_profile_read(sfd2_ctx* ctx, char* buf, long long capacity);
 /* Standalone NMS + selection on a caller-supplied heat-map (device fp32 [h,w]):
  * the part of the path that is compare-only and therefore bit-exact. */
 SFD2_API int sfd2_nms_select_dev(sfd2_ctx* ctx, const float* heat_dev, int h, int w,

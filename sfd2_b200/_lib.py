@@ -44,6 +44,8 @@ _PROTOS = {
                                          C.c_int, C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_debug_fetch": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "sfd2_launch_count": (C.c_longlong, [C.c_void_p]),
+    "sfd2_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "sfd2_profile_read": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_longlong]),
     "sfd2_nms_select_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(ExtractParams),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_debug_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
@@ -92,6 +94,21 @@ class Context:
 
     def launch_count(self) -> int:
         return int(lib().sfd2_launch_count(self.handle))
+
+    def profile(self, enable: bool):
+        check(lib().sfd2_profile(self.handle, int(enable)), "sfd2_profile")
+
+    def profile_read(self) -> dict:
+        """{label: (launches, total_ms)} since the last read (synchronises the device)."""
+        buf = C.create_string_buffer(1 << 16)
+        n = lib().sfd2_profile_read(self.handle, buf, len(buf))
+        if n < 0:
+            check(int(n), "sfd2_profile_read")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, cnt, ms = line.split("\t")
+            out[k] = (int(cnt), float(ms))
+        return out
 
     def close(self):
         if self._h:

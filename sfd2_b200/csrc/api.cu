@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 
@@ -48,6 +49,8 @@ struct sfd2_ctx {
   bool have_f32 = false, have_tc = false;
   Act acts[NUM_ACTS];
   CUtensorMap maps[NUM_ACTS][4];
+  CUtensorMap st_maps[NUM_ACTS][2];
+  CUtensorMap map_logits, map_desc;   // fp32 head outputs (TMA store views)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
   unsigned long long *cand = nullptr, *scratch = nullptr;
@@ -64,6 +67,11 @@ struct sfd2_ctx {
   float *m_d0 = nullptr, *m_d1 = nullptr; size_t m_d0_cap = 0, m_d1_cap = 0;
   int32_t* m_out = nullptr; float* m_sim = nullptr; size_t m_out_cap = 0;
   long long launches = 0;
+  // optional per-launch CUDA-event timing (sfd2_profile / sfd2_profile_read)
+  bool prof_on = false;
+  struct ProfRec { std::string label; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
 
   const Layer& L(const char* n) const { return layers[lidx.at(n)]; }
 };
@@ -158,10 +166,36 @@ static int ensure_workspace(sfd2_ctx* c, int H, int W, int prec) {
       rc = tc_make_act_maps(a, a.lo, &c->maps[i][1], &c->maps[i][3]);
       if (rc) return rc;
       a.tm = c->maps[i];
+      rc = tc_make_store_map(&c->st_maps[i][0], a.hi, a.C, a.W, a.H, a.Wp, 0);
+      if (rc) return rc;
+      rc = tc_make_store_map(&c->st_maps[i][1], a.lo, a.C, a.W, a.H, a.Wp, 0);
+      if (rc) return rc;
+      a.tm_st = c->st_maps[i];
     }
+    int rc = tc_make_store_map(&c->map_logits, c->logits, 80, c->W8, c->H8, c->W8, 1);
+    if (rc) return rc;
+    rc = tc_make_store_map(&c->map_desc, c->descmap, 128, c->W4, c->H4, c->W4, 1);
+    if (rc) return rc;
     c->have_tc = true;
   }
   return SFD2_OK;
+}
+
+static cudaEvent_t prof_event(sfd2_ctx* c) {
+  if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+static inline void prof_begin(sfd2_ctx* c, const char* label, cudaStream_t st) {
+  if (!c->prof_on) return;
+  sfd2_ctx::ProfRec r{label, prof_event(c), prof_event(c)};
+  cudaEventRecord(r.a, st);
+  c->prof.push_back(r);
+}
+static inline void prof_end(sfd2_ctx* c, cudaStream_t st) {
+  if (!c->prof_on) return;
+  cudaEventRecord(c->prof.back().b, st);
 }
 
 // one image through network + post-processing, all on `st`
@@ -173,11 +207,15 @@ static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W
   Act* A = c->acts;
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
-  RUN(launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, st));
+#define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
+  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, st));
   auto conv = [&](const char* name, int in, int out, int res) -> int {
     const Layer& L = c->L(name);
-    if (tc) return launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, split, c->num_sms, st);
-    return launch_conv_simt(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, st);
+    prof_begin(c, (std::string(tc ? "tc_conv:" : "conv_f32:") + name).c_str(), st);
+    const int r = tc ? launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, split, c->num_sms, st)
+                     : launch_conv_simt(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, st);
+    prof_end(c, st);
+    return r;
   };
   RUN(conv("conv1b", A1A, A1B, -1));
   RUN(conv("conv2a", A1B, A2A, -1));
@@ -193,21 +231,22 @@ static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W
   Act logit_act; logit_act.f32 = c->logits; logit_act.H = c->H8; logit_act.W = c->W8; logit_act.Wp = c->W8; logit_act.Hp = c->H8; logit_act.C = 80;
   Act desc_act;  desc_act.f32 = c->descmap; desc_act.H = c->H4; desc_act.W = c->W4; desc_act.Wp = c->W4; desc_act.Hp = c->H4; desc_act.C = 128;
   if (tc) {
-    RUN(launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, c->logits, split, c->num_sms, st));
-    RUN(launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, c->descmap, split, c->num_sms, st));
+    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, &c->map_logits, split, c->num_sms, st));
+    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, &c->map_desc, split, c->num_sms, st));
   } else {
-    RUN(launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
-    RUN(launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
+    RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
+    RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
   }
-  RUN(launch_softmax65(c->logits, c->H8 * c->W8, c->semi, st));
-  RUN(launch_l2norm128(c->descmap, c->H4 * c->W4, st));
-  if (p->use_stability) RUN(launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), c->sta, st));
-  RUN(launch_heat(c->semi, c->H8, c->W8, c->sta, c->H4, c->W4, p->use_stability, c->heat, H, W, st));
-  RUN(launch_nms(c->heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? c->nmsdbg : nullptr, c->cand, c->cap,
+  RUNP("softmax65", launch_softmax65(c->logits, c->H8 * c->W8, c->semi, st));
+  RUNP("l2norm128", launch_l2norm128(c->descmap, c->H4 * c->W4, st));
+  if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), c->sta, st));
+  RUNP("heat", launch_heat(c->semi, c->H8, c->W8, c->sta, c->H4, c->W4, p->use_stability, c->heat, H, W, st));
+  RUNP("nms", launch_nms(c->heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? c->nmsdbg : nullptr, c->cand, c->cap,
                  c->counter, st));
-  RUN(launch_select(c->cand, c->cap, c->counter, W, p->topk, kpts, scores, count, c->status, c->scratch, st));
-  RUN(launch_sample(c->descmap, c->H4, c->W4, H, W, kpts, count, p->topk, desc, st));
+  RUNP("select", launch_select(c->cand, c->cap, c->counter, W, p->topk, kpts, scores, count, c->status, c->scratch, st));
+  RUNP("sample", launch_sample(c->descmap, c->H4, c->W4, H, W, kpts, count, p->topk, desc, st));
 #undef RUN
+#undef RUNP
   return SFD2_OK;
 }
 
@@ -235,6 +274,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   memcpy(&nl, base + 8, 4);
   SFD2_CHECK(nl > 0 && nl < 64 && 16 + (size_t)nl * sizeof(BlobLayer) <= nbytes, SFD2_ERR_WEIGHTS, "bad layer count %u", nl);
   SFD2_CUDA(cudaSetDevice(device));
+  if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
   cudaDeviceProp prop;
@@ -278,6 +318,8 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
   cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
   cudaFree(c->m_out); cudaFree(c->m_sim);
+  for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return SFD2_OK;
@@ -369,11 +411,13 @@ static int ensure_match_ws(sfd2_ctx* c, int n0, int n1) {
 static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
                      int32_t* matches0, float* sim0, cudaStream_t st) {
   int rc;
+  prof_begin(c, p->precision == SFD2_PREC_FP32 ? "match_simt" : "match_tc", st);
   if (p->precision == SFD2_PREC_FP32)
     rc = launch_match_simt(d0, n0, d1, n1, d, c->row_key, c->col_key, st);
   else
     rc = launch_match_tc(d0, n0, d1, n1, d, p->precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->mhalf, c->row_key,
                          c->col_key, c->num_sms, st);
+  prof_end(c, st);
   if (rc) return rc;
   return launch_match_finish(c->row_key, c->col_key, n0, n1, p->do_mutual_check, p->distance_threshold, matches0, sim0, st);
 }
@@ -441,6 +485,39 @@ SFD2_API int sfd2_match_host(sfd2_ctx* c, const float* d0, int n0, const float* 
 }
 
 SFD2_API long long sfd2_launch_count(sfd2_ctx* c) { return c ? c->launches : -1; }
+
+SFD2_API int sfd2_profile(sfd2_ctx* c, int enable) {
+  SFD2_CHECK(c != nullptr, SFD2_ERR_ARG, "sfd2_profile: NULL ctx");
+  c->prof_on = enable != 0;
+  return SFD2_OK;
+}
+
+// "label\tlaunches\ttotal_ms\n" per kernel label since the last read; synchronises the device.
+SFD2_API long long sfd2_profile_read(sfd2_ctx* c, char* buf, long long capacity) {
+  if (!c || !buf || capacity < 1) { set_error("sfd2_profile_read: bad argument"); return SFD2_ERR_ARG; }
+  cudaSetDevice(c->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("sync failed"); return SFD2_ERR_CUDA; }
+  std::map<std::string, std::pair<long long, double>> agg;
+  std::vector<std::string> order;
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (!agg.count(r.label)) order.push_back(r.label);
+    auto& e = agg[r.label];
+    e.first += 1; e.second += ms;
+    c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+  }
+  c->prof.clear();
+  std::string out;
+  char line[256];
+  for (auto& k : order) {
+    snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", k.c_str(), agg[k].first, agg[k].second);
+    out += line;
+  }
+  if ((long long)out.size() + 1 > capacity) { set_error("profile buffer too small"); return SFD2_ERR_ARG; }
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return (long long)out.size();
+}
 
 SFD2_API int sfd2_nms_select_dev(sfd2_ctx* c, const float* heat, int h, int w, const sfd2_extract_params* p, float* kpts,
                         float* scores, int32_t* count, float* nms_out, void* stream) {
@@ -566,7 +643,9 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin,
     in.tm = maps;
     Act o2 = out; o2.Wp = out.W; o2.Hp = out.H; o2.C = outC_f32;
     DBG_CUDA(cudaMalloc(&yf, o2.elems() * 4));
-    if (!rc) rc = launch_conv_tc(in, L, o2, nullptr, yf, precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->num_sms, nullptr);
+    CUtensorMap omap;
+    if (!rc) rc = tc_make_store_map(&omap, yf, o2.C, o2.W, o2.H, o2.Wp, 1);
+    if (!rc) rc = launch_conv_tc(in, L, o2, nullptr, &omap, precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->num_sms, nullptr);
     if (!rc) {
       DBG_CUDA(cudaDeviceSynchronize());
       std::vector<float> tmp(o2.elems());

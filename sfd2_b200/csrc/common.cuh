@@ -42,7 +42,8 @@ struct Act {
   __half* hi = nullptr;  // TC modes: x ~ hi (+ lo)
   __half* lo = nullptr;
   int H = 0, W = 0, C = 0, Hp = 0, Wp = 0;
-  const CUtensorMap* tm = nullptr;  // [s1_hi, s1_lo, s2_hi, s2_lo] TMA views (tcgen05 modes)
+  const CUtensorMap* tm = nullptr;     // [s1_hi, s1_lo, s2_hi, s2_lo] TMA load views (tcgen05 modes)
+  const CUtensorMap* tm_st = nullptr;  // [hi, lo] TMA store views (epilogue output / residual input)
   size_t elems() const { return (size_t)Hp * Wp * C; }
 };
 
@@ -62,6 +63,7 @@ struct Layer {
   __half* w_lo = nullptr;
   int cout_tc = 0;             // rows per tap in the TC packing (multiple of 16)
   CUtensorMap tm_w_hi, tm_w_lo;
+  CUtensorMap tm_w_hi_half, tm_w_lo_half;  // boxes of n_mma/2 rows (2-CTA multicast)
 };
 
 struct TcConvLaunch;  // tc_conv.cu
@@ -78,7 +80,8 @@ int launch_l2norm128(float* desc, int npix, cudaStream_t st);
 // tc_conv.cu
 int tc_encode_weights(Layer& L);
 int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2);
-int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, float* out_f32, int split,
+int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32);
+int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
                    int num_sms, cudaStream_t st);
 // post.cu
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
@@ -107,7 +110,10 @@ PFN_encodeTiled get_encode_tiled();
 // fp16, 128B-swizzled tiled map; dims/strides innermost first (strides[0] implied = 2 bytes)
 int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int is_f32, int swizzle);
 
+extern int g_tc_multicast;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

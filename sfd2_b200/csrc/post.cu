@@ -83,51 +83,62 @@ int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int
 // Literal restatement of simple_nms (nets/extractor.py:20-35) on one smem tile with a 20-pixel
 // halo: each of the 5 max-pools / dilations reaches 4 px and the dependency chain is 4+8+8.
 // Out-of-image pixels hold -inf, which is max_pool2d's implicit padding value, and are never
-// allowed into the mask.  Windows are clamped to the tile, so only the interior (>= 20 px from
-// the tile edge) is exact - and only the interior is written.
+// allowed into the mask.  The tile arrays carry a 4-element apron of the pooling identity so the
+// 9-wide windows need no clamping; windows are still cut at the tile edge, so only the interior
+// (>= 20 px from the tile edge) is exact - and only the interior is written.
+//
+// Each 9-wide running max is computed in registers for 8 outputs at a time from 16 loaded values
+// with the doubling scheme m2 -> m4 -> m8 -> m9 (45 max ops and 16 smem reads per 8 outputs).
 constexpr int NT_W = 64, NT_H = 32, NHALO = 20, NR = 4;
-constexpr int NS_W = NT_W + 2 * NHALO;  // 104
-constexpr int NS_H = NT_H + 2 * NHALO;  // 72
-constexpr int NS_N = NS_W * NS_H;
+constexpr int NS_W = NT_W + 2 * NHALO;  // 104 (13 runs of 8)
+constexpr int NS_H = NT_H + 2 * NHALO;  // 72  (9 runs of 8)
+constexpr int NP_W = NS_W + 2 * NR;     // 112 padded pitch
+constexpr int NP_H = NS_H + 2 * NR;     // 80
+constexpr int NP_N = NP_W * NP_H;
+__device__ __forceinline__ int nidx(int y, int x) { return (y + NR) * NP_W + x + NR; }  // tile coords -> padded index
 
-// dst = 9x9 max of src (row pass into tmp, column pass into dst)
-__device__ __forceinline__ void pool9_f(const float* __restrict__ src, float* __restrict__ tmp,
-                                        float* __restrict__ dst) {
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
-    const int y = i / NS_W, x = i - y * NS_W;
-    const int a = max(x - NR, 0), b = min(x + NR, NS_W - 1);
-    float mx = src[y * NS_W + a];
-    for (int k = a + 1; k <= b; ++k) mx = fmaxf(mx, src[y * NS_W + k]);
-    tmp[i] = mx;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
-    const int y = i / NS_W, x = i - y * NS_W;
-    const int a = max(y - NR, 0), b = min(y + NR, NS_H - 1);
-    float mx = tmp[a * NS_W + x];
-    for (int k = a + 1; k <= b; ++k) mx = fmaxf(mx, tmp[k * NS_W + x]);
-    dst[i] = mx;
-  }
-  __syncthreads();
+template <typename T> __device__ __forceinline__ T pmax(T a, T b);
+template <> __device__ __forceinline__ float pmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ unsigned char pmax<unsigned char>(unsigned char a, unsigned char b) { return a | b; }
+
+template <typename T>
+__device__ __forceinline__ void run9(const T (&v)[16], T (&o)[8]) {
+  T m2[15], m4[13], m8[9];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) m2[i] = pmax(v[i], v[i + 1]);
+#pragma unroll
+  for (int i = 0; i < 13; ++i) m4[i] = pmax(m2[i], m2[i + 2]);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m8[i] = pmax(m4[i], m4[i + 4]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = pmax(m8[i], v[i + 8]);
 }
 
-// dst = 9x9 dilation of the 0/1 mask src
-__device__ __forceinline__ void dilate9(const unsigned char* __restrict__ src, unsigned char* __restrict__ tmp,
-                                        unsigned char* __restrict__ dst) {
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
-    const int y = i / NS_W, x = i - y * NS_W;
-    const int a = max(x - NR, 0), b = min(x + NR, NS_W - 1);
-    unsigned char mx = 0;
-    for (int k = a; k <= b; ++k) mx |= src[y * NS_W + k];
-    tmp[i] = mx;
+// dst = 9x9 max of src over the tile (src/tmp/dst are padded arrays whose apron holds the identity)
+template <typename T>
+__device__ __forceinline__ void pool9(const T* __restrict__ src, T* __restrict__ tmp, T* __restrict__ dst) {
+  // row pass: work item = (row, run of 8 columns)
+  for (int it = threadIdx.x; it < NS_H * (NS_W / 8); it += blockDim.x) {
+    const int y = it / (NS_W / 8), x0 = (it - y * (NS_W / 8)) * 8;
+    T v[16], o[8];
+    const T* p = src + nidx(y, x0 - NR);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = p[i];
+    run9(v, o);
+    T* q = tmp + nidx(y, x0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = o[i];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
-    const int y = i / NS_W, x = i - y * NS_W;
-    const int a = max(y - NR, 0), b = min(y + NR, NS_H - 1);
-    unsigned char mx = 0;
-    for (int k = a; k <= b; ++k) mx |= tmp[k * NS_W + x];
-    dst[i] = mx;
+  // column pass: work item = (run of 8 rows, column); consecutive threads take consecutive columns
+  for (int it = threadIdx.x; it < (NS_H / 8) * NS_W; it += blockDim.x) {
+    const int yr = it / NS_W, x = it - yr * NS_W, y0 = yr * 8;
+    T v[16], o[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = tmp[nidx(y0 - NR + i, x)];
+    run9(v, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[nidx(y0 + i, x)] = o[i];
   }
   __syncthreads();
 }
@@ -137,42 +148,61 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
            unsigned long long* __restrict__ cand, int cap, int* __restrict__ counter) {
   extern __shared__ float sm[];
   float* s = sm;             // scores (-inf outside the image)
-  float* t = sm + NS_N;      // row-pass scratch
-  float* u = sm + 2 * NS_N;  // pooled scores / suppressed scores
-  unsigned char* m = reinterpret_cast<unsigned char*>(sm + 3 * NS_N);  // max_mask
-  unsigned char* tb = m + NS_N;                                        // dilation scratch
-  unsigned char* supp = tb + NS_N;                                     // supp_mask
+  float* t = sm + NP_N;      // row-pass scratch
+  float* u = sm + 2 * NP_N;  // pooled scores / suppressed scores
+  unsigned char* m = reinterpret_cast<unsigned char*>(sm + 3 * NP_N);  // max_mask
+  unsigned char* tb = m + NP_N;                                        // dilation scratch
+  unsigned char* supp = tb + NP_N;                                     // supp_mask
   const int X0 = blockIdx.x * NT_W - NHALO, Y0 = blockIdx.y * NT_H - NHALO;
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
-    const int yy = i / NS_W;
-    const int y = Y0 + yy, x = X0 + (i - yy * NS_W);
-    s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(heat + (size_t)y * W + x) : -CUDART_INF_F;
+  for (int i = threadIdx.x; i < NP_N; i += blockDim.x) {
+    const int py = i / NP_W, px = i - py * NP_W;
+    const int ty = py - NR, tx = px - NR;
+    const int y = Y0 + ty, x = X0 + tx;
+    const bool in_tile = ty >= 0 && ty < NS_H && tx >= 0 && tx < NS_W;
+    s[i] = (in_tile && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(heat + (size_t)y * W + x) : -CUDART_INF_F;
+    t[i] = -CUDART_INF_F;   // aprons of the scratch arrays: identity of max
+    u[i] = -CUDART_INF_F;
+    m[i] = 0; tb[i] = 0; supp[i] = 0;
   }
   __syncthreads();
-  pool9_f(s, t, u);                                                    // max_pool(scores)
-  for (int i = threadIdx.x; i < NS_N; i += blockDim.x) m[i] = (s[i] != -CUDART_INF_F) && (s[i] == u[i]);
+  pool9<float>(s, t, u);                                               // max_pool(scores)
+  for (int it = threadIdx.x; it < NS_H * NS_W; it += blockDim.x) {
+    const int y = it / NS_W, x = it - y * NS_W, i = nidx(y, x);
+    m[i] = (s[i] != -CUDART_INF_F) && (s[i] == u[i]);
+  }
   __syncthreads();
   for (int round = 0; round < 2; ++round) {
-    dilate9(m, tb, supp);                                              // supp_mask = max_pool(max_mask) > 0
-    for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {
+    pool9<unsigned char>(m, tb, supp);                                 // supp_mask = max_pool(max_mask) > 0
+    for (int it = threadIdx.x; it < NS_H * NS_W; it += blockDim.x) {
+      const int y = it / NS_W, x = it - y * NS_W, i = nidx(y, x);
       const float sv = s[i];
-      u[i] = (supp[i] && sv != -CUDART_INF_F) ? 0.f : sv;              // supp_scores
+      t[i] = (supp[i] && sv != -CUDART_INF_F) ? 0.f : sv;              // supp_scores (kept in t)
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {             // row pass of max_pool(supp_scores)
-      const int y = i / NS_W, x = i - y * NS_W;
-      const int a = max(x - NR, 0), b = min(x + NR, NS_W - 1);
-      float mx = u[y * NS_W + a];
-      for (int k = a + 1; k <= b; ++k) mx = fmaxf(mx, u[y * NS_W + k]);
-      t[i] = mx;
+    // max_pool(supp_scores): row pass t -> u, column pass u -> compare in place
+    for (int it = threadIdx.x; it < NS_H * (NS_W / 8); it += blockDim.x) {
+      const int y = it / (NS_W / 8), x0 = (it - y * (NS_W / 8)) * 8;
+      float v[16], o[8];
+      const float* p = t + nidx(y, x0 - NR);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = p[i];
+      run9(v, o);
+      float* q = u + nidx(y, x0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = o[i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NS_N; i += blockDim.x) {             // column pass + mask update
-      const int y = i / NS_W, x = i - y * NS_W;
-      const int a = max(y - NR, 0), b = min(y + NR, NS_H - 1);
-      float mx = t[a * NS_W + x];
-      for (int k = a + 1; k <= b; ++k) mx = fmaxf(mx, t[k * NS_W + x]);
-      if (s[i] != -CUDART_INF_F && u[i] == mx && !supp[i]) m[i] = 1;   // max_mask |= new_max & ~supp
+    for (int it = threadIdx.x; it < (NS_H / 8) * NS_W; it += blockDim.x) {
+      const int yr = it / NS_W, x = it - yr * NS_W, y0 = yr * 8;
+      float v[16], o[8];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = u[nidx(y0 - NR + i, x)];
+      run9(v, o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = nidx(y0 + i, x);
+        if (s[id] != -CUDART_INF_F && t[id] == o[i] && !supp[id]) m[id] = 1;   // max_mask |= new_max & ~supp
+      }
     }
     __syncthreads();
   }
@@ -181,7 +211,7 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
     const int ty = i / NT_W, tx = i - ty * NT_W;
     const int y = blockIdx.y * NT_H + ty, x = blockIdx.x * NT_W + tx;
     const bool in_img = (y < H && x < W);
-    const int si = (ty + NHALO) * NS_W + tx + NHALO;
+    const int si = nidx(ty + NHALO, tx + NHALO);
     const float v = (in_img && m[si]) ? s[si] : 0.f;
     if (in_img && nms_out) nms_out[(size_t)y * W + x] = v;
     const bool is_cand = in_img && (v > conf_th) && x >= border && x < W - border && y >= border && y < H - border;
@@ -203,7 +233,7 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
 
 int launch_nms(const float* heat, int H, int W, float conf_th, int border, float* nms_out, unsigned long long* cand,
                int cap, int* counter, cudaStream_t st) {
-  const size_t smem = (size_t)3 * NS_N * sizeof(float) + 3 * NS_N;
+  const size_t smem = (size_t)3 * NP_N * sizeof(float) + 3 * NP_N;
   static bool attr = false;
   if (!attr) {
     SFD2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -220,63 +250,54 @@ int launch_nms(const float* heat, int H, int W, float conf_th, int border, float
 // ------------------------------------------------------------------------------ top-K selection
 // Candidates are 64-bit keys (score bits << 32 | ~pixel index): positive floats order like their
 // bit patterns, and the inverted index makes the lower pixel index win among exactly equal scores
-// (the reference's order there is np.argsort-unstable, nets/extractor.py:176,323).  One CTA sorts
-// them descending (bitonic) - in shared memory when they fit, otherwise in the global scratch -
-// and emits the first K as (x, y), score.
-constexpr int SEL_SMEM_KEYS = 16384;
+// (the reference's order there is np.argsort-unstable, nets/extractor.py:176,323).  Keys are unique,
+// so a candidate's position in the descending order is simply the number of keys greater than it:
+// every thread owns one candidate, streams all keys through shared memory, counts, and - if its
+// rank is below K - writes its (x, y), score straight to row `rank`.  No sort, no single-CTA tail;
+// O(n^2) compares spread over the whole GPU (n ~ 6k: 39 M compares).
+constexpr int SEL_THREADS = 256, SEL_CHUNK = 2048;
 
-__device__ __forceinline__ void bitonic_desc(unsigned long long* a, int n) {  // n = power of two
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int p = i ^ j;
-        if (p > i) {
-          const unsigned long long x = a[i], y = a[p];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (x < y) : (x > y)) { a[i] = y; a[p] = x; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* __restrict__ counter, int W, int topk,
               float* __restrict__ kpts, float* __restrict__ scores, int32_t* __restrict__ count_out,
-              int* __restrict__ status, unsigned long long* __restrict__ scratch) {
-  extern __shared__ unsigned long long keys[];
+              int* __restrict__ status) {
+  __shared__ unsigned long long keys[SEL_CHUNK];
   int n = *counter;
   if (n > cap) {                       // more candidates than the workspace holds: report, keep what fits
-    if (threadIdx.x == 0) *status = SFD2_ERR_OVERFLOW;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *status = SFD2_ERR_OVERFLOW;
     n = cap;
   }
-  int n2 = 1;
-  while (n2 < n) n2 <<= 1;
-  unsigned long long* a = (n2 <= SEL_SMEM_KEYS) ? keys : scratch;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) a[i] = (i < n) ? cand[i] : 0ull;
-  __syncthreads();
-  bitonic_desc(a, n2);
-  const int k = (topk > 0 && topk < n) ? topk : n;
-  for (int i = threadIdx.x; i < k; i += blockDim.x) {
-    const unsigned long long key = a[i];
-    const unsigned lin = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull);
-    kpts[2 * i] = (float)(lin % (unsigned)W);
-    kpts[2 * i + 1] = (float)(lin / (unsigned)W);
-    scores[i] = __uint_as_float((unsigned)(key >> 32));
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = (topk > 0 && topk < n) ? topk : n;
+  if (blockIdx.x * SEL_THREADS >= n) return;
+  const int i = blockIdx.x * SEL_THREADS + threadIdx.x;
+  const unsigned long long mine = (i < n) ? cand[i] : 0xFFFFFFFFFFFFFFFFull;
+  int rank = 0;
+  for (int c0 = 0; c0 < n; c0 += SEL_CHUNK) {
+    const int cn = min(SEL_CHUNK, n - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cn; j += SEL_THREADS) keys[j] = cand[c0 + j];
+    __syncthreads();
+    int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    int j = 0;
+    for (; j + 4 <= cn; j += 4) {
+      r0 += keys[j] > mine; r1 += keys[j + 1] > mine; r2 += keys[j + 2] > mine; r3 += keys[j + 3] > mine;
+    }
+    for (; j < cn; ++j) r0 += keys[j] > mine;
+    rank += r0 + r1 + r2 + r3;
   }
-  if (threadIdx.x == 0) *count_out = k;
+  const int k = (topk > 0 && topk < n) ? topk : n;
+  if (i < n && rank < k) {
+    const unsigned lin = 0xFFFFFFFFu - (unsigned)(mine & 0xFFFFFFFFull);
+    kpts[2 * rank] = (float)(lin % (unsigned)W);
+    kpts[2 * rank + 1] = (float)(lin / (unsigned)W);
+    scores[rank] = __uint_as_float((unsigned)(mine >> 32));
+  }
 }
 
 int launch_select(unsigned long long* cand, int cap, const int* counter, int W, int topk, float* kpts, float* scores,
                   int32_t* count_out, int* status, unsigned long long* scratch, cudaStream_t st) {
-  const size_t smem = (size_t)SEL_SMEM_KEYS * sizeof(unsigned long long);
-  static bool attr = false;
-  if (!attr) {
-    SFD2_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  select_kernel<<<1, 1024, smem, st>>>(cand, cap, counter, W, topk, kpts, scores, count_out, status, scratch);
+  (void)scratch;
+  select_kernel<<<cdiv(cap, SEL_THREADS), SEL_THREADS, 0, st>>>(cand, cap, counter, W, topk, kpts, scores, count_out, status);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

@@ -14,26 +14,34 @@
 namespace sfd2 {
 
 // ------------------------------------------------------------------------------ conv1a
-struct Conv1aWeights {
-  float w[27 * 64];  // [tap][ci][co]
-  float b[64];
-};
-
+// thread = 2 horizontally adjacent pixels x 16 output channels.  The 16-channel chunk is chosen per
+// WARP (warp & 3), so every weight read from shared memory is a warp-uniform broadcast (one wavefront
+// per LDS.128 - the first version read 4 different addresses per warp with bank conflicts and was
+// shared-memory bound at 0.62 ms); lanes are consecutive pixel pairs and write whole 32-byte sectors.
+// Weights + bias sit in shared memory ([tap*3+ci][64]).
 template <int IMG_DTYPE, int TC_OUT>
-__global__ void __launch_bounds__(128)
-conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const __grid_constant__ Conv1aWeights cw,
-              float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256)
+conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const float* __restrict__ wt /*[27][64]*/,
+              const float* __restrict__ bias, float* __restrict__ out_f32, __half* __restrict__ out_hi,
+              __half* __restrict__ out_lo) {
+  __shared__ __align__(16) float ws[27 * 64 + 64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = wt[i];
+  if (threadIdx.x < 64) ws[27 * 64 + threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cq = warp & 3;
+  const int x = blockIdx.x * 128 + ((warp >> 2) * 32 + lane) * 2;
   const int y = blockIdx.y;
   if (x >= W) return;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
-  float in[27];
+  float in[3][4][3];  // [ky][column x-1..x+2][c], normalised; zero padding AFTER normalisation
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int iy = y + ky - 1, ix = x + kx - 1;
+    for (int q = 0; q < 4; ++q) {
+      const int ix = x + q - 1;
       const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -44,43 +52,53 @@ conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const __grid_c
             raw = __ldg(reinterpret_cast<const float*>(img) + ((size_t)c * H + iy) * W + ix);
           else
             raw = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(img) + ((size_t)iy * W + ix) * 3 + c), 255.0f);
-          v = __fdiv_rn(__fsub_rn(raw, mean[c]), stdv[c]);  // (x - mean) / std, zero padding AFTER normalise
+          v = __fdiv_rn(__fsub_rn(raw, mean[c]), stdv[c]);
         }
-        in[(ky * 3 + kx) * 3 + c] = v;
+        in[ky][q][c] = v;
       }
     }
   }
-  const size_t obase = ((size_t)y * Wp + x) * 64;
+  float acc[2][16];
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    float acc[16];
+  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = ws[27 * 64 + cq * 16 + j];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = cw.b[c0 + j];
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int t = 0; t < 27; ++t) {
+    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(in[t], cw.w[t * 64 + c0 + j], acc[j]);
-    }
+      for (int c = 0; c < 3; ++c) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + cq * 16);
+        float wv[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = fmaxf(acc[j], 0.f);
+        for (int g = 0; g < 4; ++g) { const float4 t = wr[g]; wv[4 * g] = t.x; wv[4 * g + 1] = t.y; wv[4 * g + 2] = t.z; wv[4 * g + 3] = t.w; }
+        const float a0 = in[ky][kx][c], a1 = in[ky][kx + 1][c];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { acc[0][j] = fmaf(a0, wv[j], acc[0][j]); acc[1][j] = fmaf(a1, wv[j], acc[1][j]); }
+      }
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    if (x + p >= W) break;
+    const size_t obase = ((size_t)y * Wp + x + p) * 64 + cq * 16;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[p][j] = fmaxf(acc[p][j], 0.f);
     if (TC_OUT) {
       __align__(16) __half hi[16];
       __align__(16) __half lo[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        hi[j] = __float2half_rn(acc[j]);
-        lo[j] = __float2half_rn(acc[j] - __half2float(hi[j]));
+        hi[j] = __float2half_rn(acc[p][j]);
+        lo[j] = __float2half_rn(acc[p][j] - __half2float(hi[j]));
       }
-      uint4* ph = reinterpret_cast<uint4*>(out_hi + obase + c0);
-      uint4* pl = reinterpret_cast<uint4*>(out_lo + obase + c0);
+      uint4* ph = reinterpret_cast<uint4*>(out_hi + obase);
+      uint4* pl = reinterpret_cast<uint4*>(out_lo + obase);
       ph[0] = reinterpret_cast<uint4*>(hi)[0];
       ph[1] = reinterpret_cast<uint4*>(hi)[1];
       pl[0] = reinterpret_cast<uint4*>(lo)[0];
       pl[1] = reinterpret_cast<uint4*>(lo)[1];
     } else {
-      float4* p = reinterpret_cast<float4*>(out_f32 + obase + c0);
+      float4* o = reinterpret_cast<float4*>(out_f32 + obase);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) p[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      for (int g = 0; g < 4; ++g) o[g] = make_float4(acc[p][4 * g], acc[p][4 * g + 1], acc[p][4 * g + 2], acc[p][4 * g + 3]);
     }
   }
 }
@@ -88,18 +106,14 @@ conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const __grid_c
 int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out,
                   cudaStream_t st) {
   SFD2_CHECK(L.cin == 3 && L.cout == 64 && L.k == 3, SFD2_ERR_WEIGHTS, "conv1a: unexpected layer shape");
-  static thread_local Conv1aWeights cw;
-  for (int t = 0; t < 9; ++t)
-    for (int ci = 0; ci < 3; ++ci)
-      for (int co = 0; co < 64; ++co) cw.w[(t * 3 + ci) * 64 + co] = L.w[((size_t)co * 3 + ci) * 9 + t];
-  for (int co = 0; co < 64; ++co) cw.b[co] = L.b[co];
-  dim3 grid(cdiv(W, 128), H), block(128);
+  // L.w_simt is [tap][ci][cout_pad = 64] fp32 = exactly the [27][64] table the kernel stages in smem
+  dim3 grid(cdiv(W, 128), H), block(256);
   if (img_dtype == SFD2_IMG_F32_NCHW) {
-    if (tc_out) conv1a_kernel<SFD2_IMG_F32_NCHW, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, cw, nullptr, out.hi, out.lo);
-    else conv1a_kernel<SFD2_IMG_F32_NCHW, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, cw, out.f32, nullptr, nullptr);
+    if (tc_out) conv1a_kernel<SFD2_IMG_F32_NCHW, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, nullptr, out.hi, out.lo);
+    else conv1a_kernel<SFD2_IMG_F32_NCHW, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
   } else if (img_dtype == SFD2_IMG_U8_NHWC) {
-    if (tc_out) conv1a_kernel<SFD2_IMG_U8_NHWC, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, cw, nullptr, out.hi, out.lo);
-    else conv1a_kernel<SFD2_IMG_U8_NHWC, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, cw, out.f32, nullptr, nullptr);
+    if (tc_out) conv1a_kernel<SFD2_IMG_U8_NHWC, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, nullptr, out.hi, out.lo);
+    else conv1a_kernel<SFD2_IMG_U8_NHWC, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
   } else {
     SFD2_CHECK(false, SFD2_ERR_ARG, "unknown image dtype %d", img_dtype);
   }
@@ -283,46 +297,54 @@ int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cud
 }
 
 // ------------------------------------------------------------------------------ ConvSta (always fp32)
+// one warp per pixel (grid-stride), lane = 8 consecutive channels; each lane keeps its 24 weights in
+// registers, so the only memory traffic is the coalesced read of the 256-channel pixel rows.
 template <int TC_IN>
-__global__ void sta_kernel(const float* __restrict__ in_f32, const __half* __restrict__ in_hi,
-                           const __half* __restrict__ in_lo, int H, int W, int Wp,
-                           const float* __restrict__ wt /*[256][64pad]*/, const float* __restrict__ bias,
-                           float* __restrict__ logits /*[H*W][3]*/) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= H * W) return;
-  const int y = warp / W, x = warp % W;
-  const size_t base = ((size_t)y * Wp + x) * 256 + lane * 8;
-  float v[8];
-  if (TC_IN) {
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(in_hi + base));
-    const uint4 l = (TC_IN == 1) ? __ldg(reinterpret_cast<const uint4*>(in_lo + base)) : make_uint4(0, 0, 0, 0);
-    const __half* hh = reinterpret_cast<const __half*>(&h);
-    const __half* ll = reinterpret_cast<const __half*>(&l);
+__global__ void __launch_bounds__(256)
+sta_kernel(const float* __restrict__ in_f32, const __half* __restrict__ in_hi, const __half* __restrict__ in_lo,
+           int H, int W, int Wp, const float* __restrict__ wt /*[256][64pad]*/, const float* __restrict__ bias,
+           float* __restrict__ logits /*[H*W][3]*/) {
+  const int lane = threadIdx.x & 31;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float w[8][3];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __half2float(hh[j]) + (TC_IN == 1 ? __half2float(ll[j]) : 0.f);
-  } else {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(in_f32 + base));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(in_f32 + base + 4));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) w[j][c] = __ldg(wt + (size_t)(lane * 8 + j) * 64 + c);
+  const float b = (lane < 3) ? __ldg(bias + lane) : 0.f;
+  for (int pix = warp0; pix < H * W; pix += nwarps) {
+    const int y = pix / W, x = pix - y * W;
+    const size_t base = ((size_t)y * Wp + x) * 256 + lane * 8;
+    float v[8];
+    if (TC_IN) {
+      const uint4 h = __ldg(reinterpret_cast<const uint4*>(in_hi + base));
+      const uint4 l = (TC_IN == 1) ? __ldg(reinterpret_cast<const uint4*>(in_lo + base)) : make_uint4(0, 0, 0, 0);
+      const __half* hh = reinterpret_cast<const __half*>(&h);
+      const __half* ll = reinterpret_cast<const __half*>(&l);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __half2float(hh[j]) + (TC_IN == 1 ? __half2float(ll[j]) : 0.f);
+    } else {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(in_f32 + base));
+      const float4 c = __ldg(reinterpret_cast<const float4*>(in_f32 + base + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+    }
+    float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s[c] = fmaf(v[j], w[j][c], s[c]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+    if (lane < 3) logits[(size_t)pix * 3 + lane] = (lane == 0 ? s[0] : (lane == 1 ? s[1] : s[2])) + b;
   }
-  float s[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float* wr = wt + (size_t)(lane * 8 + j) * 64;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) s[c] = fmaf(v[j], __ldg(wr + c), s[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
-  if (lane < 3) logits[(size_t)warp * 3 + lane] = s[lane] + __ldg(bias + lane);
 }
 
 int launch_sta(const Act& in, int tc_in, const Layer& L, float* logits, cudaStream_t st) {
   SFD2_CHECK(L.cin == 256 && L.cout == 3 && L.k == 1, SFD2_ERR_WEIGHTS, "sta layer shape");
-  const int warps = in.H * in.W;
-  const int blocks = cdiv(warps * 32, 256);
+  const int blocks = 148 * 8;
   if (tc_in == 1) sta_kernel<1><<<blocks, 256, 0, st>>>(nullptr, in.hi, in.lo, in.H, in.W, in.Wp, L.w_simt, L.b_dev, logits);
   else if (tc_in == 2) sta_kernel<2><<<blocks, 256, 0, st>>>(nullptr, in.hi, in.lo, in.H, in.W, in.Wp, L.w_simt, L.b_dev, logits);
   else sta_kernel<0><<<blocks, 256, 0, st>>>(in.f32, nullptr, nullptr, in.H, in.W, in.Wp, L.w_simt, L.b_dev, logits);

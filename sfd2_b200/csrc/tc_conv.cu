@@ -17,6 +17,11 @@
 // * grouped 3x3 (groups=32, 8 ch/group): "diag" mode - for each 64-channel chunk the weight slab is
 //   the 64x64 block-diagonal piece, one N=64 MMA per chunk into its own 64 accumulator columns.
 //
+// * weight multicast: CTAs run as clusters of 2 neighbouring tiles; each CTA fetches HALF of every
+//   weight slab and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM traffic of
+//   the B operand (the kernel is L2-bandwidth bound otherwise).  A stage is released to the
+//   producers only when BOTH CTAs' MMAs have consumed it (multicast tcgen05.commit).
+//
 // Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
 // issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
 #include "common.cuh"
@@ -35,27 +40,38 @@ struct TcConvArgs {
   int Ho, Wo, tiles_x, num_tiles;
   int taps, stride, kchunks, diag;
   int n_mma, acc_cols, tmem_cols, cout, relu, split;
+  int corr;        // 1: the hi*lo / lo*hi passes accumulate in their own TMEM region (added in the epilogue)
+  int nbuf;        // accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
+  int buf_stride;  // TMEM columns per buffer = acc_cols * (1 + corr)
   int stages, stage_bytes, b_bytes;
+  int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
+  int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
   const float* bias;
-  __half* out_hi;
-  __half* out_lo;
-  float* out_f32;
-  int out_Wp, out_C;
-  const __half* res_hi;
-  const __half* res_lo;
+  int out_mode;    // 0: fp16 hi plane only, 1: fp16 hi + lo planes, 2: fp32
+  int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
 };
+
+constexpr int TC_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 px x 128 B)
+constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+               const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+               const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
                const __grid_constant__ TcConvArgs a) {
+  const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * a.stage_bytes);
+  uint8_t* staging = smem + (size_t)a.stages * a.stage_bytes;            // 1024-aligned (stage_bytes % 1024 == 0)
+  float* sbias = reinterpret_cast<float*>(staging + TC_STAGING_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* resbar = tempty + 2;                                         // [4 warps][2 buffers]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -64,23 +80,32 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (a.split == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 8; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  for (int i = threadIdx.x; i < (int)(TC_BIAS_BYTES / sizeof(float)); i += blockDim.x)
+    sbias[i] = (i < ((a.cout + 31) / 32) * 32) ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
+  if (a.mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nkb = a.taps * a.kchunks;
+  // tile of iteration `it`; a cluster whose FIRST tile is out of range skips the iteration as a whole,
+  // otherwise an out-of-range tile is processed as an all-padding dummy so that peers stay in lock step
+  const int cl_first = (int)blockIdx.x - (int)crank;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < a.iters; ++it) {
+        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+        const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * TC_TILE_H, x0 = (tile % a.tiles_x) * TC_TILE_W;
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
@@ -102,8 +127,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.acc_cols;
             const int bcol = a.diag ? 0 : c0;
-            tma_load_2d(sb, &tmB_hi, &full[stage], bcol, brow);
-            if (a.split == 3) tma_load_2d(sb + a.b_bytes, &tmB_lo, &full[stage], bcol, brow);
+            if (a.mc > 1) {   // my half of the slab, delivered to both CTAs
+              const int hrows = a.n_mma / 2;
+              const int ro = (int)crank * hrows;
+              tma_load_2d_mc(sb + ro * 128, &tmB_hi, &full[stage], bcol, brow + ro, cmask);
+              if (a.split == 3) tma_load_2d_mc(sb + a.b_bytes + ro * 128, &tmB_lo, &full[stage], bcol, brow + ro, cmask);
+            } else {
+              tma_load_2d(sb, &tmB_hi, &full[stage], bcol, brow);
+              if (a.split == 3) tma_load_2d(sb + a.b_bytes, &tmB_lo, &full[stage], bcol, brow);
+            }
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -117,7 +149,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t phase = 0;
       int buf = 0;
       uint32_t bphase = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int it = 0; it < a.iters; ++it) {
+        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
@@ -127,107 +160,174 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint32_t sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
           const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TC_A_BYTES);
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + a.b_bytes);
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.acc_cols + (a.diag ? (kb % a.kchunks) * 64 : 0));
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? (kb % a.kchunks) * 64 : 0));
           const bool first = a.diag ? (kb < a.kchunks) : (kb == 0);
 #pragma unroll 1
           for (int pass = 0; pass < a.split; ++pass) {
             const uint64_t da = (pass == 2) ? da_lo : da_hi;
             const uint64_t db = (pass == 1) ? db_lo : db_hi;
+            // the tensor core truncates (round-toward-zero) every time it adds into the fp32 accumulator, so
+            // the two small correction passes go to their own accumulator: truncation there is relative to a
+            // ~2^-11 smaller magnitude, and the main accumulator sees 3x fewer additions.
+            const bool to_corr = a.corr && pass > 0;
+            const uint32_t d = to_corr ? dcol + (uint32_t)a.acc_cols : dcol;
+            const int first_pass = to_corr ? 1 : 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(dcol, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (first && pass == 0 && k == 0) ? 0u : 1u);
+              umma_f16(d, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (first && pass == first_pass && k == 0) ? 0u : 1u);
           }
-          umma_commit(&empty[stage]);           // smem slot free once these MMAs have read it
+          // smem slot free once these MMAs have read it (in both CTAs when the slab is multicast)
+          if (a.mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[buf]);               // accumulator complete -> epilogue
-        if (++buf == 2) { buf = 0; bphase ^= 1; }
+        if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // Per 32-channel chunk: TMEM -> registers -> (+bias, +residual, ReLU, fp16 hi/lo split) -> this warp's
+    // swizzled staging tile in smem -> ONE TMA store per plane (box {32 ch, 16 px, 2 rows}).  TMA clips
+    // partial tiles and writes full lines; the threads never touch global memory (per-lane 16-byte
+    // stores at a 512-byte stride cost ~8k LSU cycles per tile in the first version and bounded every 1x1
+    // layer).  Residual tiles arrive the same way (TMA load into the staging buffer, two chunks ahead).
     const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int ty = row >> 4, tx = row & 15;
+    uint8_t* wstage = staging + q * 2 * 4096;
+    uint64_t* wres = resbar + q * 2;
     int buf = 0;
     uint32_t bphase = 0;
     const int nchunks = (a.cout + 31) / 32;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int oy = (tile / a.tiles_x) * TC_TILE_H + ty, ox = (tile % a.tiles_x) * TC_TILE_W + tx;
-      const bool valid = (oy < a.Ho) && (ox < a.Wo);
-      const size_t opix = (size_t)oy * a.out_Wp + ox;
+    const int r = lane;                          // row of this warp's 32-pixel box (2 tile rows x 16 px)
+    // chunk sequence number over (iteration, chunk): staging buffer = seq & 1
+    auto tile_xy = [&](int it, int& x0, int& y0) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      x0 = (tile % a.tiles_x) * TC_TILE_W;
+      y0 = (tile / a.tiles_x) * TC_TILE_H + 2 * q;
+    };
+    auto issue_res = [&](int it, int ch, int sb) {   // lane 0 only
+      if (it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
+      int x0, y0;
+      tile_xy(it, x0, y0);
+      uint8_t* dst = wstage + sb * 4096;
+      mbar_expect_tx(&wres[sb], a.has_res == 2 ? 4096u : 2048u);
+      tma_load_3d(dst, &tmR_hi, &wres[sb], ch * 32, x0, y0);
+      if (a.has_res == 2) tma_load_3d(dst + 2048, &tmR_lo, &wres[sb], ch * 32, x0, y0);
+    };
+    uint32_t seq = 0;
+    uint32_t rphase[2] = {0u, 0u};
+    if (a.has_res && lane == 0) {                 // prefetch the residual of the first two chunks
+      issue_res(0, 0, 0);
+      if (nchunks > 1) issue_res(0, 1, 1); else issue_res(1, 0, 1);
+    }
+    for (int it = 0; it < a.iters; ++it) {
+      if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+      int x0, y0;
+      tile_xy(it, x0, y0);
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.acc_cols);
-      for (int ch = 0; ch < nchunks; ++ch) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
+      for (int ch = 0; ch < nchunks; ++ch, ++seq) {
         const int c0 = ch * 32;
+        const int sb = seq & 1;
+        uint8_t* st = wstage + sb * 4096;
         uint32_t v[32];
+        float x[32];
         tmem_ld32(taddr + c0, v);
+        if (!a.has_res) {                         // the store issued from this buffer two chunks ago must have
+          if (lane == 0) bulk_wait_read<1>();     // finished reading it (with a residual, issue_res waited already)
+          __syncwarp();
+        }
         tmem_ld_wait();
-        if (valid) {
-          float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + __ldg(a.bias + c0 + j);
-          if (a.res_hi) {
-            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + opix * a.out_C + c0);
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+        if (a.corr) {
+          tmem_ld32(taddr + a.acc_cols + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(v[j]);
+        }
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + g * 4);
+          x[g * 4] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
+        }
+        const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
+        if (a.has_res) {
+          mbar_wait(&wres[sb], rphase[sb]);
+          rphase[sb] ^= 1u;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 h = *reinterpret_cast<const uint4*>(st + r * 64 + ((g ^ sw64) << 4));
+            const __half* hh = reinterpret_cast<const __half*>(&h);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(hh[j]);
+          }
+          if (a.has_res == 2) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint4 h = __ldg(rh + g);
-              const __half* hh = reinterpret_cast<const __half*>(&h);
+              const uint4 l = *reinterpret_cast<const uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4));
+              const __half* ll = reinterpret_cast<const __half*>(&l);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(hh[j]);
-            }
-            if (a.res_lo) {
-              const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + opix * a.out_C + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 l = __ldg(rl + g);
-                const __half* ll = reinterpret_cast<const __half*>(&l);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(ll[j]);
-              }
+              for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(ll[j]);
             }
           }
-          if (a.relu) {
+          __syncwarp();                           // everyone has read the residual before it is overwritten
+        }
+        if (a.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (a.out_mode == 2) {                    // fp32 rows of 128 B, SWIZZLE_128B
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(st + r * 128 + ((g ^ (r & 7)) << 4)) =
+                make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+        } else {
+          __align__(16) __half hi[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hi[j] = __float2half_rn(x[j]);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(st + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
+          if (a.out_mode == 1) {
+            __align__(16) __half lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) lo[j] = __float2half_rn(x[j] - __half2float(hi[j]));
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
           }
-          if (a.out_f32) {
-            float* o = a.out_f32 + opix * a.out_C + c0;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (c0 + g * 4 < a.out_C)
-                *reinterpret_cast<float4*>(o + g * 4) = make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
-          } else {
-            __align__(16) __half hi[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) hi[j] = __float2half_rn(x[j]);
-            uint4* oh = reinterpret_cast<uint4*>(a.out_hi + opix * a.out_C + c0);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) oh[g] = reinterpret_cast<const uint4*>(hi)[g];
-            if (a.out_lo) {
-              __align__(16) __half lo[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) lo[j] = __float2half_rn(x[j] - __half2float(hi[j]));
-              uint4* ol = reinterpret_cast<uint4*>(a.out_lo + opix * a.out_C + c0);
-#pragma unroll
-              for (int g = 0; g < 4; ++g) ol[g] = reinterpret_cast<const uint4*>(lo)[g];
-            }
+        }
+        fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO_hi, st, c0, x0, y0);
+          if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, c0, x0, y0);
+          bulk_commit();
+          if (a.has_res) {                        // refill this buffer with the residual two chunks ahead
+            bulk_wait_read<0>();
+            int nit = it, nch = ch + 2;
+            while (nch >= nchunks) { nch -= nchunks; ++nit; }
+            issue_res(nit, nch, sb);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
-      if (++buf == 2) { buf = 0; bphase ^= 1; }
+      if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
     }
+    if (lane == 0) bulk_wait_all();               // all output bytes are in global memory before the CTA exits
   }
   tc_fence_before();
   __syncthreads();
+  if (a.mc > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
   if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------ host side
+int g_tc_multicast = 1;   // SFD2_TC_MULTICAST=0 in the environment disables the 2-CTA weight multicast
+
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
   if (!fn) {
@@ -242,14 +342,21 @@ PFN_encodeTiled get_encode_tiled() {
 
 int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+  return make_tmap(tm, base, rank, dims, strides_bytes, box, 0, 128);
+}
+
+// is_f32: element type fp32 instead of fp16; swizzle: 64 or 128 (bytes)
+int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, int is_f32, int swizzle) {
   PFN_encodeTiled enc = get_encode_tiled();
   SFD2_CHECK(enc != nullptr, SFD2_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
-                         bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUresult r = enc(tm, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                         const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SFD2_CHECK(r == CUDA_SUCCESS, SFD2_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
   return SFD2_OK;
@@ -290,7 +397,13 @@ int tc_encode_weights(Layer& L) {
   const uint32_t box[2] = {64u, (uint32_t)(diag ? 64 : L.cout_tc)};
   int rc = make_tmap_f16(&L.tm_w_hi, L.w_hi, 2, dims, strides, box);
   if (rc) return rc;
-  return make_tmap_f16(&L.tm_w_lo, L.w_lo, 2, dims, strides, box);
+  rc = make_tmap_f16(&L.tm_w_lo, L.w_lo, 2, dims, strides, box);
+  if (rc) return rc;
+  // half-slab boxes for the 2-CTA multicast path (each CTA fetches n_mma/2 rows)
+  const uint32_t hbox[2] = {64u, box[1] / 2};
+  rc = make_tmap_f16(&L.tm_w_hi_half, L.w_hi, 2, dims, strides, hbox);
+  if (rc) return rc;
+  return make_tmap_f16(&L.tm_w_lo_half, L.w_lo, 2, dims, strides, hbox);
 }
 
 // Activation tensor maps: [0] stride-1 view {C, W, H}, box {64,16,8};
@@ -311,8 +424,18 @@ int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensor
   }
 }
 
-int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, float* out_f32, int split, int num_sms,
-                   cudaStream_t st) {
+// Epilogue-side view of an activation plane: {C, W, H}, box {32 ch, 16 px, 2 rows}.  fp16 planes use the
+// 64-byte swizzle (64-byte rows in the staging tile), fp32 head outputs the 128-byte swizzle.
+int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32) {
+  const uint64_t es = is_f32 ? 4 : 2;
+  const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
+  const uint64_t str[2] = {(uint64_t)C * es, (uint64_t)Wp * C * es};
+  const uint32_t box[3] = {32u, (uint32_t)TC_TILE_W, 2u};
+  return make_tmap(tm, base, 3, dims, str, box, is_f32, is_f32 ? 128 : 64);
+}
+
+int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
+                   int num_sms, cudaStream_t st) {
   SFD2_CHECK(in.tm != nullptr && in.hi != nullptr, SFD2_ERR_ARG, "conv_tc(%s): input has no tensor maps", L.name.c_str());
   SFD2_CHECK(in.C == L.cin && in.C % 64 == 0, SFD2_ERR_ARG, "conv_tc(%s): cin %d", L.name.c_str(), in.C);
   SFD2_CHECK(split == 1 || split == 3, SFD2_ERR_ARG, "conv_tc: split must be 1 or 3");
@@ -325,30 +448,61 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, float
   a.kchunks = L.cin / 64;
   a.n_mma = diag ? 64 : L.cout_tc;
   a.acc_cols = L.cout_tc;
+  // (block-diagonal grouped layers add mostly exact zeros, so their single accumulator is already accurate)
+  a.corr = (split == 3 && L.k == 3 && !diag) ? 1 : 0;
+  a.buf_stride = a.acc_cols * (1 + a.corr);
+  // the epilogue reads 32-column chunks, so an 80-wide accumulator (headP) is over-read by 16 columns:
+  // keep that inside the allocation
+  int over = a.corr * a.acc_cols + round_up(L.cout, 32) - a.buf_stride;
+  if (over < 0) over = 0;
+  SFD2_CHECK(a.buf_stride + over <= 512, SFD2_ERR_ARG, "conv_tc(%s): accumulator too wide", L.name.c_str());
+  a.nbuf = (2 * a.buf_stride + over <= 512) ? 2 : 1;
   int tc = 32;
-  while (tc < 2 * a.acc_cols) tc <<= 1;
-  SFD2_CHECK(tc <= 512, SFD2_ERR_ARG, "conv_tc(%s): accumulator too wide", L.name.c_str());
+  while (tc < a.nbuf * a.buf_stride + over) tc <<= 1;
   a.tmem_cols = tc;
   a.cout = L.cout; a.relu = L.relu; a.split = split;
   a.b_bytes = a.n_mma * 128;
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;
-  int stages = (smem_max - 2048) / a.stage_bytes;
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + 256;   // alignment slack, staging, bias, barriers
+  int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
   a.stages = stages;
   a.bias = L.b_dev;
-  a.out_hi = out_f32 ? nullptr : out.hi;
-  a.out_lo = (out_f32 || split == 1) ? nullptr : out.lo;
-  a.out_f32 = out_f32;
-  a.out_Wp = out.Wp; a.out_C = out.C;
-  a.res_hi = res ? res->hi : nullptr;
-  a.res_lo = (res && split == 3) ? res->lo : nullptr;
-  const size_t smem = (size_t)stages * a.stage_bytes + 1024 + 256;
+  a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
+  a.has_res = res ? (split == 3 ? 2 : 1) : 0;
+  SFD2_CHECK(out_f32_map || out.tm_st, SFD2_ERR_ARG, "conv_tc(%s): output has no store maps", L.name.c_str());
+  SFD2_CHECK(!res || res->tm_st, SFD2_ERR_ARG, "conv_tc(%s): residual has no store maps", L.name.c_str());
+  SFD2_CHECK(L.cout <= 256, SFD2_ERR_ARG, "conv_tc(%s): cout > 256", L.name.c_str());
+  const CUtensorMap& o_hi = out_f32_map ? *out_f32_map : out.tm_st[0];
+  const CUtensorMap& o_lo = out_f32_map ? *out_f32_map : out.tm_st[1];
+  const CUtensorMap& r_hi = res ? res->tm_st[0] : o_hi;
+  const CUtensorMap& r_lo = res ? res->tm_st[1] : o_lo;
+  const size_t smem = (size_t)stages * a.stage_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (L.stride == 2 ? 2 : 0);
-  const int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
-  tc_conv_kernel<<<grid, TC_THREADS, smem, st>>>(tmA[0], tmA[1], L.tm_w_hi, L.tm_w_lo, a);
+  // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
+  a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
+  int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
+  if (a.mc > 1 && grid > num_sms) grid -= 2;
+  a.iters = cdiv(a.num_tiles, grid);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)a.mc;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const CUtensorMap& wb_hi = (a.mc > 1) ? L.tm_w_hi_half : L.tm_w_hi;
+  const CUtensorMap& wb_lo = (a.mc > 1) ? L.tm_w_lo_half : L.tm_w_lo;
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

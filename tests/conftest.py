@@ -5,8 +5,9 @@ import numpy as np
 import pytest
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-if REPO not in sys.path:
-    sys.path.insert(0, REPO)
+for _p in (REPO, os.path.join(REPO, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 GOLDEN = os.path.join(REPO, "tests", "golden")
 WEIGHTS = os.path.join(REPO, "weights", "ressegnetv2_wapv2.npz")
 
