@@ -144,6 +144,9 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* ctx, const float* x_host, int h, int w, i
                     const float* b_host, int cout, int ksize, int stride, int groups, int relu,
                     int precision, float* y_host);
 
+/* Hardware probe used while designing the conv kernel's operand staging (tools/umma_probe.py). */
+SFD2_API int sfd2_debug_umma_probe(int pitch, int ky, int kx, int use_base_offset, int pattern, float* out_host);
+
 #ifdef __cplusplus
 }
 #endif

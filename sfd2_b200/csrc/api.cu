@@ -48,9 +48,9 @@ struct sfd2_ctx {
   int wsH = 0, wsW = 0;
   bool have_f32 = false, have_tc = false;
   Act acts[NUM_ACTS];
-  CUtensorMap maps[NUM_ACTS][4];
-  CUtensorMap st_maps[NUM_ACTS][2];
-  CUtensorMap map_logits, map_desc;   // fp32 head outputs (TMA store views)
+  CUtensorMap maps[NUM_ACTS][6];
+  CUtensorMap st_maps[NUM_ACTS][4];
+  CUtensorMap map_logits[2], map_desc[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
   unsigned long long *cand = nullptr, *scratch = nullptr;
@@ -161,20 +161,23 @@ static int ensure_workspace(sfd2_ctx* c, int H, int W, int prec) {
       SFD2_CUDA(cudaMalloc(&a.lo, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.hi, 0, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.lo, 0, a.elems() * sizeof(__half)));
-      int rc = tc_make_act_maps(a, a.hi, &c->maps[i][0], &c->maps[i][2]);
+      int rc = tc_make_act_maps(a, a.hi, &c->maps[i][0], &c->maps[i][2], &c->maps[i][4]);
       if (rc) return rc;
-      rc = tc_make_act_maps(a, a.lo, &c->maps[i][1], &c->maps[i][3]);
+      rc = tc_make_act_maps(a, a.lo, &c->maps[i][1], &c->maps[i][3], &c->maps[i][5]);
       if (rc) return rc;
       a.tm = c->maps[i];
-      rc = tc_make_store_map(&c->st_maps[i][0], a.hi, a.C, a.W, a.H, a.Wp, 0);
-      if (rc) return rc;
-      rc = tc_make_store_map(&c->st_maps[i][1], a.lo, a.C, a.W, a.H, a.Wp, 0);
+      for (int b = 0; b < 2 && !rc; ++b) {
+        rc = tc_make_store_map(&c->st_maps[i][2 * b], a.hi, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
+        if (!rc) rc = tc_make_store_map(&c->st_maps[i][2 * b + 1], a.lo, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
+      }
       if (rc) return rc;
       a.tm_st = c->st_maps[i];
     }
-    int rc = tc_make_store_map(&c->map_logits, c->logits, 80, c->W8, c->H8, c->W8, 1);
-    if (rc) return rc;
-    rc = tc_make_store_map(&c->map_desc, c->descmap, 128, c->W4, c->H4, c->W4, 1);
+    int rc = 0;
+    for (int b = 0; b < 2 && !rc; ++b) {
+      rc = tc_make_store_map(&c->map_logits[b], c->logits, 80, c->W8, c->H8, c->W8, 1, b ? 8 : 16);
+      if (!rc) rc = tc_make_store_map(&c->map_desc[b], c->descmap, 128, c->W4, c->H4, c->W4, 1, b ? 8 : 16);
+    }
     if (rc) return rc;
     c->have_tc = true;
   }
@@ -231,8 +234,8 @@ static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W
   Act logit_act; logit_act.f32 = c->logits; logit_act.H = c->H8; logit_act.W = c->W8; logit_act.Wp = c->W8; logit_act.Hp = c->H8; logit_act.C = 80;
   Act desc_act;  desc_act.f32 = c->descmap; desc_act.H = c->H4; desc_act.W = c->W4; desc_act.Wp = c->W4; desc_act.Hp = c->H4; desc_act.C = 128;
   if (tc) {
-    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, &c->map_logits, split, c->num_sms, st));
-    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, &c->map_desc, split, c->num_sms, st));
+    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, c->map_logits, split, c->num_sms, st));
+    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, c->map_desc, split, c->num_sms, st));
   } else {
     RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
     RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
@@ -275,6 +278,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   SFD2_CHECK(nl > 0 && nl < 64 && 16 + (size_t)nl * sizeof(BlobLayer) <= nbytes, SFD2_ERR_WEIGHTS, "bad layer count %u", nl);
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
   cudaDeviceProp prop;
@@ -616,7 +620,7 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin,
   in.H = h; in.W = w; in.C = cin; in.Hp = round_up(h, 2); in.Wp = round_up(w, 2);
   out.H = conv_out(h, stride); out.W = conv_out(w, stride); out.C = cout; out.Hp = round_up(out.H, 2); out.Wp = round_up(out.W, 2);
   const int outC_f32 = round_up(cout, 16);
-  CUtensorMap maps[4];
+  CUtensorMap maps[6];
   float* yf = nullptr;
   std::vector<float> xin(in.elems(), 0.f);
   for (int yy = 0; yy < h; ++yy) memcpy(xin.data() + (size_t)yy * in.Wp * cin, x + (size_t)yy * w * cin, (size_t)w * cin * 4);
@@ -638,14 +642,15 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin,
     DBG_CUDA(cudaMalloc(&in.lo, in.elems() * 2));
     DBG_CUDA(cudaMemcpy(in.hi, hi.data(), in.elems() * 2, cudaMemcpyHostToDevice));
     DBG_CUDA(cudaMemcpy(in.lo, lo.data(), in.elems() * 2, cudaMemcpyHostToDevice));
-    rc = tc_make_act_maps(in, in.hi, &maps[0], &maps[2]);
-    if (!rc) rc = tc_make_act_maps(in, in.lo, &maps[1], &maps[3]);
+    rc = tc_make_act_maps(in, in.hi, &maps[0], &maps[2], &maps[4]);
+    if (!rc) rc = tc_make_act_maps(in, in.lo, &maps[1], &maps[3], &maps[5]);
     in.tm = maps;
     Act o2 = out; o2.Wp = out.W; o2.Hp = out.H; o2.C = outC_f32;
     DBG_CUDA(cudaMalloc(&yf, o2.elems() * 4));
-    CUtensorMap omap;
-    if (!rc) rc = tc_make_store_map(&omap, yf, o2.C, o2.W, o2.H, o2.Wp, 1);
-    if (!rc) rc = launch_conv_tc(in, L, o2, nullptr, &omap, precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->num_sms, nullptr);
+    CUtensorMap omap[2];
+    if (!rc) rc = tc_make_store_map(&omap[0], yf, o2.C, o2.W, o2.H, o2.Wp, 1, 16);
+    if (!rc) rc = tc_make_store_map(&omap[1], yf, o2.C, o2.W, o2.H, o2.Wp, 1, 8);
+    if (!rc) rc = launch_conv_tc(in, L, o2, nullptr, omap, precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->num_sms, nullptr);
     if (!rc) {
       DBG_CUDA(cudaDeviceSynchronize());
       std::vector<float> tmp(o2.elems());

@@ -42,8 +42,8 @@ struct Act {
   __half* hi = nullptr;  // TC modes: x ~ hi (+ lo)
   __half* lo = nullptr;
   int H = 0, W = 0, C = 0, Hp = 0, Wp = 0;
-  const CUtensorMap* tm = nullptr;     // [s1_hi, s1_lo, s2_hi, s2_lo] TMA load views (tcgen05 modes)
-  const CUtensorMap* tm_st = nullptr;  // [hi, lo] TMA store views (epilogue output / residual input)
+  const CUtensorMap* tm = nullptr;     // [s1_hi, s1_lo, s2_hi, s2_lo, halo_hi, halo_lo] TMA load views
+  const CUtensorMap* tm_st = nullptr;  // [hi, lo] 16x2-pixel boxes, [hi, lo] 8x4-pixel boxes: TMA store views
   size_t elems() const { return (size_t)Hp * Wp * C; }
 };
 
@@ -79,8 +79,8 @@ int launch_softmax65(const float* logits, int npix, float* semi, cudaStream_t st
 int launch_l2norm128(float* desc, int npix, cudaStream_t st);
 // tc_conv.cu
 int tc_encode_weights(Layer& L);
-int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2);
-int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32);
+int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo);
+int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w);
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
                    int num_sms, cudaStream_t st);
 // post.cu
@@ -113,7 +113,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_multicast;
+extern int g_tc_multicast, g_tc_halo;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

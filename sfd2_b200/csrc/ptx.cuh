@@ -178,6 +178,17 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
 }
+// same layout, but the 8-row groups are `sbo_bytes` apart (a halo tile whose pixel rows are wider than 8)
+// and the start address may be any 128-byte row of the TMA-written tile
+__device__ __forceinline__ uint64_t make_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // advance a SW128 K-major descriptor by k UMMA_K steps (16 fp16 = 32 bytes inside the swizzle atom)
 __device__ __forceinline__ uint64_t desc_advance_k(uint64_t d, int k) { return d + (uint64_t)((k * 32) >> 4); }
 

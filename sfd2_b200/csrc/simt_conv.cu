@@ -25,56 +25,54 @@ conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const float* _
               const float* __restrict__ bias, float* __restrict__ out_f32, __half* __restrict__ out_hi,
               __half* __restrict__ out_lo) {
   __shared__ __align__(16) float ws[27 * 64 + 64];
+  __shared__ float patch[3][3][132];   // [ky][c][column x0-1 .. x0+128], normalised, zero outside the image
+  const int x0 = blockIdx.x * 128, y = blockIdx.y;
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = wt[i];
   if (threadIdx.x < 64) ws[27 * 64 + threadIdx.x] = bias[threadIdx.x];
+  // the block's 3 x 130 x 3 input patch: every value is normalised ONCE with the reference's exact
+  // (x - mean) / std (IEEE division, tvf.Normalize) instead of once per tap per thread
+  for (int i = threadIdx.x; i < 3 * 3 * 130; i += blockDim.x) {
+    const int col = i % 130, c = (i / 130) % 3, ky = i / 390;
+    const int iy = y + ky - 1, ix = x0 + col - 1;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      float raw;
+      if (IMG_DTYPE == SFD2_IMG_F32_NCHW)
+        raw = __ldg(reinterpret_cast<const float*>(img) + ((size_t)c * H + iy) * W + ix);
+      else
+        raw = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(img) + ((size_t)iy * W + ix) * 3 + c), 255.0f);
+      const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+      const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+      v = __fdiv_rn(__fsub_rn(raw, mean), stdv);
+    }
+    patch[ky][c][col] = v;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cq = warp & 3;
-  const int x = blockIdx.x * 128 + ((warp >> 2) * 32 + lane) * 2;
-  const int y = blockIdx.y;
+  const int px = ((warp >> 2) * 32 + lane) * 2;   // first pixel of this thread's pair, relative to x0
+  const int x = x0 + px;
   if (x >= W) return;
-  const float mean[3] = {0.485f, 0.456f, 0.406f};
-  const float stdv[3] = {0.229f, 0.224f, 0.225f};
-  float in[3][4][3];  // [ky][column x-1..x+2][c], normalised; zero padding AFTER normalisation
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = y + ky - 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ix = x + q - 1;
-      const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = 0.f;
-        if (ok) {
-          float raw;
-          if (IMG_DTYPE == SFD2_IMG_F32_NCHW)
-            raw = __ldg(reinterpret_cast<const float*>(img) + ((size_t)c * H + iy) * W + ix);
-          else
-            raw = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(img) + ((size_t)iy * W + ix) * 3 + c), 255.0f);
-          v = __fdiv_rn(__fsub_rn(raw, mean[c]), stdv[c]);
-        }
-        in[ky][q][c] = v;
-      }
-    }
-  }
   float acc[2][16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = ws[27 * 64 + cq * 16 + j];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx)
+    for (int c = 0; c < 3; ++c) {
+      float in[4];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int q = 0; q < 4; ++q) in[q] = patch[ky][c][px + q];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
         const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + cq * 16);
         float wv[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) { const float4 t = wr[g]; wv[4 * g] = t.x; wv[4 * g + 1] = t.y; wv[4 * g + 2] = t.z; wv[4 * g + 3] = t.w; }
-        const float a0 = in[ky][kx][c], a1 = in[ky][kx + 1][c];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { acc[0][j] = fmaf(a0, wv[j], acc[0][j]); acc[1][j] = fmaf(a1, wv[j], acc[1][j]); }
+        for (int j = 0; j < 16; ++j) { acc[0][j] = fmaf(in[kx], wv[j], acc[0][j]); acc[1][j] = fmaf(in[kx + 1], wv[j], acc[1][j]); }
       }
+    }
 #pragma unroll
   for (int p = 0; p < 2; ++p) {
     if (x + p >= W) break;

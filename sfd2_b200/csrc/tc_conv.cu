@@ -44,6 +44,13 @@ struct TcConvArgs {
   int nbuf;        // accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
   int buf_stride;  // TMEM columns per buffer = acc_cols * (1 + corr)
   int stages, stage_bytes, b_bytes;
+  // "halo" staging for stride-1 3x3 layers: the tile is 16 rows x 8 px and ONE {64 ch, 10 px, 18 rows} box per
+  // 64-channel chunk serves all nine taps - each tap's A operand is the same smem tile read through a UMMA
+  // descriptor whose start address is shifted by (ky*10 + kx) pixel rows and whose 8-row-group stride is one
+  // halo row (1280 B).  The swizzle is a function of the absolute smem address, so the shifted views decode
+  // correctly (profiles/r1_umma_halo_probe.log).  A and B then use separate rings.
+  int halo, a_slots, a_slot_bytes, b_stages;
+  int tile_w, tile_h, epi_rows, ring_bytes;
   int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
   const float* bias;
@@ -51,6 +58,9 @@ struct TcConvArgs {
   int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
 };
 
+constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
+constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
+constexpr int TC_HALO_SLOT = 23 * 1024;                                // per plane, 1024-aligned
 constexpr int TC_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 px x 128 B)
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 
@@ -64,14 +74,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* staging = smem + (size_t)a.stages * a.stage_bytes;            // 1024-aligned (stage_bytes % 1024 == 0)
+  uint8_t* staging = smem + (size_t)a.ring_bytes;                        // 1024-aligned
   float* sbias = reinterpret_cast<float*>(staging + TC_STAGING_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* resbar = tempty + 2;                                         // [4 warps][2 buffers]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resbar + 8);
+  uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
+  uint64_t* emptyA = fullA + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -80,7 +92,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (a.split == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
+    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
     for (int i = 0; i < 8; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
@@ -100,13 +113,49 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
+    const bool leader = elect_one();
+    if (leader && a.halo) {
+      const int planes = (a.split == 3) ? 2 : 1;
+      uint8_t* bring = smem + (size_t)a.a_slots * a.a_slot_bytes;
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int it = 0; it < a.iters; ++it) {
+        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&emptyA[sa], pha ^ 1);
+          uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
+          mbar_expect_tx(&fullA[sa], (uint32_t)(planes * TC_HALO_BYTES));
+          tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - 1, y0 - 1);
+          if (planes == 2) tma_load_3d(slot + TC_HALO_SLOT, &tmA_lo, &fullA[sa], kc * 64, x0 - 1, y0 - 1);
+          if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.acc_cols;
+            const int bcol = a.diag ? 0 : kc * 64;
+            for (int pl = 0; pl < planes; ++pl) {
+              mbar_wait(&empty[sb], phb ^ 1);
+              uint8_t* bs = bring + (size_t)sb * a.b_bytes;
+              mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
+              const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
+              if (a.mc > 1) {
+                const int ro = (int)crank * (a.n_mma / 2);
+                tma_load_2d_mc(bs + ro * 128, tb, &full[sb], bcol, brow + ro, cmask);
+              } else {
+                tma_load_2d(bs, tb, &full[sb], bcol, brow);
+              }
+              if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (leader && !a.halo) {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < a.iters; ++it) {
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
-        const int y0 = (tile / a.tiles_x) * TC_TILE_H, x0 = (tile % a.tiles_x) * TC_TILE_W;
+        const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -143,7 +192,59 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    const bool leader = elect_one();
+    if (leader && a.halo) {
+      const uint32_t idesc = make_idesc_f16(128, a.n_mma);
+      const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
+      int sa = 0, sb = 0, buf = 0;
+      uint32_t pha = 0, phb = 0, bphase = 0;
+      for (int it = 0; it < a.iters; ++it) {
+        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+        mbar_wait(&tempty[buf], bphase ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&fullA[sa], pha);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem + (size_t)sa * a.a_slot_bytes);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? kc * 64 : 0));
+          const uint32_t ccol = a.corr ? dcol + (uint32_t)a.acc_cols : dcol;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t off = (uint32_t)(((tap / 3) * TC_HALO_W + (tap % 3)) * 128);
+            const uint64_t da_hi = make_desc_sw128_sbo(abase + off, TC_HALO_W * 128);
+            const uint64_t da_lo = make_desc_sw128_sbo(abase + TC_HALO_SLOT + off, TC_HALO_W * 128);
+            const bool first = (tap == 0) && (a.diag || kc == 0);
+            // weight slab, hi plane: main product, then (exact mode) a_lo * w_hi into the correction accumulator
+            mbar_wait(&full[sb], phb);
+            tc_fence_after();
+            uint64_t db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (first && k == 0) ? 0u : 1u);
+            if (a.split == 3) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, (a.corr && first && k == 0) ? 0u : 1u);
+            }
+            if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+            if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+            if (a.split == 3) {                 // weight slab, lo plane: a_hi * w_lo
+              mbar_wait(&full[sb], phb);
+              tc_fence_after();
+              db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(ccol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
+              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+              if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+            }
+          }
+          umma_commit(&emptyA[sa]);             // halo tile free once all nine taps have read it
+          if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+        if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+      }
+    } else if (leader && !a.halo) {
       const uint32_t idesc = make_idesc_f16(128, a.n_mma);
       int stage = 0;
       uint32_t phase = 0;
@@ -201,8 +302,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // chunk sequence number over (iteration, chunk): staging buffer = seq & 1
     auto tile_xy = [&](int it, int& x0, int& y0) {
       const int tile = blockIdx.x + it * gridDim.x;
-      x0 = (tile % a.tiles_x) * TC_TILE_W;
-      y0 = (tile / a.tiles_x) * TC_TILE_H + 2 * q;
+      x0 = (tile % a.tiles_x) * a.tile_w;
+      y0 = (tile / a.tiles_x) * a.tile_h + a.epi_rows * q;
     };
     auto issue_res = [&](int it, int ch, int sb) {   // lane 0 only
       if (it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
@@ -406,9 +507,17 @@ int tc_encode_weights(Layer& L) {
   return make_tmap_f16(&L.tm_w_lo_half, L.w_lo, 2, dims, strides, hbox);
 }
 
-// Activation tensor maps: [0] stride-1 view {C, W, H}, box {64,16,8};
-//                         [1] stride-2 view {C, 2, Wp/2, 2, Hp/2}, box {64,1,16,1,8}.
-int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2) {
+// Activation tensor maps: s1   stride-1 view {C, W, H}, box {64,16,8}          (per-tap loads, 1x1 layers)
+//                         s2   stride-2 view {C, 2, Wp/2, 2, Hp/2}, box {64,1,16,1,8}
+//                         halo stride-1 view {C, W, H}, box {64,10,18}          (one load per chunk, 3x3 layers)
+int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo) {
+  {
+    const uint64_t dims[3] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H};
+    const uint64_t str[2] = {(uint64_t)t.C * 2, (uint64_t)t.Wp * t.C * 2};
+    const uint32_t box[3] = {64u, (uint32_t)TC_HALO_W, (uint32_t)TC_HALO_H};
+    int rc = make_tmap_f16(halo, base, 3, dims, str, box);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[3] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H};
     const uint64_t str[2] = {(uint64_t)t.C * 2, (uint64_t)t.Wp * t.C * 2};
@@ -426,14 +535,18 @@ int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensor
 
 // Epilogue-side view of an activation plane: {C, W, H}, box {32 ch, 16 px, 2 rows}.  fp16 planes use the
 // 64-byte swizzle (64-byte rows in the staging tile), fp32 head outputs the 128-byte swizzle.
-int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32) {
+// box_w x box_h = 16 x 2 (8 x 16 tiles) or 8 x 4 (16 x 8 "halo" tiles): one epilogue warp's 32 pixels
+int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w) {
   const uint64_t es = is_f32 ? 4 : 2;
   const uint64_t dims[3] = {(uint64_t)C, (uint64_t)W, (uint64_t)H};
   const uint64_t str[2] = {(uint64_t)C * es, (uint64_t)Wp * C * es};
-  const uint32_t box[3] = {32u, (uint32_t)TC_TILE_W, 2u};
+  const uint32_t box[3] = {32u, (uint32_t)box_w, (uint32_t)(32 / box_w)};
   return make_tmap(tm, base, 3, dims, str, box, is_f32, is_f32 ? 128 : 64);
 }
 
+int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
+
+// out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
                    int num_sms, cudaStream_t st) {
   SFD2_CHECK(in.tm != nullptr && in.hi != nullptr, SFD2_ERR_ARG, "conv_tc(%s): input has no tensor maps", L.name.c_str());
@@ -442,8 +555,12 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const bool diag = (L.groups == 32);
   TcConvArgs a{};
   a.Ho = out.H; a.Wo = out.W;
-  a.tiles_x = cdiv(out.W, TC_TILE_W);
-  a.num_tiles = a.tiles_x * cdiv(out.H, TC_TILE_H);
+  a.halo = (g_tc_halo && L.k == 3 && L.stride == 1) ? 1 : 0;
+  a.tile_w = a.halo ? 8 : TC_TILE_W;
+  a.tile_h = a.halo ? 16 : TC_TILE_H;
+  a.epi_rows = a.halo ? 4 : 2;
+  a.tiles_x = cdiv(out.W, a.tile_w);
+  a.num_tiles = a.tiles_x * cdiv(out.H, a.tile_h);
   a.taps = L.k * L.k; a.stride = L.stride; a.diag = diag ? 1 : 0;
   a.kchunks = L.cin / 64;
   a.n_mma = diag ? 64 : L.cout_tc;
@@ -464,24 +581,35 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.b_bytes = a.n_mma * 128;
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;
-  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + 256;   // alignment slack, staging, bias, barriers
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + 512;   // alignment slack, staging, bias, barriers
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
   a.stages = stages;
+  a.ring_bytes = stages * a.stage_bytes;
+  if (a.halo) {
+    a.a_slot_bytes = (split == 3 ? 2 : 1) * TC_HALO_SLOT;
+    a.a_slots = 2;
+    int bs = (smem_max - smem_fixed - a.a_slots * a.a_slot_bytes) / a.b_bytes;
+    if (bs > TC_MAX_STAGES) bs = TC_MAX_STAGES;
+    SFD2_CHECK(bs >= 2, SFD2_ERR_ARG, "conv_tc(%s): weight ring does not fit", L.name.c_str());
+    a.b_stages = bs;
+    a.ring_bytes = a.a_slots * a.a_slot_bytes + bs * a.b_bytes;
+  }
   a.bias = L.b_dev;
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
   SFD2_CHECK(out_f32_map || out.tm_st, SFD2_ERR_ARG, "conv_tc(%s): output has no store maps", L.name.c_str());
   SFD2_CHECK(!res || res->tm_st, SFD2_ERR_ARG, "conv_tc(%s): residual has no store maps", L.name.c_str());
   SFD2_CHECK(L.cout <= 256, SFD2_ERR_ARG, "conv_tc(%s): cout > 256", L.name.c_str());
-  const CUtensorMap& o_hi = out_f32_map ? *out_f32_map : out.tm_st[0];
-  const CUtensorMap& o_lo = out_f32_map ? *out_f32_map : out.tm_st[1];
+  const int so = a.halo ? 2 : 0;   // store maps: [hi, lo] with 16x2 boxes, then [hi, lo] with 8x4 boxes
+  const CUtensorMap& o_hi = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so];
+  const CUtensorMap& o_lo = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so + 1];
   const CUtensorMap& r_hi = res ? res->tm_st[0] : o_hi;
   const CUtensorMap& r_lo = res ? res->tm_st[1] : o_lo;
-  const size_t smem = (size_t)stages * a.stage_bytes + smem_fixed;
+  const size_t smem = (size_t)a.ring_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const CUtensorMap* tmA = in.tm + (L.stride == 2 ? 2 : 0);
+  const CUtensorMap* tmA = in.tm + (a.halo ? 4 : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
   a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;

@@ -6,6 +6,8 @@
 // ~22 bits): split==3 issues d0_hi*d1_hi + d0_hi*d1_lo + d0_lo*d1_hi into one fp32 accumulator,
 // which reproduces the fp32 reference arg-max on real SFD2 descriptors;
 // split==1 is the single-pass fp16 variant.
+#include <math_constants.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -146,35 +148,37 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
-      unsigned long long rbest = 0ull;
+      float rbest = -CUDART_INF_F;              // plain float compares in the loops; keys are built once per tile
+      int rbest_j = -1;
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t v[32];
         tmem_ld32(taddr + ch * 32, v);
         tmem_ld_wait();
         const int jbase = c0 + ch * 32;
-        // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row)
+        // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row); strict '>' keeps
+        // the lowest column among equal values
+        const int cols_valid = min(32, a.n1 - jbase);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (jbase + j < a.n1) {
-            const unsigned long long k = m_key(__uint_as_float(v[j]), jbase + j);
-            rbest = (k > rbest) ? k : rbest;
-          }
+          const float s = __uint_as_float(v[j]);
+          if (j < cols_valid && s > rbest) { rbest = s; rbest_j = jbase + j; }
         }
         // column arg-max over this warp's 32 rows: transpose through smem, one column per lane
 #pragma unroll
         for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = __uint_as_float(v[j]);
         __syncwarp();
         const int rows_valid = min(32, a.n0 - (r0 + q * 32));
-        float best = 0.f;
+        float best = -CUDART_INF_F;
         int besti = -1;
-        for (int r = 0; r < rows_valid; ++r) {
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
           const float s = xp[r * 33 + lane];
-          if (besti < 0 || s > best) { best = s; besti = r; }
+          if (r < rows_valid && s > best) { best = s; besti = r; }
         }
         __syncwarp();
-        if (besti >= 0 && jbase + lane < a.n1) atomicMax(a.col_key + jbase + lane, m_key(best, r0 + q * 32 + besti));
+        if (besti >= 0 && lane < cols_valid) atomicMax(a.col_key + jbase + lane, m_key(best, r0 + q * 32 + besti));
       }
-      if (i < a.n0 && rbest) atomicMax(a.row_key + i, rbest);
+      if (i < a.n0 && rbest_j >= 0) atomicMax(a.row_key + i, m_key(rbest, rbest_j));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
