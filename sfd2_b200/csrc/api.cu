@@ -39,12 +39,8 @@ struct BlobLayer {
 
 enum ActId { A1A, A1B, A2A, A2B, A3A, A3B, T1, T2, BA, BB, PA, DA, NUM_ACTS };
 
-struct sfd2_ctx {
-  int device = 0, num_sms = 148;
-  std::vector<Layer> layers;
-  std::map<std::string, int> lidx;
-  cudaStream_t stream = nullptr;  // used by the *_host entry points
-  // extract workspace (sized for one image of wsH x wsW)
+// per-image extract workspace (activations, TMA views, head buffers, candidate list), sized for wsH x wsW
+struct Ws {
   int wsH = 0, wsW = 0;
   bool have_f32 = false, have_tc = false;
   Act acts[NUM_ACTS];
@@ -56,6 +52,17 @@ struct sfd2_ctx {
   unsigned long long *cand = nullptr, *scratch = nullptr;
   int cap = 0;
   int *counter = nullptr, *status = nullptr;
+};
+
+struct sfd2_ctx {
+  int device = 0, num_sms = 148;
+  std::vector<Layer> layers;
+  std::map<std::string, int> lidx;
+  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  Ws ws[2];                       // two per-image workspaces: consecutive images of a batch alternate between
+  cudaStream_t aux[2] = {nullptr, nullptr};   // two internal streams so one image's kernel tails overlap the other's
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  int nstreams = 2;
   int debug_flags = 0;
   int last_prec = -1;
   // host-API staging
@@ -101,85 +108,85 @@ static void free_layer(Layer& L) {
   L.w_simt = L.b_dev = nullptr; L.w_hi = L.w_lo = nullptr;
 }
 
-static void free_workspace(sfd2_ctx* c) {
+static void free_workspace(Ws& w) {
   for (int i = 0; i < NUM_ACTS; ++i) {
-    cudaFree(c->acts[i].f32); cudaFree(c->acts[i].hi); cudaFree(c->acts[i].lo);
-    c->acts[i] = Act();
+    cudaFree(w.acts[i].f32); cudaFree(w.acts[i].hi); cudaFree(w.acts[i].lo);
+    w.acts[i] = Act();
   }
-  cudaFree(c->logits); cudaFree(c->semi); cudaFree(c->descmap); cudaFree(c->sta); cudaFree(c->heat); cudaFree(c->nmsdbg);
-  cudaFree(c->cand); cudaFree(c->scratch); cudaFree(c->counter); cudaFree(c->status);
-  c->logits = c->semi = c->descmap = c->sta = c->heat = c->nmsdbg = nullptr;
-  c->cand = c->scratch = nullptr; c->counter = c->status = nullptr;
-  c->wsH = c->wsW = 0; c->have_f32 = c->have_tc = false;
+  cudaFree(w.logits); cudaFree(w.semi); cudaFree(w.descmap); cudaFree(w.sta); cudaFree(w.heat); cudaFree(w.nmsdbg);
+  cudaFree(w.cand); cudaFree(w.scratch); cudaFree(w.counter); cudaFree(w.status);
+  w.logits = w.semi = w.descmap = w.sta = w.heat = w.nmsdbg = nullptr;
+  w.cand = w.scratch = nullptr; w.counter = w.status = nullptr;
+  w.wsH = w.wsW = 0; w.have_f32 = w.have_tc = false;
 }
 
-static int ensure_workspace(sfd2_ctx* c, int H, int W, int prec) {
-  if (c->wsH != H || c->wsW != W) {
-    free_workspace(c);
-    c->wsH = H; c->wsW = W;
-    c->H2 = conv_out(H, 2); c->W2 = conv_out(W, 2);
-    c->H4 = conv_out(c->H2, 2); c->W4 = conv_out(c->W2, 2);
-    c->H8 = conv_out(c->H4, 2); c->W8 = conv_out(c->W4, 2);
-    const int dims[NUM_ACTS][3] = {{H, W, 64}, {c->H2, c->W2, 64}, {c->H2, c->W2, 128}, {c->H4, c->W4, 128},
-                                   {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H4, c->W4, 256},
-                                   {c->H4, c->W4, 256}, {c->H4, c->W4, 256}, {c->H8, c->W8, 256}, {c->H4, c->W4, 256}};
+static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
+  if (w.wsH != H || w.wsW != W) {
+    free_workspace(w);
+    w.wsH = H; w.wsW = W;
+    w.H2 = conv_out(H, 2); w.W2 = conv_out(W, 2);
+    w.H4 = conv_out(w.H2, 2); w.W4 = conv_out(w.W2, 2);
+    w.H8 = conv_out(w.H4, 2); w.W8 = conv_out(w.W4, 2);
+    const int dims[NUM_ACTS][3] = {{H, W, 64}, {w.H2, w.W2, 64}, {w.H2, w.W2, 128}, {w.H4, w.W4, 128},
+                                   {w.H4, w.W4, 256}, {w.H4, w.W4, 256}, {w.H4, w.W4, 256}, {w.H4, w.W4, 256},
+                                   {w.H4, w.W4, 256}, {w.H4, w.W4, 256}, {w.H8, w.W8, c->L("convPa0").cout}, {w.H4, w.W4, c->L("convDa0").cout}};
     for (int i = 0; i < NUM_ACTS; ++i) {
-      Act& a = c->acts[i];
+      Act& a = w.acts[i];
       a.H = dims[i][0]; a.W = dims[i][1]; a.C = dims[i][2];
       a.Hp = round_up(a.H, 2); a.Wp = round_up(a.W, 2);
     }
-    const size_t n8 = (size_t)c->H8 * c->W8, n4 = (size_t)c->H4 * c->W4;
-    SFD2_CUDA(cudaMalloc(&c->logits, n8 * 80 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&c->semi, n8 * 64 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&c->descmap, n4 * 128 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&c->sta, n4 * 3 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&c->heat, (size_t)H * W * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&c->nmsdbg, (size_t)H * W * sizeof(float)));
+    const size_t n8 = (size_t)w.H8 * w.W8, n4 = (size_t)w.H4 * w.W4;
+    SFD2_CUDA(cudaMalloc(&w.logits, n8 * 80 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&w.semi, n8 * 64 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&w.descmap, n4 * 128 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&w.sta, n4 * 3 * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&w.heat, (size_t)H * W * sizeof(float)));
+    SFD2_CUDA(cudaMalloc(&w.nmsdbg, (size_t)H * W * sizeof(float)));
     // NMS survivors are >= 5 px apart except on exact plateaus: H*W/16 leaves 1.5x headroom.
-    c->cap = (int)(((size_t)H * W) / 16) + 4096;
+    w.cap = (int)(((size_t)H * W) / 16) + 4096;
     int cap2 = 1;
-    while (cap2 < c->cap) cap2 <<= 1;
-    SFD2_CUDA(cudaMalloc(&c->cand, (size_t)c->cap * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMalloc(&c->scratch, (size_t)cap2 * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMalloc(&c->counter, sizeof(int)));
-    SFD2_CUDA(cudaMalloc(&c->status, sizeof(int)));
-    SFD2_CUDA(cudaMemset(c->status, 0, sizeof(int)));
+    while (cap2 < w.cap) cap2 <<= 1;
+    SFD2_CUDA(cudaMalloc(&w.cand, (size_t)w.cap * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&w.scratch, (size_t)cap2 * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&w.counter, sizeof(int)));
+    SFD2_CUDA(cudaMalloc(&w.status, sizeof(int)));
+    SFD2_CUDA(cudaMemset(w.status, 0, sizeof(int)));
   }
   const bool want_tc = (prec != SFD2_PREC_FP32);
-  if (!want_tc && !c->have_f32) {
+  if (!want_tc && !w.have_f32) {
     for (int i = 0; i < NUM_ACTS; ++i) {
-      Act& a = c->acts[i];
+      Act& a = w.acts[i];
       SFD2_CUDA(cudaMalloc(&a.f32, a.elems() * sizeof(float)));
       SFD2_CUDA(cudaMemset(a.f32, 0, a.elems() * sizeof(float)));
     }
-    c->have_f32 = true;
+    w.have_f32 = true;
   }
-  if (want_tc && !c->have_tc) {
+  if (want_tc && !w.have_tc) {
     for (int i = 0; i < NUM_ACTS; ++i) {
-      Act& a = c->acts[i];
+      Act& a = w.acts[i];
       SFD2_CUDA(cudaMalloc(&a.hi, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMalloc(&a.lo, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.hi, 0, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.lo, 0, a.elems() * sizeof(__half)));
-      int rc = tc_make_act_maps(a, a.hi, &c->maps[i][0], &c->maps[i][2], &c->maps[i][4]);
+      int rc = tc_make_act_maps(a, a.hi, &w.maps[i][0], &w.maps[i][2], &w.maps[i][4]);
       if (rc) return rc;
-      rc = tc_make_act_maps(a, a.lo, &c->maps[i][1], &c->maps[i][3], &c->maps[i][5]);
+      rc = tc_make_act_maps(a, a.lo, &w.maps[i][1], &w.maps[i][3], &w.maps[i][5]);
       if (rc) return rc;
-      a.tm = c->maps[i];
+      a.tm = w.maps[i];
       for (int b = 0; b < 2 && !rc; ++b) {
-        rc = tc_make_store_map(&c->st_maps[i][2 * b], a.hi, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
-        if (!rc) rc = tc_make_store_map(&c->st_maps[i][2 * b + 1], a.lo, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
+        rc = tc_make_store_map(&w.st_maps[i][2 * b], a.hi, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
+        if (!rc) rc = tc_make_store_map(&w.st_maps[i][2 * b + 1], a.lo, a.C, a.W, a.H, a.Wp, 0, b ? 8 : 16);
       }
       if (rc) return rc;
-      a.tm_st = c->st_maps[i];
+      a.tm_st = w.st_maps[i];
     }
     int rc = 0;
     for (int b = 0; b < 2 && !rc; ++b) {
-      rc = tc_make_store_map(&c->map_logits[b], c->logits, 80, c->W8, c->H8, c->W8, 1, b ? 8 : 16);
-      if (!rc) rc = tc_make_store_map(&c->map_desc[b], c->descmap, 128, c->W4, c->H4, c->W4, 1, b ? 8 : 16);
+      rc = tc_make_store_map(&w.map_logits[b], w.logits, 80, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
+      if (!rc) rc = tc_make_store_map(&w.map_desc[b], w.descmap, 128, w.W4, w.H4, w.W4, 1, b ? 8 : 16);
     }
     if (rc) return rc;
-    c->have_tc = true;
+    w.have_tc = true;
   }
   return SFD2_OK;
 }
@@ -202,12 +209,12 @@ static inline void prof_end(sfd2_ctx* c, cudaStream_t st) {
 }
 
 // one image through network + post-processing, all on `st`
-static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W, const sfd2_extract_params* p,
+static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H, int W, const sfd2_extract_params* p,
                        float* kpts, float* scores, float* desc, int32_t* count, cudaStream_t st) {
   const int prec = p->precision;
   const bool tc = prec != SFD2_PREC_FP32;
   const int split = (prec == SFD2_PREC_TC_EXACT) ? 3 : 1;
-  Act* A = c->acts;
+  Act* A = w.acts;
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
@@ -231,23 +238,23 @@ static int extract_one(sfd2_ctx* c, const void* img, int img_dtype, int H, int W
   RUN(conv("convPa0", BA, PA, -1));
   RUN(conv("convDa0", BA, DA, -1));
   // heads: fp32 outputs
-  Act logit_act; logit_act.f32 = c->logits; logit_act.H = c->H8; logit_act.W = c->W8; logit_act.Wp = c->W8; logit_act.Hp = c->H8; logit_act.C = 80;
-  Act desc_act;  desc_act.f32 = c->descmap; desc_act.H = c->H4; desc_act.W = c->W4; desc_act.Wp = c->W4; desc_act.Hp = c->H4; desc_act.C = 128;
+  Act logit_act; logit_act.f32 = w.logits; logit_act.H = w.H8; logit_act.W = w.W8; logit_act.Wp = w.W8; logit_act.Hp = w.H8; logit_act.C = 80;
+  Act desc_act;  desc_act.f32 = w.descmap; desc_act.H = w.H4; desc_act.W = w.W4; desc_act.Wp = w.W4; desc_act.Hp = w.H4; desc_act.C = 128;
   if (tc) {
-    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, c->map_logits, split, c->num_sms, st));
-    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, c->map_desc, split, c->num_sms, st));
+    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, w.map_logits, split, c->num_sms, st));
+    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split, c->num_sms, st));
   } else {
     RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
     RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
   }
-  RUNP("softmax65", launch_softmax65(c->logits, c->H8 * c->W8, c->semi, st));
-  RUNP("l2norm128", launch_l2norm128(c->descmap, c->H4 * c->W4, st));
-  if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), c->sta, st));
-  RUNP("heat", launch_heat(c->semi, c->H8, c->W8, c->sta, c->H4, c->W4, p->use_stability, c->heat, H, W, st));
-  RUNP("nms", launch_nms(c->heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? c->nmsdbg : nullptr, c->cand, c->cap,
-                 c->counter, st));
-  RUNP("select", launch_select(c->cand, c->cap, c->counter, W, p->topk, kpts, scores, count, c->status, c->scratch, st));
-  RUNP("sample", launch_sample(c->descmap, c->H4, c->W4, H, W, kpts, count, p->topk, desc, st));
+  RUNP("softmax65", launch_softmax65(w.logits, w.H8 * w.W8, w.semi, st));
+  RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
+  if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
+  RUNP("heat", launch_heat(w.semi, w.H8, w.W8, w.sta, w.H4, w.W4, p->use_stability, w.heat, H, W, st));
+  RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
+                 w.counter, st));
+  RUNP("select", launch_select(w.cand, w.cap, w.counter, W, p->topk, kpts, scores, count, w.status, w.scratch, st));
+  RUNP("sample", launch_sample(w.descmap, w.H4, w.W4, H, W, kpts, count, p->topk, desc, st));
 #undef RUN
 #undef RUNP
   return SFD2_OK;
@@ -279,8 +286,10 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
+  const char* env_streams = getenv("SFD2_STREAMS");
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
+  if (env_streams) c->nstreams = atoi(env_streams);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; set_error("cudaGetDeviceProperties failed"); return SFD2_ERR_CUDA; }
   c->num_sms = prop.multiProcessorCount;
@@ -317,7 +326,7 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   if (!c) return SFD2_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  free_workspace(c);
+  for (Ws& w : c->ws) free_workspace(w);
   for (Layer& L : c->layers) free_layer(L);
   cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
   cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
@@ -325,6 +334,8 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
+  for (int k = 0; k < 2; ++k) { if (c->aux[k]) cudaStreamDestroy(c->aux[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   delete c;
   return SFD2_OK;
 }
@@ -336,17 +347,41 @@ SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n
   if (rc) return rc;
   SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "bad image dtype %d", img_dtype);
   SFD2_CUDA(cudaSetDevice(c->device));
-  rc = ensure_workspace(c, h, w, p->precision);
-  if (rc) return rc;
+  // A batch alternates between two workspaces on two internal streams (forked from / joined to the caller's
+  // stream with events): every conv kernel is a persistent 1-CTA/SM grid whose last wave leaves SMs idle
+  // (950 tiles over 148 SMs = 6.4 waves), and the other image's next kernel fills them.  Per-launch
+  // profiling needs un-overlapped kernels, so it forces a single stream.
+  const int ns = (n > 1 && c->nstreams > 1 && !c->prof_on) ? 2 : 1;
+  for (int k = 0; k < ns; ++k) {
+    rc = ensure_workspace(c, c->ws[k], h, w, p->precision);
+    if (rc) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ns > 1) {
+    if (!c->ev_fork) {
+      SFD2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      for (int k = 0; k < 2; ++k) {
+        SFD2_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+        SFD2_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+      }
+    }
+    SFD2_CUDA(cudaEventRecord(c->ev_fork, st));
+    for (int k = 0; k < 2; ++k) SFD2_CUDA(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
+  }
   const size_t img_stride = (size_t)h * w * 3 * (img_dtype == SFD2_IMG_F32_NCHW ? 4 : 1);
   const long long before = g_launches;
   for (int i = 0; i < n; ++i) {
-    rc = extract_one(c, static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
+    const int k = (ns > 1) ? (i & 1) : 0;
+    rc = extract_one(c, c->ws[k], static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
                      kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
-                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, st);
+                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, ns > 1 ? c->aux[k] : st);
     if (rc) return rc;
   }
+  if (ns > 1)
+    for (int k = 0; k < 2; ++k) {
+      SFD2_CUDA(cudaEventRecord(c->ev_join[k], c->aux[k]));
+      SFD2_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
+    }
   c->launches += g_launches - before;
   c->last_prec = p->precision;
   return SFD2_OK;
@@ -384,12 +419,14 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
   SFD2_CUDA(cudaMemcpyAsync(scores, c->sc_dev, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(desc, c->de_dev, rows * SFD2_DESC_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(counts, c->cnt_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  int status = 0;
-  SFD2_CUDA(cudaMemcpyAsync(&status, c->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  int status[2] = {0, 0};
+  for (int k = 0; k < 2; ++k)
+    if (c->ws[k].status) SFD2_CUDA(cudaMemcpyAsync(&status[k], c->ws[k].status, sizeof(int), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaStreamSynchronize(st));
-  if (status != 0) {
-    cudaMemset(c->status, 0, sizeof(int));
-    set_error("NMS produced more candidates than the workspace holds (cap %d); results truncated", c->cap);
+  if (status[0] != 0 || status[1] != 0) {
+    for (int k = 0; k < 2; ++k)
+      if (c->ws[k].status) cudaMemset(c->ws[k].status, 0, sizeof(int));
+    set_error("NMS produced more candidates than the workspace holds (cap %d); results truncated", c->ws[0].cap);
     return SFD2_ERR_OVERFLOW;
   }
   return SFD2_OK;
@@ -559,15 +596,16 @@ SFD2_API long long sfd2_debug_fetch(sfd2_ctx* c, const char* name, float* out, l
   cudaDeviceSynchronize();
   const std::string n(name);
   if (n == "enable_nms_out") { c->debug_flags |= 1; return 0; }
-  if (c->wsH == 0) { set_error("no image has been extracted yet"); return SFD2_ERR_ARG; }
+  Ws& w = c->ws[0];   // single-image calls (and the even images of a batch) use workspace 0
+  if (w.wsH == 0) { set_error("no image has been extracted yet"); return SFD2_ERR_ARG; }
   const float* src = nullptr;
   long long cnt = 0;
-  if (n == "heat") { src = c->heat; cnt = (long long)c->wsH * c->wsW; }
-  else if (n == "nms") { src = c->nmsdbg; cnt = (long long)c->wsH * c->wsW; }
-  else if (n == "semi") { src = c->semi; cnt = (long long)c->H8 * c->W8 * 64; }
-  else if (n == "logits") { src = c->logits; cnt = (long long)c->H8 * c->W8 * 80; }
-  else if (n == "desc_map") { src = c->descmap; cnt = (long long)c->H4 * c->W4 * 128; }
-  else if (n == "sta_logits") { src = c->sta; cnt = (long long)c->H4 * c->W4 * 3; }
+  if (n == "heat") { src = w.heat; cnt = (long long)w.wsH * w.wsW; }
+  else if (n == "nms") { src = w.nmsdbg; cnt = (long long)w.wsH * w.wsW; }
+  else if (n == "semi") { src = w.semi; cnt = (long long)w.H8 * w.W8 * 64; }
+  else if (n == "logits") { src = w.logits; cnt = (long long)w.H8 * w.W8 * 80; }
+  else if (n == "desc_map") { src = w.descmap; cnt = (long long)w.H4 * w.W4 * 128; }
+  else if (n == "sta_logits") { src = w.sta; cnt = (long long)w.H4 * w.W4 * 3; }
   if (src) {
     if (cnt > capacity) { set_error("buffer too small: need %lld floats", cnt); return SFD2_ERR_ARG; }
     if (cudaMemcpy(out, src, (size_t)cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return SFD2_ERR_CUDA; }
@@ -578,7 +616,7 @@ SFD2_API long long sfd2_debug_fetch(sfd2_ctx* c, const char* name, float* out, l
                                                  {"out4", BA}, {"rb1", BB}, {"convPa0", PA}, {"convDa0", DA}};
   auto it = ids.find(n);
   if (it == ids.end()) { set_error("unknown intermediate '%s'", name); return SFD2_ERR_ARG; }
-  const Act& a = c->acts[it->second];
+  const Act& a = w.acts[it->second];
   cnt = (long long)a.H * a.W * a.C;
   if (cnt > capacity) { set_error("buffer too small: need %lld floats", cnt); return SFD2_ERR_ARG; }
   const bool tc = (c->last_prec != SFD2_PREC_FP32);
