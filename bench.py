@@ -220,17 +220,27 @@ def run_ours(args):
     ms_clean = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: the reference-facing call with HOST buffers, one image per call ----
+    # ---- e2e: HOST buffers in, HOST features out, copies inside the timed region ----
+    # (a) the batched C-ABI call sfd2_extract_host on B pinned host images per step (H2D of image i+1 overlaps
+    #     the kernels of image i); (b) the reference-facing single-image call extract_resnet_return.
     model = ex.model
-    n_e2e = max(4, min(B * K, 32))
+    host_batch = torch.cat(host_imgs[:min(B, len(host_imgs))] * ((B + len(host_imgs) - 1) // len(host_imgs)))[:B].pin_memory()
+    for i in range(2):
+        ex.extract_host(host_batch)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        r = ex.extract_host(host_batch)
+    e2e_s = time.perf_counter() - t0
+    n_e2e = B * K
+    n_single = max(4, min(B * K, 24))
     for i in range(2):
         extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
     barrier()
     t0 = time.perf_counter()
-    for i in range(n_e2e):
+    for i in range(n_single):
         r = extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    single_s = time.perf_counter() - t0
 
     # ---- matcher (configs[2]): 4096 x 4096 x 128 mutual NN, device-resident ----
     d0, d1 = synth_descriptors(rank, 4096, 4096)
@@ -302,9 +312,11 @@ def run_ours(args):
                                    f"precision={args.precision}", "image": [H, W], "topk": TOPK, "batch_per_gpu": B,
                        "l2": f"inputs cycle through a {pool_n}-image pool ({pool_n * H * W * 12 / 1e6:.0f} MB > 126 MB L2); "
                              "every image rewrites >1 GB of activations", "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "e2e": {"value": world * n_e2e / e2e_s, "unit": "images/s", "h2d_bytes_per_step": H * W * 3 * 4,
-                    "d2h_bytes_per_step": TOPK * (2 + 1 + 128) * 4 + 4,
-                    "note": "extract_resnet_return(model, pinned host image) per image; a step here is ONE image"},
+            "e2e": {"value": world * n_e2e / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 * 4,
+                    "d2h_bytes_per_step": B * (TOPK * (2 + 1 + 128) * 4 + 4),
+                    "note": f"sfd2_extract_host (C ABI) on {B} pinned host images per step, results to pinned host buffers",
+                    "single_image_call": {"value": world * n_single / single_s, "unit": "images/s",
+                                          "note": "extract_resnet_return(model, pinned host image): one synchronous call per image"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel" if args.precision != "fp32" else "conv_f32_kernel",

@@ -46,8 +46,10 @@ struct Ws {
   Act acts[NUM_ACTS];
   CUtensorMap maps[NUM_ACTS][6];
   CUtensorMap st_maps[NUM_ACTS][4];
+  CUtensorMap map_1a[2];                    // conv1a output rows: box {64 ch, 128 px, 1 row}
   CUtensorMap map_logits[2], map_desc[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
+  float4* nimg = nullptr;  // normalised image, NHWC4 fp32
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
   unsigned long long *cand = nullptr, *scratch = nullptr;
   int cap = 0;
@@ -63,6 +65,8 @@ struct sfd2_ctx {
   cudaStream_t aux[2] = {nullptr, nullptr};   // two internal streams so one image's kernel tails overlap the other's
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   int nstreams = 2;
+  cudaStream_t copy_stream = nullptr;          // H2D of batched host inputs
+  std::vector<cudaEvent_t> img_ready;
   int debug_flags = 0;
   int last_prec = -1;
   // host-API staging
@@ -113,6 +117,7 @@ static void free_workspace(Ws& w) {
     cudaFree(w.acts[i].f32); cudaFree(w.acts[i].hi); cudaFree(w.acts[i].lo);
     w.acts[i] = Act();
   }
+  cudaFree(w.nimg); w.nimg = nullptr;
   cudaFree(w.logits); cudaFree(w.semi); cudaFree(w.descmap); cudaFree(w.sta); cudaFree(w.heat); cudaFree(w.nmsdbg);
   cudaFree(w.cand); cudaFree(w.scratch); cudaFree(w.counter); cudaFree(w.status);
   w.logits = w.semi = w.descmap = w.sta = w.heat = w.nmsdbg = nullptr;
@@ -136,6 +141,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       a.Hp = round_up(a.H, 2); a.Wp = round_up(a.W, 2);
     }
     const size_t n8 = (size_t)w.H8 * w.W8, n4 = (size_t)w.H4 * w.W4;
+    SFD2_CUDA(cudaMalloc(&w.nimg, (size_t)H * W * sizeof(float4)));
     SFD2_CUDA(cudaMalloc(&w.logits, n8 * 80 * sizeof(float)));
     SFD2_CUDA(cudaMalloc(&w.semi, n8 * 64 * sizeof(float)));
     SFD2_CUDA(cudaMalloc(&w.descmap, n4 * 128 * sizeof(float)));
@@ -181,6 +187,13 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       a.tm_st = w.st_maps[i];
     }
     int rc = 0;
+    for (int pl = 0; pl < 2 && !rc; ++pl) {
+      const Act& a = w.acts[A1A];
+      const uint64_t dims[3] = {64, (uint64_t)a.W, (uint64_t)a.H};
+      const uint64_t str[2] = {128, (uint64_t)a.Wp * 128};
+      const uint32_t box[3] = {64u, 128u, 1u};
+      rc = make_tmap(&w.map_1a[pl], pl ? (const void*)a.lo : (const void*)a.hi, 3, dims, str, box, 0, 128);
+    }
     for (int b = 0; b < 2 && !rc; ++b) {
       rc = tc_make_store_map(&w.map_logits[b], w.logits, 80, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
       if (!rc) rc = tc_make_store_map(&w.map_desc[b], w.descmap, 128, w.W4, w.H4, w.W4, 1, b ? 8 : 16);
@@ -218,7 +231,7 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
-  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, st));
+  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, w.nimg, tc ? w.map_1a : nullptr, st));
   auto conv = [&](const char* name, int in, int out, int res) -> int {
     const Layer& L = c->L(name);
     prof_begin(c, (std::string(tc ? "tc_conv:" : "conv_f32:") + name).c_str(), st);
@@ -336,12 +349,15 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   if (c->stream) cudaStreamDestroy(c->stream);
   for (int k = 0; k < 2; ++k) { if (c->aux[k]) cudaStreamDestroy(c->aux[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  for (auto e : c->img_ready) cudaEventDestroy(e);
   delete c;
   return SFD2_OK;
 }
 
-SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
-                     float* kpts, float* scores, float* desc, int32_t* counts, void* stream) {
+// `ready`: optional per-image events (recorded on another stream when that image's bytes are in HBM)
+static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
+                         float* kpts, float* scores, float* desc, int32_t* counts, void* stream, const cudaEvent_t* ready) {
   SFD2_CHECK(c && img && kpts && scores && desc && counts, SFD2_ERR_ARG, "sfd2_extract_dev: NULL argument");
   int rc = check_params(p, n, h, w);
   if (rc) return rc;
@@ -351,7 +367,7 @@ SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n
   // stream with events): every conv kernel is a persistent 1-CTA/SM grid whose last wave leaves SMs idle
   // (950 tiles over 148 SMs = 6.4 waves), and the other image's next kernel fills them.  Per-launch
   // profiling needs un-overlapped kernels, so it forces a single stream.
-  const int ns = (n > 1 && c->nstreams > 1 && !c->prof_on) ? 2 : 1;
+  const int ns = ((n > 1 || ready) && c->nstreams > 1 && !c->prof_on) ? 2 : 1;
   for (int k = 0; k < ns; ++k) {
     rc = ensure_workspace(c, c->ws[k], h, w, p->precision);
     if (rc) return rc;
@@ -372,6 +388,7 @@ SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n
   const long long before = g_launches;
   for (int i = 0; i < n; ++i) {
     const int k = (ns > 1) ? (i & 1) : 0;
+    if (ready) SFD2_CUDA(cudaStreamWaitEvent(ns > 1 ? c->aux[k] : st, ready[i], 0));
     rc = extract_one(c, c->ws[k], static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
                      kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
                      desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, ns > 1 ? c->aux[k] : st);
@@ -385,6 +402,11 @@ SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n
   c->launches += g_launches - before;
   c->last_prec = p->precision;
   return SFD2_OK;
+}
+
+SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
+                     float* kpts, float* scores, float* desc, int32_t* counts, void* stream) {
+  return extract_batch(c, img, img_dtype, n, h, w, p, kpts, scores, desc, counts, stream, nullptr);
 }
 
 SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
@@ -410,10 +432,29 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
     c->out_cap = rows;
   }
   cudaStream_t st = c->stream;
-  SFD2_CUDA(cudaMemcpyAsync(c->img_dev, img, img_bytes, cudaMemcpyHostToDevice, st));
   SFD2_CUDA(cudaMemsetAsync(c->kp_dev, 0, rows * 2 * sizeof(float), st));
   SFD2_CUDA(cudaMemsetAsync(c->sc_dev, 0, rows * sizeof(float), st));
-  rc = sfd2_extract_dev(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st);
+  if (n == 1) {
+    SFD2_CUDA(cudaMemcpyAsync(c->img_dev, img, img_bytes, cudaMemcpyHostToDevice, st));
+    rc = extract_batch(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st, nullptr);
+  } else {
+    // batch: the images stream in on a copy stream, one event per image, so image i+1's H2D overlaps image i's kernels
+    if (!c->copy_stream) SFD2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while ((int)c->img_ready.size() < n) {
+      cudaEvent_t e = nullptr;
+      SFD2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->img_ready.push_back(e);
+    }
+    const size_t one = img_bytes / n;
+    SFD2_CUDA(cudaEventRecord(c->img_ready[0], st));               // previous users of img_dev on st are done
+    SFD2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->img_ready[0], 0));
+    for (int i = 0; i < n; ++i) {
+      SFD2_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(c->img_dev) + i * one, static_cast<const uint8_t*>(img) + i * one, one,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+      SFD2_CUDA(cudaEventRecord(c->img_ready[i], c->copy_stream));
+    }
+    rc = extract_batch(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st, c->img_ready.data());
+  }
   if (rc) return rc;
   SFD2_CUDA(cudaMemcpyAsync(kpts, c->kp_dev, rows * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(scores, c->sc_dev, rows * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -70,8 +70,8 @@ struct TcConvLaunch;  // tc_conv.cu
 
 // ---- kernels' host-side launchers (each returns a sfd2_status) -------------------
 // simt_conv.cu
-int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out,
-                  cudaStream_t st);
+int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out, float4* nimg,
+                  const CUtensorMap* tm1a, cudaStream_t st);
 int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cudaStream_t st);
 // tc_in: 0 = fp32 input, 1 = fp16 hi+lo, 2 = fp16 hi only
 int launch_sta(const Act& in, int tc_in, const Layer& L, float* logits, cudaStream_t st);

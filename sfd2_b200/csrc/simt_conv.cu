@@ -13,79 +13,88 @@
 
 namespace sfd2 {
 
-// ------------------------------------------------------------------------------ conv1a
-// thread = 2 horizontally adjacent pixels x 16 output channels.  The 16-channel chunk is chosen per
-// WARP (warp & 3), so every weight read from shared memory is a warp-uniform broadcast (one wavefront
-// per LDS.128 - the first version read 4 different addresses per warp with bank conflicts and was
-// shared-memory bound at 0.62 ms); lanes are consecutive pixel pairs and write whole 32-byte sectors.
-// Weights + bias sit in shared memory ([tap*3+ci][64]).
-template <int IMG_DTYPE, int TC_OUT>
+// ------------------------------------------------------------------------------ normalise + conv1a
+// norm_kernel: (x - mean) / std with the reference's exact IEEE divisions (tvf.Normalize; u8 inputs are
+// divided by 255 first), once per value, into an NHWC4 fp32 image (r, g, b, 0).  Doing it here instead of
+// inside conv1a removes ~50 division instructions per value per tap-neighbourhood from the conv kernel.
+template <int IMG_DTYPE>
 __global__ void __launch_bounds__(256)
-conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const float* __restrict__ wt /*[27][64]*/,
+norm_kernel(const void* __restrict__ img, int H, int W, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * W) return;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float raw;
+    if (IMG_DTYPE == SFD2_IMG_F32_NCHW) raw = __ldg(reinterpret_cast<const float*>(img) + (size_t)c * H * W + i);
+    else raw = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(img) + (size_t)i * 3 + c), 255.0f);
+    const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+    const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+    v[c] = __fdiv_rn(__fsub_rn(raw, mean), stdv);
+  }
+  out[i] = make_float4(v[0], v[1], v[2], 0.f);
+}
+
+// conv1a: thread = 4 horizontally adjacent pixels x 16 output channels.  The 16-channel chunk is chosen per
+// WARP (warp & 3), so every weight read from shared memory is a warp-uniform broadcast; lanes are consecutive
+// pixel quads and write whole 32-byte sectors.  1728 FMAs per thread against 108 LDS.128 and 18 LDG.128.
+template <int TC_OUT>
+__global__ void __launch_bounds__(128)
+conv1a_kernel(const float4* __restrict__ nimg, int H, int W, int Wp, const float* __restrict__ wt /*[27][64]*/,
               const float* __restrict__ bias, float* __restrict__ out_f32, __half* __restrict__ out_hi,
               __half* __restrict__ out_lo) {
   __shared__ __align__(16) float ws[27 * 64 + 64];
-  __shared__ float patch[3][3][132];   // [ky][c][column x0-1 .. x0+128], normalised, zero outside the image
-  const int x0 = blockIdx.x * 128, y = blockIdx.y;
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = wt[i];
   if (threadIdx.x < 64) ws[27 * 64 + threadIdx.x] = bias[threadIdx.x];
-  // the block's 3 x 130 x 3 input patch: every value is normalised ONCE with the reference's exact
-  // (x - mean) / std (IEEE division, tvf.Normalize) instead of once per tap per thread
-  for (int i = threadIdx.x; i < 3 * 3 * 130; i += blockDim.x) {
-    const int col = i % 130, c = (i / 130) % 3, ky = i / 390;
-    const int iy = y + ky - 1, ix = x0 + col - 1;
-    float v = 0.f;
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      float raw;
-      if (IMG_DTYPE == SFD2_IMG_F32_NCHW)
-        raw = __ldg(reinterpret_cast<const float*>(img) + ((size_t)c * H + iy) * W + ix);
-      else
-        raw = __fdiv_rn((float)__ldg(reinterpret_cast<const unsigned char*>(img) + ((size_t)iy * W + ix) * 3 + c), 255.0f);
-      const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
-      const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
-      v = __fdiv_rn(__fsub_rn(raw, mean), stdv);
-    }
-    patch[ky][c][col] = v;
-  }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cq = warp & 3;
-  const int px = ((warp >> 2) * 32 + lane) * 2;   // first pixel of this thread's pair, relative to x0
-  const int x = x0 + px;
+  const int lane = threadIdx.x & 31, cq = threadIdx.x >> 5;
+  const int x = (blockIdx.x * 32 + lane) * 4;
+  const int y = blockIdx.y;
   if (x >= W) return;
-  float acc[2][16];
+  float acc[4][16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = ws[27 * 64 + cq * 16 + j];
+  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = ws[27 * 64 + cq * 16 + j];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = y + ky - 1;
+    float in[6][3];   // columns x-1 .. x+4 of this row (zero padding outside the image)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float in[4];
+    for (int q = 0; q < 6; ++q) {
+      const int ix = x + q - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(nimg + (size_t)iy * W + ix);
+      in[q][0] = v.x; in[q][1] = v.y; in[q][2] = v.z;
+    }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) in[q] = patch[ky][c][px + q];
+    for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
+      for (int c = 0; c < 3; ++c) {
         const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + cq * 16);
         float wv[16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) { const float4 t = wr[g]; wv[4 * g] = t.x; wv[4 * g + 1] = t.y; wv[4 * g + 2] = t.z; wv[4 * g + 3] = t.w; }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { acc[0][j] = fmaf(in[kx], wv[j], acc[0][j]); acc[1][j] = fmaf(in[kx + 1], wv[j], acc[1][j]); }
-      }
-    }
+        for (int p = 0; p < 4; ++p) {
+          const float a = in[kx + p][c];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
+          for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(a, wv[j], acc[p][j]);
+        }
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
     if (x + p >= W) break;
     const size_t obase = ((size_t)y * Wp + x + p) * 64 + cq * 16;
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[p][j] = fmaxf(acc[p][j], 0.f);
     if (TC_OUT) {
-      __align__(16) __half hi[16];
-      __align__(16) __half lo[16];
+      __align__(16) __half2 hi[8];
+      __align__(16) __half2 lo[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        hi[j] = __float2half_rn(acc[p][j]);
-        lo[j] = __float2half_rn(acc[p][j] - __half2float(hi[j]));
+      for (int j = 0; j < 8; ++j) {
+        hi[j] = __floats2half2_rn(acc[p][2 * j], acc[p][2 * j + 1]);
+        const float2 hf = __half22float2(hi[j]);
+        lo[j] = __floats2half2_rn(acc[p][2 * j] - hf.x, acc[p][2 * j + 1] - hf.y);
       }
       uint4* ph = reinterpret_cast<uint4*>(out_hi + obase);
       uint4* pl = reinterpret_cast<uint4*>(out_lo + obase);
@@ -101,21 +110,113 @@ conv1a_kernel(const void* __restrict__ img, int H, int W, int Wp, const float* _
   }
 }
 
-int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out,
-                  cudaStream_t st) {
-  SFD2_CHECK(L.cin == 3 && L.cout == 64 && L.k == 3, SFD2_ERR_WEIGHTS, "conv1a: unexpected layer shape");
-  // L.w_simt is [tap][ci][cout_pad = 64] fp32 = exactly the [27][64] table the kernel stages in smem
-  dim3 grid(cdiv(W, 128), H), block(256);
-  if (img_dtype == SFD2_IMG_F32_NCHW) {
-    if (tc_out) conv1a_kernel<SFD2_IMG_F32_NCHW, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, nullptr, out.hi, out.lo);
-    else conv1a_kernel<SFD2_IMG_F32_NCHW, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
-  } else if (img_dtype == SFD2_IMG_U8_NHWC) {
-    if (tc_out) conv1a_kernel<SFD2_IMG_U8_NHWC, 1><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, nullptr, out.hi, out.lo);
-    else conv1a_kernel<SFD2_IMG_U8_NHWC, 0><<<grid, block, 0, st>>>(img, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
-  } else {
-    SFD2_CHECK(false, SFD2_ERR_ARG, "unknown image dtype %d", img_dtype);
+// conv1a for the tcgen05 modes: same arithmetic, but the memory side goes through shared memory both ways.
+//  * the block's 3 x 130 normalised input pixels are staged once (coalesced float4 loads);
+//  * a thread owns pixels lane, lane+32, lane+64, lane+96 of the block's 128-pixel row segment and the warp's
+//    16-channel chunk, so its fp16 hi/lo results land in the 128-byte-swizzled [128 px][64 ch] staging tiles
+//    with the minimum 4 bank wavefronts per 16-byte store;
+//  * one thread then issues two TMA stores (hi, lo plane; box {64 ch, 128 px, 1 row}, clipped at the image edge).
+// The first versions wrote 16-byte pieces at a 512-byte lane stride straight to global memory and were bound by
+// L1 store wavefronts (ncu: L1/TEX 70 %, DRAM 16 %, 0.35 ms for 491 MB).
+__global__ void __launch_bounds__(128)
+conv1a_tc_kernel(const float4* __restrict__ nimg, int H, int W, const float* __restrict__ wt /*[27][64]*/,
+                 const float* __restrict__ bias, const __grid_constant__ CUtensorMap tm_hi,
+                 const __grid_constant__ CUtensorMap tm_lo) {
+  extern __shared__ uint8_t smem_raw1a[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw1a) + 1023) & ~(uintptr_t)1023);
+  uint8_t* t_hi = base;                                   // [128 px][128 B], SWIZZLE_128B
+  uint8_t* t_lo = base + 16384;
+  float* ws = reinterpret_cast<float*>(base + 32768);     // [27][64] + bias[64]
+  float4* patch = reinterpret_cast<float4*>(base + 32768 + 7168);   // [3][132]
+  const int x0 = blockIdx.x * 128, y = blockIdx.y;
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = wt[i];
+  if (threadIdx.x < 64) ws[27 * 64 + threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
+    const int ky = i / 130, col = i - ky * 130;
+    const int iy = y + ky - 1, ix = x0 + col - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(nimg + (size_t)iy * W + ix);
+    patch[ky * 132 + col] = v;
   }
-  ++g_launches;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, cq = threadIdx.x >> 5;
+  float acc[4][16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = ws[27 * 64 + cq * 16 + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      float4 in[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) in[p] = patch[ky * 132 + lane + 32 * p + kx];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + cq * 16);
+        float wv[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { const float4 t = wr[g]; wv[4 * g] = t.x; wv[4 * g + 1] = t.y; wv[4 * g + 2] = t.z; wv[4 * g + 3] = t.w; }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float a = (c == 0) ? in[p].x : (c == 1 ? in[p].y : in[p].z);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(a, wv[j], acc[p][j]);
+        }
+      }
+    }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int row = lane + 32 * p;                        // pixel within the segment = row of the staging tile
+    __align__(16) __half2 hi[8];
+    __align__(16) __half2 lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
+      hi[j] = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hi[j]);
+      lo[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int chunk = (cq * 2 + g) ^ (row & 7);         // SWIZZLE_128B
+      *reinterpret_cast<uint4*>(t_hi + row * 128 + chunk * 16) = reinterpret_cast<const uint4*>(hi)[g];
+      *reinterpret_cast<uint4*>(t_lo + row * 128 + chunk * 16) = reinterpret_cast<const uint4*>(lo)[g];
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(&tm_hi)), "r"((uint32_t)__cvta_generic_to_shared(t_hi)), "r"(0), "r"(x0), "r"(y) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(&tm_lo)), "r"((uint32_t)__cvta_generic_to_shared(t_lo)), "r"(0), "r"(x0), "r"(y) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+// tm1a: [hi, lo] store maps of the conv1a output with box {64 ch, 128 px, 1 row} (tcgen05 modes only)
+int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out, float4* nimg,
+                  const CUtensorMap* tm1a, cudaStream_t st) {
+  SFD2_CHECK(L.cin == 3 && L.cout == 64 && L.k == 3, SFD2_ERR_WEIGHTS, "conv1a: unexpected layer shape");
+  SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "unknown image dtype %d", img_dtype);
+  if (img_dtype == SFD2_IMG_F32_NCHW) norm_kernel<SFD2_IMG_F32_NCHW><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
+  else norm_kernel<SFD2_IMG_U8_NHWC><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
+  // L.w_simt is [tap][ci][cout_pad = 64] fp32 = exactly the [27][64] table the kernels stage in smem
+  dim3 grid(cdiv(W, 128), H), block(128);
+  if (tc_out) {
+    SFD2_CHECK(tm1a != nullptr, SFD2_ERR_ARG, "conv1a: store maps missing");
+    const int smem = 1024 + 32768 + 7168 + 3 * 132 * 16;
+    static bool attr = false;
+    if (!attr) {
+      SFD2_CUDA(cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      attr = true;
+    }
+    conv1a_tc_kernel<<<grid, block, smem, st>>>(nimg, H, W, L.w_simt, L.b_dev, tm1a[0], tm1a[1]);
+  } else {
+    conv1a_kernel<0><<<grid, block, 0, st>>>(nimg, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
+  }
+  g_launches += 2;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
 }

@@ -186,3 +186,37 @@ class Extractor:
                                                kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
                    "sfd2_extract_dev")
         return {"keypoints": kp, "scores": sc, "descriptors": de, "counts": cnt}
+
+    def extract_host(self, images):
+        """Batched host entry point (sfd2_extract_host): images = CPU tensor / ndarray float32 [n,3,H,W] in
+        [0,1] (pinned memory makes the copies asynchronous) or uint8 [n,H,W,3].  The H2D copy of image
+        i+1 overlaps the kernels of image i; returns numpy arrays with fixed capacity + counts."""
+        t = torch.as_tensor(images)
+        if t.is_cuda:
+            raise ValueError("extract_host takes host images; call the Extractor for device-resident batches")
+        t = t.contiguous()
+        if t.dtype == torch.uint8:
+            n, H, W, _ = t.shape
+            dt = _lib.IMG_U8_NHWC
+        else:
+            t = t.float()
+            n, _, H, W = t.shape
+            dt = _lib.IMG_F32_NCHW
+        kp = self._pinned("kp", (n, self.topk, 2), torch.float32)
+        sc = self._pinned("sc", (n, self.topk), torch.float32)
+        de = self._pinned("de", (n, self.topk, _lib.DESC_DIM), torch.float32)
+        cnt = self._pinned("cnt", (n,), torch.int32)
+        p = _params(self.model, self.conf_th, self.topk)
+        _lib.check(_lib.lib().sfd2_extract_host(self.model.ctx.handle, t.data_ptr(), dt, n, H, W, C.byref(p),
+                                                kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr()),
+                   "sfd2_extract_host")
+        return {"keypoints": kp.numpy(), "scores": sc.numpy(), "descriptors": de.numpy(), "counts": cnt.numpy()}
+
+    def _pinned(self, name, shape, dtype):
+        """Reusable pinned output buffers (results are overwritten by the next extract_host call)."""
+        cache = self.__dict__.setdefault("_pin", {})
+        t = cache.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype).pin_memory()
+            cache[name] = t
+        return t
