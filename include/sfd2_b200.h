@@ -77,6 +77,8 @@ typedef struct {
   float distance_threshold; /* :30 ; <= 0 means None                                     */
   float ratio_threshold;    /* :29 ; <= 0 means None                                     */
   int32_t precision;        /* sfd2_precision (FP32 = CUDA cores, TC_* = tcgen05)        */
+  int32_t ratio_mode;       /* 0: hloc find_nn formula (nearest_neighbor.py:10-11);
+                               1: it_loc mutual_nn_ratio_matcher formula (it_loc/matcher.py:172-174) */
 } sfd2_match_params;
 
 SFD2_API int sfd2_abi_version(void);
@@ -106,7 +108,8 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* ctx, const void* img_host, int img_dtyp
 /* Replaces NearestNeighbor._forward (hloc/matchers/nearest_neighbor.py:38-57) and
  * Matcher.mutual_nn_matcher (it_loc/matcher.py:122-130).
  *   d0 float32 [n0, d] row-major, d1 float32 [n1, d]   (d = 128)
- *   matches0 int32 [n0]  index into d1 or -1
+ *   matches0 int32 [n0]  index into d1; -1 = no candidate / rejected by the row's own ratio or distance
+ *                        test; -2 = rejected only by the mutual check (hloc keeps that row's score)
  *   sim0     float32 [n0] raw max cosine of every row (callers map to (s+1)/2)  */
 SFD2_API int sfd2_match_dev(sfd2_ctx* ctx, const float* d0_dev, int n0, const float* d1_dev, int n1, int d,
                    const sfd2_match_params* p, int32_t* matches0_dev, float* sim0_dev, void* stream);

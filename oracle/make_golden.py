@@ -135,6 +135,9 @@ def fixture_match():
     nn = NearestNeighbor({"do_mutual_check": True, "distance_threshold": None}).eval()
     nn1 = NearestNeighbor({"do_mutual_check": False, "distance_threshold": None}).eval()
     mt = Matcher(conf=itloc_confs["NNM"]).eval()
+    mtr = Matcher(conf=itloc_confs["NNR"]).eval()                      # mutual NN + symmetric Lowe ratio 0.9
+    nnr = NearestNeighbor({"do_mutual_check": True, "ratio_threshold": 0.8, "distance_threshold": 0.7}).eval()
+    nnr1 = NearestNeighbor({"do_mutual_check": False, "ratio_threshold": 0.9, "distance_threshold": None}).eval()
     for tag, (n, m_) in {"sq": (512, 512), "wide": (300, 1000), "tall": (777, 129), "one": (1, 50), "col": (40, 1)}.items():
         d0, d1 = synth_descriptors(11, n, m_)
         with torch.no_grad():
@@ -144,10 +147,36 @@ def fixture_match():
         out[f"{tag}_hloc_m0"] = ph["matches0"][0].numpy().astype(np.int32)
         out[f"{tag}_hloc_s0"] = ph["matching_scores0"][0].numpy()
         out[f"{tag}_hloc_nomutual_m0"] = po["matches0"][0].numpy().astype(np.int32)
+        if m_ > 1 and n > 1:    # topk(2) needs two candidates in both directions
+            with torch.no_grad():
+                t0, t1 = torch.from_numpy(d0.T.copy())[None], torch.from_numpy(d1.T.copy())[None]
+                pr = nnr({"descriptors0": t0, "descriptors1": t1})
+                pr1 = nnr1({"descriptors0": t0, "descriptors1": t1})
+            out[f"{tag}_hloc_ratio_m0"] = pr["matches0"][0].numpy().astype(np.int32)
+            out[f"{tag}_hloc_ratio_s0"] = pr["matching_scores0"][0].numpy()
+            out[f"{tag}_hloc_ratio_nomutual_m0"] = pr1["matches0"][0].numpy().astype(np.int32)
+            out[f"{tag}_hloc_ratio_nomutual_s0"] = pr1["matching_scores0"][0].numpy()
+            pir = mtr({"descriptors0": d0.astype(np.float64), "descriptors1": d1.astype(np.float64)})
+            out[f"{tag}_itloc_nnr_m0"] = np.asarray(pir["matches0"]).astype(np.int32)
         if n > 1:   # the reference's .squeeze() mis-shapes N==1
             pi = mt({"descriptors0": d0.astype(np.float64), "descriptors1": d1.astype(np.float64)})
             out[f"{tag}_itloc_m0"] = np.asarray(pi["matches0"]).astype(np.int32)
             out[f"{tag}_itloc_s0"] = np.asarray(pi["matching_scores0"]).astype(np.float64).reshape(-1)
+    # ratio tests on real SFD2 descriptors (the C1 pair stored in c1_640x480.npz): many near-threshold rows
+    c1p = os.path.join(OUT, "c1_640x480.npz")
+    if os.path.exists(c1p):
+        c1 = np.load(c1p)
+        d0, d1 = c1["desc"], c1["desc_b"]
+        with torch.no_grad():
+            t0, t1 = torch.from_numpy(d0.T.copy())[None], torch.from_numpy(d1.T.copy())[None]
+            pr = nnr({"descriptors0": t0, "descriptors1": t1})
+            pr1 = nnr1({"descriptors0": t0, "descriptors1": t1})
+        pir = mtr({"descriptors0": d0.astype(np.float64), "descriptors1": d1.astype(np.float64)})
+        out["c1_hloc_ratio_m0"] = pr["matches0"][0].numpy().astype(np.int32)
+        out["c1_hloc_ratio_s0"] = pr["matching_scores0"][0].numpy()
+        out["c1_hloc_ratio_nomutual_m0"] = pr1["matches0"][0].numpy().astype(np.int32)
+        out["c1_hloc_ratio_nomutual_s0"] = pr1["matching_scores0"][0].numpy()
+        out["c1_itloc_nnr_m0"] = np.asarray(pir["matches0"]).astype(np.int32)
     np.savez_compressed(os.path.join(OUT, "match_cases.npz"), **out)
     print("match_cases", {k: v.shape for k, v in out.items() if k.endswith("m0")})
 

@@ -298,6 +298,28 @@ def match_itloc(descriptors0: np.ndarray, descriptors1: np.ndarray):
     return {"matches0": all_matches, "matching_scores0": scores.squeeze(-1).numpy()}
 
 
+def match_itloc_nnr(descriptors0: np.ndarray, descriptors1: np.ndarray, ratio: float = 0.9):
+    """it_loc/matcher.py mode 'nnr' (:101-103) -> mutual_nn_ratio_matcher (:165-194): mutual NN plus the
+    symmetric Lowe ratio test sqrt(2-2 s0) / (sqrt(2-2 s1) + 1e-8) <= ratio in both directions."""
+    d1 = torch.from_numpy(np.ascontiguousarray(descriptors0))
+    d2 = torch.from_numpy(np.ascontiguousarray(descriptors1))
+    sim = d1 @ d2.t()
+    nns_sim, nns = torch.topk(sim, 2, dim=1)
+    nns_dist = torch.sqrt(2 - 2 * nns_sim)
+    ratios12 = nns_dist[:, 0] / (nns_dist[:, 1] + 1e-8)
+    nn12 = nns[:, 0]
+    nns_sim, nns = torch.topk(sim.t(), 2, dim=1)
+    nns_dist = torch.sqrt(2 - 2 * nns_sim)
+    ratios21 = nns_dist[:, 0] / (nns_dist[:, 1] + 1e-8)
+    nn21 = nns[:, 0]
+    ids1 = torch.arange(0, sim.shape[0])
+    mask = torch.min(ids1 == nn21[nn12], torch.min(ratios12 <= ratio, ratios21[nn12] <= ratio))
+    all_matches = np.ones((d1.shape[0],), dtype=int) * -1
+    all_matches[ids1[mask].numpy()] = nn12[mask].numpy()
+    scores = torch.topk(sim, dim=1, k=1)[0]
+    return {"matches0": all_matches, "matching_scores0": scores.squeeze(-1).numpy()}
+
+
 def mutual_nn_exact(d0: np.ndarray, d1: np.ndarray):
     """Tie-aware float64 restatement of A.8 used to classify disagreements:
     returns sim-free nn12, nn21 (lowest index on ties) and the top-1/top-2 gap per row."""

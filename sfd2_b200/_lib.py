@@ -17,7 +17,7 @@ class ExtractParams(C.Structure):
 
 class MatchParams(C.Structure):
     _fields_ = [("do_mutual_check", C.c_int32), ("distance_threshold", C.c_float),
-                ("ratio_threshold", C.c_float), ("precision", C.c_int32)]
+                ("ratio_threshold", C.c_float), ("precision", C.c_int32), ("ratio_mode", C.c_int32)]
 
 
 class Sfd2Error(RuntimeError):

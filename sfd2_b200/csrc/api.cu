@@ -46,7 +46,7 @@ struct Ws {
   Act acts[NUM_ACTS];
   CUtensorMap maps[NUM_ACTS][6];
   CUtensorMap st_maps[NUM_ACTS][4];
-  CUtensorMap map_1a[2];                    // conv1a output rows: box {64 ch, 128 px, 1 row}
+  CUtensorMap map_1a[2];                    // conv1a output rows: box {64 ch, 256 px, 1 row}
   CUtensorMap map_logits[2], map_desc[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float4* nimg = nullptr;  // normalised image, NHWC4 fp32
@@ -61,9 +61,10 @@ struct sfd2_ctx {
   std::vector<Layer> layers;
   std::map<std::string, int> lidx;
   cudaStream_t stream = nullptr;  // used by the *_host entry points
-  Ws ws[2];                       // two per-image workspaces: consecutive images of a batch alternate between
-  cudaStream_t aux[2] = {nullptr, nullptr};   // two internal streams so one image's kernel tails overlap the other's
-  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  static constexpr int kMaxStreams = 4;
+  Ws ws[kMaxStreams];             // per-image workspaces: consecutive images of a batch rotate through nstreams of them
+  cudaStream_t aux[kMaxStreams] = {};   // internal streams so one image's kernel tails overlap the others'
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxStreams] = {};
   int nstreams = 2;
   cudaStream_t copy_stream = nullptr;          // H2D of batched host inputs
   std::vector<cudaEvent_t> img_ready;
@@ -74,6 +75,7 @@ struct sfd2_ctx {
   float *kp_dev = nullptr, *sc_dev = nullptr, *de_dev = nullptr; int32_t* cnt_dev = nullptr; size_t out_cap = 0;
   // matcher workspace
   unsigned long long *row_key = nullptr, *col_key = nullptr; size_t key_cap = 0;
+  unsigned *row2 = nullptr, *col2 = nullptr;   // second-best similarities (ratio tests)
   __half* mhalf = nullptr; size_t mhalf_cap = 0;
   float *m_d0 = nullptr, *m_d1 = nullptr; size_t m_d0_cap = 0, m_d1_cap = 0;
   int32_t* m_out = nullptr; float* m_sim = nullptr; size_t m_out_cap = 0;
@@ -191,7 +193,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       const Act& a = w.acts[A1A];
       const uint64_t dims[3] = {64, (uint64_t)a.W, (uint64_t)a.H};
       const uint64_t str[2] = {128, (uint64_t)a.Wp * 128};
-      const uint32_t box[3] = {64u, 128u, 1u};
+      const uint32_t box[3] = {64u, 256u, 1u};
       rc = make_tmap(&w.map_1a[pl], pl ? (const void*)a.lo : (const void*)a.hi, 3, dims, str, box, 0, 128);
     }
     for (int b = 0; b < 2 && !rc; ++b) {
@@ -342,12 +344,12 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   for (Ws& w : c->ws) free_workspace(w);
   for (Layer& L : c->layers) free_layer(L);
   cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
-  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
+  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
   cudaFree(c->m_out); cudaFree(c->m_sim);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
-  for (int k = 0; k < 2; ++k) { if (c->aux[k]) cudaStreamDestroy(c->aux[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
+  for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k) { if (c->aux[k]) cudaStreamDestroy(c->aux[k]); if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   for (auto e : c->img_ready) cudaEventDestroy(e);
@@ -367,7 +369,8 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
   // stream with events): every conv kernel is a persistent 1-CTA/SM grid whose last wave leaves SMs idle
   // (950 tiles over 148 SMs = 6.4 waves), and the other image's next kernel fills them.  Per-launch
   // profiling needs un-overlapped kernels, so it forces a single stream.
-  const int ns = ((n > 1 || ready) && c->nstreams > 1 && !c->prof_on) ? 2 : 1;
+  int ns = ((n > 1 || ready) && c->nstreams > 1 && !c->prof_on) ? std::min(c->nstreams, (int)sfd2_ctx::kMaxStreams) : 1;
+  if (ns > n && n > 1) ns = n;
   for (int k = 0; k < ns; ++k) {
     rc = ensure_workspace(c, c->ws[k], h, w, p->precision);
     if (rc) return rc;
@@ -376,18 +379,18 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
   if (ns > 1) {
     if (!c->ev_fork) {
       SFD2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-      for (int k = 0; k < 2; ++k) {
+      for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k) {
         SFD2_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
         SFD2_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
       }
     }
     SFD2_CUDA(cudaEventRecord(c->ev_fork, st));
-    for (int k = 0; k < 2; ++k) SFD2_CUDA(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
+    for (int k = 0; k < ns; ++k) SFD2_CUDA(cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0));
   }
   const size_t img_stride = (size_t)h * w * 3 * (img_dtype == SFD2_IMG_F32_NCHW ? 4 : 1);
   const long long before = g_launches;
   for (int i = 0; i < n; ++i) {
-    const int k = (ns > 1) ? (i & 1) : 0;
+    const int k = (ns > 1) ? (i % ns) : 0;
     if (ready) SFD2_CUDA(cudaStreamWaitEvent(ns > 1 ? c->aux[k] : st, ready[i], 0));
     rc = extract_one(c, c->ws[k], static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
                      kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
@@ -395,7 +398,7 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
     if (rc) return rc;
   }
   if (ns > 1)
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < ns; ++k) {
       SFD2_CUDA(cudaEventRecord(c->ev_join[k], c->aux[k]));
       SFD2_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
     }
@@ -460,12 +463,12 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
   SFD2_CUDA(cudaMemcpyAsync(scores, c->sc_dev, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(desc, c->de_dev, rows * SFD2_DESC_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(counts, c->cnt_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  int status[2] = {0, 0};
-  for (int k = 0; k < 2; ++k)
+  int status[sfd2_ctx::kMaxStreams] = {};
+  for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k)
     if (c->ws[k].status) SFD2_CUDA(cudaMemcpyAsync(&status[k], c->ws[k].status, sizeof(int), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaStreamSynchronize(st));
-  if (status[0] != 0 || status[1] != 0) {
-    for (int k = 0; k < 2; ++k)
+  if (status[0] | status[1] | status[2] | status[3]) {
+    for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k)
       if (c->ws[k].status) cudaMemset(c->ws[k].status, 0, sizeof(int));
     set_error("NMS produced more candidates than the workspace holds (cap %d); results truncated", c->ws[0].cap);
     return SFD2_ERR_OVERFLOW;
@@ -476,9 +479,12 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
 static int ensure_match_ws(sfd2_ctx* c, int n0, int n1) {
   const size_t need = (size_t)(n0 > n1 ? n0 : n1) + 128;
   if (need > c->key_cap) {
-    cudaFree(c->row_key); cudaFree(c->col_key); c->row_key = c->col_key = nullptr; c->key_cap = 0;
+    cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2);
+    c->row_key = c->col_key = nullptr; c->row2 = c->col2 = nullptr; c->key_cap = 0;
     SFD2_CUDA(cudaMalloc(&c->row_key, need * sizeof(unsigned long long)));
     SFD2_CUDA(cudaMalloc(&c->col_key, need * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->row2, need * sizeof(unsigned)));
+    SFD2_CUDA(cudaMalloc(&c->col2, need * sizeof(unsigned)));
     c->key_cap = need;
   }
   const size_t hneed = 2 * ((size_t)round_up(n0 > 0 ? n0 : 1, 128) + round_up(n1 > 0 ? n1 : 1, 128)) * 128;
@@ -501,14 +507,18 @@ static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int 
                          c->col_key, c->num_sms, st);
   prof_end(c, st);
   if (rc) return rc;
-  return launch_match_finish(c->row_key, c->col_key, n0, n1, p->do_mutual_check, p->distance_threshold, matches0, sim0, st);
+  if (p->ratio_threshold > 0.f) {   // second-best pass (CUDA-core fp32 in every precision mode)
+    rc = launch_match_second(d0, n0, d1, n1, d, c->row_key, c->col_key, c->row2, c->col2, st);
+    if (rc) return rc;
+  }
+  return launch_match_finish(c->row_key, c->col_key, n0, n1, p->do_mutual_check, p->distance_threshold,
+                             p->ratio_threshold, p->ratio_mode == 1 ? 2 : 1, c->row2, c->col2, matches0, sim0, st);
 }
 
 SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
                    int32_t* matches0, float* sim0, void* stream) {
   SFD2_CHECK(c && p && (n0 == 0 || (d0 && matches0 && sim0)) && (n1 == 0 || d1), SFD2_ERR_ARG, "sfd2_match_dev: NULL argument");
   SFD2_CHECK(n0 >= 0 && n1 >= 0 && d >= 1, SFD2_ERR_ARG, "sfd2_match_dev: bad shape %d x %d x %d", n0, n1, d);
-  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio_threshold is not implemented yet");
   SFD2_CHECK(p->precision >= 0 && p->precision <= 2, SFD2_ERR_ARG, "bad precision %d", p->precision);
   SFD2_CUDA(cudaSetDevice(c->device));
   int rc = ensure_match_ws(c, n0, n1);
@@ -522,7 +532,6 @@ SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d
 SFD2_API int sfd2_match_batched_dev(sfd2_ctx* c, const float* d0, const int32_t* off0, const float* d1, const int32_t* off1,
                            int npairs, int d, const sfd2_match_params* p, int32_t* matches0, float* sim0, void* stream) {
   SFD2_CHECK(c && p && off0 && off1 && npairs >= 0, SFD2_ERR_ARG, "sfd2_match_batched_dev: bad argument");
-  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio_threshold is not implemented yet");
   SFD2_CUDA(cudaSetDevice(c->device));
   int mx0 = 0, mx1 = 0;
   for (int i = 0; i < npairs; ++i) {

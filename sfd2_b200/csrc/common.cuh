@@ -98,8 +98,11 @@ int launch_match_simt(const float* d0, int n0, const float* d1, int n1, int d, u
                       unsigned long long* col_key, cudaStream_t st);
 int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int split, __half* ws_half,
                     unsigned long long* row_key, unsigned long long* col_key, int num_sms, cudaStream_t st);
+int launch_match_second(const float* d0, int n0, const float* d1, int n1, int d, const unsigned long long* row_key,
+                        const unsigned long long* col_key, unsigned* row2, unsigned* col2, cudaStream_t st);
 int launch_match_finish(const unsigned long long* row_key, const unsigned long long* col_key, int n0, int n1,
-                        int mutual, float dist_th, int32_t* matches0, float* sim0, cudaStream_t st);
+                        int mutual, float dist_th, float ratio_th, int ratio_mode, const unsigned* row2,
+                        const unsigned* col2, int32_t* matches0, float* sim0, cudaStream_t st);
 
 // driver entry point for TMA descriptors, resolved once through cudart (no -lcuda link)
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -9,6 +9,8 @@
 //  * gconv_f32_kernel: the ResBlock's grouped 3x3 (groups = 32, 8 ch/group; nets/sfd2.py:32).
 //  * sta_kernel      : ConvSta 1x1 256->3 (nets/sfd2.py:303,345), always fp32.
 //  * softmax65 / l2norm128 : head epilogues (nets/sfd2.py:330-333, :342).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sfd2 {
@@ -111,88 +113,94 @@ conv1a_kernel(const float4* __restrict__ nimg, int H, int W, int Wp, const float
 }
 
 // conv1a for the tcgen05 modes: same arithmetic, but the memory side goes through shared memory both ways.
-//  * the block's 3 x 130 normalised input pixels are staged once (coalesced float4 loads);
-//  * a thread owns pixels lane, lane+32, lane+64, lane+96 of the block's 128-pixel row segment and the warp's
-//    16-channel chunk, so its fp16 hi/lo results land in the 128-byte-swizzled [128 px][64 ch] staging tiles
-//    with the minimum 4 bank wavefronts per 16-byte store;
-//  * one thread then issues two TMA stores (hi, lo plane; box {64 ch, 128 px, 1 row}, clipped at the image edge).
-// The first versions wrote 16-byte pieces at a 512-byte lane stride straight to global memory and were bound by
-// L1 store wavefronts (ncu: L1/TEX 70 %, DRAM 16 %, 0.35 ms for 491 MB).
-__global__ void __launch_bounds__(128)
+//  * the block's 3 x 258 normalised input pixels are staged once per 256-pixel row segment (coalesced float4);
+//  * thread = 8 pixels (lane, lane+32, ... lane+224 of the segment) x 8 output channels (chosen per WARP, so weight
+//    reads are warp-uniform broadcasts).  Every weight fetched from smem feeds 8 FMAs: at 4 px/thread the kernel
+//    needed 128 B/clk/SM of shared-memory bandwidth - exactly the hardware limit (ncu: L1/TEX 78 %);
+//  * fp16 hi/lo results go to 128-byte-swizzled [256 px][64 ch] staging tiles (4 bank wavefronts per 16-byte
+//    store, the minimum) and leave through two TMA stores per segment (box {64 ch, 256 px, 1 row}, clipped at
+//    the image edge).  Direct 16-byte global stores at a 512-byte lane stride made the first versions L1-bound.
+//  * persistent: weights are staged once per block, blocks walk over row segments.
+constexpr int C1_SEG = 256;
+__global__ void __launch_bounds__(256, 2)
 conv1a_tc_kernel(const float4* __restrict__ nimg, int H, int W, const float* __restrict__ wt /*[27][64]*/,
                  const float* __restrict__ bias, const __grid_constant__ CUtensorMap tm_hi,
                  const __grid_constant__ CUtensorMap tm_lo) {
   extern __shared__ uint8_t smem_raw1a[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw1a) + 1023) & ~(uintptr_t)1023);
-  uint8_t* t_hi = base;                                   // [128 px][128 B], SWIZZLE_128B
-  uint8_t* t_lo = base + 16384;
-  float* ws = reinterpret_cast<float*>(base + 32768);     // [27][64] + bias[64]
-  float4* patch = reinterpret_cast<float4*>(base + 32768 + 7168);   // [3][132]
-  const int x0 = blockIdx.x * 128, y = blockIdx.y;
+  uint8_t* t_hi = base;                                   // [256 px][128 B], SWIZZLE_128B
+  uint8_t* t_lo = base + C1_SEG * 128;
+  float* ws = reinterpret_cast<float*>(base + 2 * C1_SEG * 128);            // [27][64] + bias[64]
+  float* patch = reinterpret_cast<float*>(base + 2 * C1_SEG * 128 + 7168);    // [3 rows][3 ch][260]
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) ws[i] = wt[i];
   if (threadIdx.x < 64) ws[27 * 64 + threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 3 * 130; i += blockDim.x) {
-    const int ky = i / 130, col = i - ky * 130;
-    const int iy = y + ky - 1, ix = x0 + col - 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(nimg + (size_t)iy * W + ix);
-    patch[ky * 132 + col] = v;
-  }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, cq = threadIdx.x >> 5;
-  float acc[4][16];
+  const int lane = threadIdx.x & 31, co = (threadIdx.x >> 5) * 8;   // this warp's 8 output channels
+  const int segs_x = (W + C1_SEG - 1) / C1_SEG, nseg = segs_x * H;
+  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
+    const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1_SEG;
+    for (int i = threadIdx.x; i < 3 * (C1_SEG + 2); i += blockDim.x) {
+      const int ky = i / (C1_SEG + 2), col = i - ky * (C1_SEG + 2);
+      const int iy = y + ky - 1, ix = x0 + col - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(nimg + (size_t)iy * W + ix);
+      patch[(ky * 3 + 0) * 260 + col] = v.x;
+      patch[(ky * 3 + 1) * 260 + col] = v.y;
+      patch[(ky * 3 + 2) * 260 + col] = v.z;
+    }
+    __syncthreads();
+    float acc[8][8];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[0][j] = acc[1][j] = acc[2][j] = acc[3][j] = ws[27 * 64 + cq * 16 + j];
+    for (int p = 0; p < 8; ++p)
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+      for (int j = 0; j < 8; ++j) acc[p][j] = ws[27 * 64 + co + j];
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      float4 in[4];
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int p = 0; p < 4; ++p) in[p] = patch[ky * 132 + lane + 32 * p + kx];
+      for (int kx = 0; kx < 3; ++kx) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + cq * 16);
-        float wv[16];
+        for (int c = 0; c < 3; ++c) {
+          float in[8];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) { const float4 t = wr[g]; wv[4 * g] = t.x; wv[4 * g + 1] = t.y; wv[4 * g + 2] = t.z; wv[4 * g + 3] = t.w; }
+          for (int p = 0; p < 8; ++p) in[p] = patch[(ky * 3 + c) * 260 + lane + 32 * p + kx];
+          const float4* wr = reinterpret_cast<const float4*>(ws + ((ky * 3 + kx) * 3 + c) * 64 + co);
+          const float4 w0 = wr[0], w1 = wr[1];
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const float a = (c == 0) ? in[p].x : (c == 1 ? in[p].y : in[p].z);
+          for (int p = 0; p < 8; ++p)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(a, wv[j], acc[p][j]);
+            for (int j = 0; j < 8; ++j) acc[p][j] = fmaf(in[p], wv[j], acc[p][j]);
         }
       }
+    // the previous segment's TMA stores must have finished reading the staging tiles
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int row = lane + 32 * p;                      // pixel within the segment = row of the staging tile
+      __align__(16) __half2 hi[4];
+      __align__(16) __half2 lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
+        hi[j] = __floats2half2_rn(v0, v1);
+        const float2 hf = __half22float2(hi[j]);
+        lo[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      }
+      const int chunk = (co >> 3) ^ (row & 7);            // SWIZZLE_128B
+      *reinterpret_cast<uint4*>(t_hi + row * 128 + chunk * 16) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(t_lo + row * 128 + chunk * 16) = *reinterpret_cast<const uint4*>(lo);
     }
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int row = lane + 32 * p;                        // pixel within the segment = row of the staging tile
-    __align__(16) __half2 hi[8];
-    __align__(16) __half2 lo[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v0 = fmaxf(acc[p][2 * j], 0.f), v1 = fmaxf(acc[p][2 * j + 1], 0.f);
-      hi[j] = __floats2half2_rn(v0, v1);
-      const float2 hf = __half22float2(hi[j]);
-      lo[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-    }
-#pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int chunk = (cq * 2 + g) ^ (row & 7);         // SWIZZLE_128B
-      *reinterpret_cast<uint4*>(t_hi + row * 128 + chunk * 16) = reinterpret_cast<const uint4*>(hi)[g];
-      *reinterpret_cast<uint4*>(t_lo + row * 128 + chunk * 16) = reinterpret_cast<const uint4*>(lo)[g];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();                                      // tiles complete; also: everyone is done with `patch`
+    if (threadIdx.x == 0) {
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(reinterpret_cast<uint64_t>(&tm_hi)), "r"((uint32_t)__cvta_generic_to_shared(t_hi)), "r"(0), "r"(x0), "r"(y) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                   ::"l"(reinterpret_cast<uint64_t>(&tm_lo)), "r"((uint32_t)__cvta_generic_to_shared(t_lo)), "r"(0), "r"(x0), "r"(y) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(&tm_hi)), "r"((uint32_t)__cvta_generic_to_shared(t_hi)), "r"(0), "r"(x0), "r"(y) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(&tm_lo)), "r"((uint32_t)__cvta_generic_to_shared(t_lo)), "r"(0), "r"(x0), "r"(y) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // tm1a: [hi, lo] store maps of the conv1a output with box {64 ch, 128 px, 1 row} (tcgen05 modes only)
@@ -206,13 +214,14 @@ int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, 
   dim3 grid(cdiv(W, 128), H), block(128);
   if (tc_out) {
     SFD2_CHECK(tm1a != nullptr, SFD2_ERR_ARG, "conv1a: store maps missing");
-    const int smem = 1024 + 32768 + 7168 + 3 * 132 * 16;
+    const int smem = 1024 + 2 * C1_SEG * 128 + 7168 + 9 * 260 * 4;
     static bool attr = false;
     if (!attr) {
       SFD2_CUDA(cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       attr = true;
     }
-    conv1a_tc_kernel<<<grid, block, smem, st>>>(nimg, H, W, L.w_simt, L.b_dev, tm1a[0], tm1a[1]);
+    const int nseg = cdiv(W, C1_SEG) * H;
+    conv1a_tc_kernel<<<std::min(nseg, 148 * 2), 256, smem, st>>>(nimg, H, W, L.w_simt, L.b_dev, tm1a[0], tm1a[1]);
   } else {
     conv1a_kernel<0><<<grid, block, 0, st>>>(nimg, H, W, out.Wp, L.w_simt, L.b_dev, out.f32, nullptr, nullptr);
   }

@@ -44,15 +44,18 @@ def _ctx(device_index: int) -> "_lib.Context":
     return _CTX[device_index]
 
 
-def _mparams(mutual, dist_th, ratio_th, precision):
+def _mparams(mutual, dist_th, ratio_th, precision, ratio_mode=0):
     return _lib.MatchParams(do_mutual_check=int(bool(mutual)),
                             distance_threshold=float(dist_th) if dist_th else 0.0,
                             ratio_threshold=float(ratio_th) if ratio_th else 0.0,
-                            precision=_lib.PREC[precision])
+                            precision=_lib.PREC[precision], ratio_mode=int(ratio_mode))
 
 
-def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, ratio_th=None, precision="exact"):
-    """d0 [N,D], d1 [M,D] CUDA float32 row-major -> (matches0 int32 [N], sim0 float32 [N]) on the device."""
+def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, ratio_th=None, precision="exact",
+              ratio_mode=0, raw=False):
+    """d0 [N,D], d1 [M,D] CUDA float32 row-major -> (matches0 int32 [N], sim0 float32 [N]) on the device.
+    matches0 < 0 means no match; with raw=True the native codes are kept (-1 = the row failed its own
+    ratio/distance test, -2 = it failed only the mutual check)."""
     assert d0.is_cuda and d1.is_cuda and d0.dtype == torch.float32 and d1.dtype == torch.float32
     d0, d1 = d0.contiguous(), d1.contiguous()
     n0, d = d0.shape
@@ -62,10 +65,12 @@ def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, rat
     s0 = torch.zeros((n0,), dtype=torch.float32, device=dev)
     if n0 == 0:
         return m0, s0
-    p = _mparams(mutual, dist_th, ratio_th, precision)
+    p = _mparams(mutual, dist_th, ratio_th, precision, ratio_mode)
     st = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(_lib.lib().sfd2_match_dev(_ctx(dev.index or 0).handle, d0.data_ptr(), n0, d1.data_ptr(), n1, d,
                                          C.byref(p), m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_dev")
+    if not raw:
+        m0.clamp_(min=-1)
     return m0, s0
 
 
@@ -84,6 +89,7 @@ def match_batched(d0: torch.Tensor, off0, d1: torch.Tensor, off1, mutual=True, d
                                                  o0.ctypes.data_as(C.c_void_p), d1.data_ptr(),
                                                  o1.ctypes.data_as(C.c_void_p), npairs, d0.shape[1], C.byref(p),
                                                  m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_batched_dev")
+    m0.clamp_(min=-1)
     return m0, s0
 
 
@@ -123,8 +129,7 @@ class NearestNeighborMixin:
     required_inputs = ["descriptors0", "descriptors1"]
 
     def _init(self, conf):
-        if conf.get("ratio_threshold"):
-            raise NotImplementedError("ratio_threshold needs top-2 in the epilogue: not implemented yet")
+        pass
 
     def _forward(self, data):
         d0, d1 = data["descriptors0"], data["descriptors1"]      # [B, D, N], [B, D, M]
@@ -135,12 +140,12 @@ class NearestNeighborMixin:
         for b in range(B):
             a = d0[b].float().t().contiguous()
             c = d1[b].float().t().contiguous()
-            m0, s0 = match_dev(a, c, self.conf["do_mutual_check"], self.conf["distance_threshold"], None,
-                               self.conf.get("precision", "exact"))
-            scores = (s0 + 1) / 2                                 # nearest_neighbor.py:15
-            if self.conf["distance_threshold"]:
-                ok = (2 * (1 - s0)) <= self.conf["distance_threshold"] ** 2
-                scores = torch.where(ok, scores, scores.new_tensor(0))
+            m0, s0 = match_dev(a, c, self.conf["do_mutual_check"], self.conf["distance_threshold"],
+                               self.conf["ratio_threshold"], self.conf.get("precision", "exact"), ratio_mode=0, raw=True)
+            # find_nn (nearest_neighbor.py:14-15): rows failing their own ratio / distance test get score 0;
+            # rows rejected only by the mutual check keep (sim + 1) / 2
+            scores = torch.where(m0 == -1, s0.new_tensor(0), (s0 + 1) / 2)
+            m0 = m0.clamp(min=-1)
             ms.append(m0.long())
             ss.append(scores)
         return {"matches0": torch.stack(ms), "matching_scores0": torch.stack(ss)}
@@ -153,6 +158,7 @@ class NearestNeighbor(NearestNeighborMixin, BaseModel):
 confs = {   # it_loc/matcher.py:24-82, the entries on the hot path
     "NNM": {"output": "NNM", "model": {"name": "nnm", "do_mutual_check": True, "distance_threshold": None}},
     "ONN": {"output": "ONN", "model": {"name": "nn", "do_mutual_check": False, "distance_threshold": None}},
+    "NNR": {"output": "NNR", "model": {"name": "nnr", "do_mutual_check": True, "distance_threshold": 0.9}},
 }
 
 
@@ -165,7 +171,7 @@ class Matcher(torch.nn.Module):
         self.conf = conf
         self.mode = conf["model"]["name"]
         self.precision = precision
-        if self.mode not in ("nnm", "nn"):
+        if self.mode not in ("nnm", "nn", "nnr"):
             raise NotImplementedError(f"matcher mode '{self.mode}' is outside the hot path")
 
     def cuda(self, device=None):
@@ -180,10 +186,12 @@ class Matcher(torch.nn.Module):
         m0 = np.full((n0,), -1, np.int32)
         s0 = np.zeros((n0,), np.float32)
         if n0 > 0:
-            p = _mparams(self.mode == "nnm", None, None, self.precision)
+            # 'nnr' = mutual NN + symmetric Lowe ratio with ratio = conf distance_threshold (matcher.py:101-103)
+            ratio = self.conf["model"].get("distance_threshold") if self.mode == "nnr" else None
+            p = _mparams(self.mode in ("nnm", "nnr"), None, ratio, self.precision, ratio_mode=1)
             dev = torch.cuda.current_device()
             _lib.check(_lib.lib().sfd2_match_host(_ctx(dev).handle, d0.ctypes.data_as(C.c_void_p), n0,
                                                   d1.ctypes.data_as(C.c_void_p), n1, d, C.byref(p),
                                                   m0.ctypes.data_as(C.c_void_p), s0.ctypes.data_as(C.c_void_p)),
                        "sfd2_match_host")
-        return {"matches0": m0.astype(int), "matching_scores0": s0}
+        return {"matches0": np.maximum(m0, -1).astype(int), "matching_scores0": s0}

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.ExtractParams) == 24
-    assert C.sizeof(_lib.MatchParams) == 16
+    assert C.sizeof(_lib.MatchParams) == 20
 
 
 def test_create_rejects_bad_blob_without_touching_cuda():

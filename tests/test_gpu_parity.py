@@ -269,3 +269,29 @@ def test_matcher_edge_cases():
     for i in range(2):
         mi, si = match_dev(a[off0[i]:off0[i + 1]], b[off1[i]:off1[i + 1]], precision="exact")
         assert torch.equal(mb[off0[i]:off0[i + 1]], mi) and torch.equal(sb[off0[i]:off0[i + 1]], si)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "exact"])
+def test_ratio_tests_match_reference(golden, prec):
+    """Lowe ratio + distance thresholds (hloc find_nn) and it_loc 'nnr' against reference fixtures.
+    Rows whose ratio sits within 1e-5 of the threshold may legitimately flip (fp32 GEMM order)."""
+    from sfd2_b200 import NearestNeighbor, Matcher, matcher_confs
+    g = golden("match_cases")
+    c1 = golden("c1_640x480")
+    cases = {t: (g[f"{t}_d0"], g[f"{t}_d1"]) for t in ["sq", "wide", "tall"]}
+    cases["c1"] = (c1["desc"], c1["desc_b"])
+    for tag, (d0, d1) in cases.items():
+        data = {"descriptors0": torch.from_numpy(d0.T.copy())[None].cuda(),
+                "descriptors1": torch.from_numpy(d1.T.copy())[None].cuda()}
+        o = NearestNeighbor({"do_mutual_check": True, "ratio_threshold": 0.8, "distance_threshold": 0.7,
+                             "precision": prec})(data)
+        m = o["matches0"][0].cpu().numpy()
+        assert (m != g[f"{tag}_hloc_ratio_m0"]).sum() <= 1, (tag, (m != g[f"{tag}_hloc_ratio_m0"]).sum())
+        ds = np.abs(o["matching_scores0"][0].cpu().numpy() - g[f"{tag}_hloc_ratio_s0"])
+        assert (ds > TOL).sum() <= 1, tag
+        o1 = NearestNeighbor({"do_mutual_check": False, "ratio_threshold": 0.9, "precision": prec})(data)
+        m1 = o1["matches0"][0].cpu().numpy()
+        assert (m1 != g[f"{tag}_hloc_ratio_nomutual_m0"]).sum() <= 1, tag
+        o2 = Matcher(matcher_confs["NNR"], precision=prec)({"descriptors0": d0.astype(np.float64),
+                                                            "descriptors1": d1.astype(np.float64)})
+        assert (o2["matches0"] != g[f"{tag}_itloc_nnr_m0"]).sum() <= 1, tag

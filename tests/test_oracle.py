@@ -91,3 +91,18 @@ def test_pair_matches_reference(golden):
     agree = (pi["matches0"] == g["itloc_matches0"]).mean()
     assert agree > 0.999
     assert (g["hloc_matches0"] == g["itloc_matches0"]).mean() > 0.999
+
+
+def test_ratio_matchers_match_reference(golden):
+    g = golden("match_cases")
+    c1 = golden("c1_640x480")
+    cases = {t: (g[f"{t}_d0"], g[f"{t}_d1"]) for t in ["sq", "wide", "tall"]}
+    cases["c1"] = (c1["desc"], c1["desc_b"])
+    for tag, (d0, d1) in cases.items():
+        pr = orc.match_hloc(d0.T[None], d1.T[None], ratio_threshold=0.8, distance_threshold=0.7)
+        assert np.array_equal(pr["matches0"][0].numpy(), g[f"{tag}_hloc_ratio_m0"]), tag
+        np.testing.assert_allclose(pr["matching_scores0"][0].numpy(), g[f"{tag}_hloc_ratio_s0"], atol=1e-6)
+        p1 = orc.match_hloc(d0.T[None], d1.T[None], ratio_threshold=0.9, do_mutual_check=False)
+        assert np.array_equal(p1["matches0"][0].numpy(), g[f"{tag}_hloc_ratio_nomutual_m0"]), tag
+        pi = orc.match_itloc_nnr(d0.astype(np.float64), d1.astype(np.float64), 0.9)
+        assert np.array_equal(pi["matches0"], g[f"{tag}_itloc_nnr_m0"]), tag
