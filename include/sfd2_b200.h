@@ -70,6 +70,9 @@ typedef struct {
   int32_t topk;       /* extract_localization.py max_keypoints; rows of every output    */
   int32_t precision;  /* sfd2_precision                                                 */
   int32_t use_stability; /* extract_localization.py:30 use_stability                    */
+  int32_t border_w;   /* extents the border test uses; 0 = the image's own w / h.  The  */
+  int32_t border_h;   /* reference's multi-scale loop tests SCALED coordinates against   */
+                      /* the ORIGINAL size (nets/extractor.py:181-182)                   */
 } sfd2_extract_params;
 
 typedef struct {

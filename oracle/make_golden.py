@@ -103,6 +103,19 @@ def fixture_extract(m, name, seed, H, W, K, keep_image, with_maps=False, twin=Tr
           "score[-1]", sc[-1] if len(sc) else None, "next", nxt)
 
 
+def fixture_multiscale(m):
+    """Multi-scale extraction (nets/extractor.py:113-125, scale loop): one small image, scales [1.0, 0.75, 1.25]."""
+    H, W, K = 128, 160, 120
+    u8 = synth_image_u8(11, H, W)
+    scales = [1.0, 0.75, 1.25]
+    out = extract_resnet_return(m, img=to_input(u8), topK=K, mask=None, conf_th=0.001, scales=scales)
+    o = np.lexsort((out["keypoints"][:, 1] * 100000 + out["keypoints"][:, 0], -out["scores"]))
+    np.savez_compressed(os.path.join(OUT, "ms_128x160.npz"), image_u8=u8, H=H, W=W, K=K, scales=np.array(scales),
+                        kp=out["keypoints"][o].astype(np.float32), scores=out["scores"][o].astype(np.float32),
+                        desc=out["descriptors"][o].astype(np.float32))
+    print("ms_128x160 kpts", len(out["scores"]), out["scores"][:3])
+
+
 def fixture_nms():
     """simple_nms on hand-made maps: plateaus, exact ties, all-zero, borders."""
     rng = np.random.RandomState(7)
@@ -192,6 +205,8 @@ def main(which):
         fixture_extract(m, "c1_640x480", 0, 480, 640, 1000, keep_image=True)
     if not which or "c2" in which:
         fixture_extract(m, "c2_1600x1200", 0, 1200, 1600, 4096, keep_image=False)
+    if not which or "ms" in which:
+        fixture_multiscale(m)
     if not which or "nms" in which:
         fixture_nms()
     if not which or "match" in which:

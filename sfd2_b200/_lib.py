@@ -12,7 +12,8 @@ DESC_DIM = 128
 
 class ExtractParams(C.Structure):
     _fields_ = [("conf_th", C.c_float), ("nms_radius", C.c_int32), ("border", C.c_int32),
-                ("topk", C.c_int32), ("precision", C.c_int32), ("use_stability", C.c_int32)]
+                ("topk", C.c_int32), ("precision", C.c_int32), ("use_stability", C.c_int32),
+                ("border_w", C.c_int32), ("border_h", C.c_int32)]
 
 
 class MatchParams(C.Structure):

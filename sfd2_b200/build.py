@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsfd2_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_match.cu", "post.cu", "match.cu", "umma_probe.cu"]
+SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_match.cu", "post.cu", "match.cu", "umma_probe.cu"]
 HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "sfd2_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

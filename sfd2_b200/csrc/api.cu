@@ -46,7 +46,7 @@ struct Ws {
   Act acts[NUM_ACTS];
   CUtensorMap maps[NUM_ACTS][6];
   CUtensorMap st_maps[NUM_ACTS][4];
-  CUtensorMap map_1a[2];                    // conv1a output rows: box {64 ch, 256 px, 1 row}
+  CUtensorMap map_1a[4];                    // conv1a output rows: [hi, lo] box {64 ch, 256 px, 1 row}, [hi, lo] box {64, 128, 1}
   CUtensorMap map_logits[2], map_desc[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float4* nimg = nullptr;  // normalised image, NHWC4 fp32
@@ -189,12 +189,12 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       a.tm_st = w.st_maps[i];
     }
     int rc = 0;
-    for (int pl = 0; pl < 2 && !rc; ++pl) {
+    for (int pl = 0; pl < 4 && !rc; ++pl) {
       const Act& a = w.acts[A1A];
       const uint64_t dims[3] = {64, (uint64_t)a.W, (uint64_t)a.H};
       const uint64_t str[2] = {128, (uint64_t)a.Wp * 128};
-      const uint32_t box[3] = {64u, 256u, 1u};
-      rc = make_tmap(&w.map_1a[pl], pl ? (const void*)a.lo : (const void*)a.hi, 3, dims, str, box, 0, 128);
+      const uint32_t box[3] = {64u, pl < 2 ? 256u : 128u, 1u};
+      rc = make_tmap(&w.map_1a[pl], (pl & 1) ? (const void*)a.lo : (const void*)a.hi, 3, dims, str, box, 0, 128);
     }
     for (int b = 0; b < 2 && !rc; ++b) {
       rc = tc_make_store_map(&w.map_logits[b], w.logits, 80, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
@@ -233,7 +233,7 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
-  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? 1 : 0, w.nimg, tc ? w.map_1a : nullptr, st));
+  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
   auto conv = [&](const char* name, int in, int out, int res) -> int {
     const Layer& L = c->L(name);
     prof_begin(c, (std::string(tc ? "tc_conv:" : "conv_f32:") + name).c_str(), st);
@@ -266,7 +266,8 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
   if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
   RUNP("heat", launch_heat(w.semi, w.H8, w.W8, w.sta, w.H4, w.W4, p->use_stability, w.heat, H, W, st));
-  RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
+  RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, p->border_w > 0 ? p->border_w : W, p->border_h > 0 ? p->border_h : H,
+                         (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
                  w.counter, st));
   RUNP("select", launch_select(w.cand, w.cap, w.counter, W, p->topk, kpts, scores, count, w.status, w.scratch, st));
   RUNP("sample", launch_sample(w.descmap, w.H4, w.W4, H, W, kpts, count, p->topk, desc, st));
@@ -301,6 +302,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;
   const char* env_streams = getenv("SFD2_STREAMS");
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
@@ -330,6 +332,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   for (Layer& L : c->layers) {
     int rc = upload_simt(L);
     if (!rc && L.cin % 64 == 0 && L.cout > 3) rc = tc_encode_weights(L);
+    if (!rc && L.name == "conv1a") rc = conv1a_mma_encode(L);
     if (rc) { sfd2_destroy(c); return rc; }
   }
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { sfd2_destroy(c); set_error("stream create failed"); return SFD2_ERR_CUDA; }
@@ -628,7 +631,8 @@ SFD2_API int sfd2_nms_select_dev(sfd2_ctx* c, const float* heat, int h, int w, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SFD2_CUDA(cudaMemsetAsync(status, 0, 4, st));
   const long long before = g_launches;
-  int rc = launch_nms(heat, h, w, p->conf_th, p->border, nms_out, cand, cap, counter, st);
+  int rc = launch_nms(heat, h, w, p->conf_th, p->border, p->border_w > 0 ? p->border_w : w, p->border_h > 0 ? p->border_h : h,
+                      nms_out, cand, cap, counter, st);
   if (!rc) rc = launch_select(cand, cap, counter, w, p->topk, kpts, scores, count, status, scratch, st);
   c->launches += g_launches - before;
   int hstatus = 0;

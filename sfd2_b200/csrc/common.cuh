@@ -71,7 +71,11 @@ struct TcConvLaunch;  // tc_conv.cu
 // ---- kernels' host-side launchers (each returns a sfd2_status) -------------------
 // simt_conv.cu
 int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out, float4* nimg,
-                  const CUtensorMap* tm1a, cudaStream_t st);
+                  const CUtensorMap* tm1a, int num_sms, cudaStream_t st);
+// tc_conv1a.cu
+int conv1a_mma_encode(Layer& L);
+int launch_conv1a_mma(const float4* nimg, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split, int num_sms,
+                      cudaStream_t st);
 int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cudaStream_t st);
 // tc_in: 0 = fp32 input, 1 = fp16 hi+lo, 2 = fp16 hi only
 int launch_sta(const Act& in, int tc_in, const Layer& L, float* logits, cudaStream_t st);
@@ -86,7 +90,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
 // post.cu
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st);
-int launch_nms(const float* heat, int H, int W, float conf_th, int border, float* nms_out,
+int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out,
                unsigned long long* cand, int cap, int* counter, cudaStream_t st);
 int launch_select(unsigned long long* cand, int cap, const int* counter, int W, int topk, float* kpts,
                   float* scores, int32_t* count_out, int* status, unsigned long long* scratch,
@@ -116,7 +120,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_multicast, g_tc_halo;
+extern int g_tc_multicast, g_tc_halo, g_conv1a_mma;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

@@ -144,7 +144,8 @@ __device__ __forceinline__ void pool9(const T* __restrict__ src, T* __restrict__
 }
 
 __global__ void __launch_bounds__(512)
-nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int border, float* __restrict__ nms_out,
+nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int border, int bw, int bh,
+           float* __restrict__ nms_out,
            unsigned long long* __restrict__ cand, int cap, int* __restrict__ counter) {
   extern __shared__ float sm[];
   float* s = sm;             // scores (-inf outside the image)
@@ -214,7 +215,7 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
     const int si = nidx(ty + NHALO, tx + NHALO);
     const float v = (in_img && m[si]) ? s[si] : 0.f;
     if (in_img && nms_out) nms_out[(size_t)y * W + x] = v;
-    const bool is_cand = in_img && (v > conf_th) && x >= border && x < W - border && y >= border && y < H - border;
+    const bool is_cand = in_img && (v > conf_th) && x >= border && x < bw - border && y >= border && y < bh - border;
     const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
     if (is_cand) {
       const int lane = threadIdx.x & 31;
@@ -231,7 +232,9 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
   }
 }
 
-int launch_nms(const float* heat, int H, int W, float conf_th, int border, float* nms_out, unsigned long long* cand,
+// bw / bh: the extents the border test uses (the reference tests scaled coordinates against the ORIGINAL
+// image size in its multi-scale loop, nets/extractor.py:181-182); pass W / H for the single-scale case
+int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out, unsigned long long* cand,
                int cap, int* counter, cudaStream_t st) {
   const size_t smem = (size_t)3 * NP_N * sizeof(float) + 3 * NP_N;
   static bool attr = false;
@@ -241,7 +244,7 @@ int launch_nms(const float* heat, int H, int W, float conf_th, int border, float
   }
   SFD2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   dim3 grid(cdiv(W, NT_W), cdiv(H, NT_H));
-  nms_kernel<<<grid, 512, smem, st>>>(heat, H, W, conf_th, border, nms_out, cand, cap, counter);
+  nms_kernel<<<grid, 512, smem, st>>>(heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

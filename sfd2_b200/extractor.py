@@ -100,9 +100,10 @@ def get_model(model_name, weight_path, use_stability=False, precision="exact"):
     return model, extract_resnet_return
 
 
-def _params(model, conf_th, topk, border=4):
+def _params(model, conf_th, topk, border=4, border_wh=(0, 0)):
     return _lib.ExtractParams(conf_th=float(conf_th), nms_radius=4, border=border, topk=int(topk),
-                              precision=_lib.PREC[model.precision], use_stability=int(model.require_stability))
+                              precision=_lib.PREC[model.precision], use_stability=int(model.require_stability),
+                              border_w=int(border_wh[0]), border_h=int(border_wh[1]))
 
 
 def _pack(kp, sc, de, n):
@@ -120,7 +121,7 @@ def extract_resnet_return(model, img, conf_th=0.001, mask=None, topK=-1, **kwarg
         raise NotImplementedError("the reference's mask/label branch is unreachable (labels undefined, :314)")
     scales = list(kwargs.get("scales", [1.0]))
     if scales != [1.0]:
-        raise NotImplementedError("multi-scale extraction is not implemented yet (all shipped presets use [1.0])")
+        return _extract_multiscale(model, img, conf_th, topK, scales)
     img = torch.as_tensor(img)
     if img.dtype != torch.float32:
         img = img.float()
@@ -153,6 +154,50 @@ def extract_resnet_return(model, img, conf_th=0.001, mask=None, topK=-1, **kwarg
     _lib.check(lib.sfd2_extract_host(ctx.handle, _np_ptr(a), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
                                      _np_ptr(kp), _np_ptr(sc), _np_ptr(de), _np_ptr(cnt)), "sfd2_extract_host")
     return _pack(kp, sc, de, int(cnt[0]))
+
+
+def _extract_multiscale(model, img, conf_th, topK, scales):
+    """The reference's scale loop (nets/extractor.py:118-220): for every scale the image is bilinearly
+    resized (the reference resizes the normalised image; normalisation is affine per channel, so resizing the
+    raw image and normalising on the device is the same map up to fp32 rounding), extracted at that size with
+    the border test against the ORIGINAL extents (:181-182), keypoints are mapped back with x*W/nw, y*H/nh in
+    float32 (:214-215), and the union is cut to topK by score (:322-326)."""
+    import torch.nn.functional as F
+    img = torch.as_tensor(img).float()
+    img = img.reshape(1, *img.shape[-3:]).cuda()
+    _, _, H, W = img.shape
+    ctx = model.ctx
+    lib = _lib.lib()
+    pts, descs, lin = [], [], []
+    for si, s in enumerate(scales):
+        if s == 1.0:
+            cur = img
+        else:
+            cur = F.interpolate(img, size=(int(H * s), int(W * s)), mode="bilinear", align_corners=False)
+        cur = cur.contiguous()
+        nh, nw = int(cur.shape[2]), int(cur.shape[3])
+        cap = int(topK) if topK and topK > 0 else (nh * nw) // 16 + 4096
+        kp = torch.zeros(cap, 2, dtype=torch.float32, device=img.device)
+        sc = torch.zeros(cap, dtype=torch.float32, device=img.device)
+        de = torch.empty(cap, _lib.DESC_DIM, dtype=torch.float32, device=img.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=img.device)
+        p = _params(model, conf_th, cap, border_wh=(W, H))
+        st = torch.cuda.current_stream(img.device).cuda_stream
+        _lib.check(lib.sfd2_extract_dev(ctx.handle, cur.data_ptr(), _lib.IMG_F32_NCHW, 1, nh, nw, C.byref(p),
+                                        kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
+                   "sfd2_extract_dev")
+        n = int(cnt.item())
+        k = kp[:n].cpu().numpy()
+        lin.append((si << 40) + k[:, 1].astype(np.int64) * nw + k[:, 0].astype(np.int64))
+        k = np.stack([k[:, 0] * np.float32(W) / np.float32(nw), k[:, 1] * np.float32(H) / np.float32(nh)], 1)
+        pts.append(np.concatenate([k.astype(np.float32), sc[:n].cpu().numpy()[:, None]], 1))
+        descs.append(de[:n].cpu().numpy())
+    pts, descs, lin = np.vstack(pts), np.vstack(descs), np.concatenate(lin)
+    order = np.lexsort((lin, -pts[:, 2].astype(np.float64)))
+    if topK and topK > 0:
+        order = order[:topK]
+    return {"keypoints": np.array(pts[order, :2], dtype=float), "descriptors": np.array(descs[order], dtype=float),
+            "scores": np.array(pts[order, 2], dtype=float)}
 
 
 class Extractor:

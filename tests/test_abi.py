@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     import ctypes as C
-    assert C.sizeof(_lib.ExtractParams) == 24
+    assert C.sizeof(_lib.ExtractParams) == 32
     assert C.sizeof(_lib.MatchParams) == 20
 
 

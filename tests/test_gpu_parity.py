@@ -295,3 +295,22 @@ def test_ratio_tests_match_reference(golden, prec):
         o2 = Matcher(matcher_confs["NNR"], precision=prec)({"descriptors0": d0.astype(np.float64),
                                                             "descriptors1": d1.astype(np.float64)})
         assert (o2["matches0"] != g[f"{tag}_itloc_nnr_m0"]).sum() <= 1, tag
+
+
+@pytest.mark.parametrize("prec", ["fp32", "exact"])
+def test_multiscale_extract_matches_reference(golden, prec):
+    """scales=[1.0, 0.75, 1.25] (nets/extractor.py:113-125): per-scale bilinear resize, border test against the
+    original extents, keypoints mapped back, union cut to topK."""
+    from gpu_util import model
+    from sfd2_b200 import extract_resnet_return
+    g = golden("ms_128x160")
+    img = torch.from_numpy((g["image_u8"].astype(np.float32) / np.float32(255)).transpose(2, 0, 1)[None].copy())
+    out = extract_resnet_return(model(prec), img, topK=int(g["K"]), conf_th=0.001, scales=list(g["scales"]))
+    a = {tuple(np.round(k, 3)) for k in out["keypoints"]}
+    b = {tuple(np.round(k, 3)) for k in g["kp"].astype(np.float64)}
+    assert len(a & b) >= len(b) - 2, f"{len(a & b)}/{len(b)} keypoints shared"
+    idx = {tuple(np.round(k, 3)): i for i, k in enumerate(g["kp"].astype(np.float64))}
+    hit = [(i, idx[tuple(np.round(k, 3))]) for i, k in enumerate(out["keypoints"]) if tuple(np.round(k, 3)) in idx]
+    i0, i1 = np.array(hit).T
+    assert np.abs(out["scores"][i0] - g["scores"][i1]).max() <= TOL
+    assert np.abs(out["descriptors"][i0] - g["desc"][i1]).max() <= TOL

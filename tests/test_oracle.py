@@ -106,3 +106,11 @@ def test_ratio_matchers_match_reference(golden):
         assert np.array_equal(p1["matches0"][0].numpy(), g[f"{tag}_hloc_ratio_nomutual_m0"]), tag
         pi = orc.match_itloc_nnr(d0.astype(np.float64), d1.astype(np.float64), 0.9)
         assert np.array_equal(pi["matches0"], g[f"{tag}_itloc_nnr_m0"]), tag
+
+
+def test_multiscale_extract_matches_reference(golden, oracle_state):
+    g = golden("ms_128x160")
+    out = orc.extract(oracle_state, _img(g["image_u8"]), topK=int(g["K"]), scales=list(g["scales"]))
+    np.testing.assert_allclose(out["keypoints"], g["kp"], atol=1e-4)
+    np.testing.assert_allclose(out["scores"], g["scores"], atol=1e-6)
+    np.testing.assert_allclose(out["descriptors"], g["desc"], atol=1e-5)
