@@ -47,7 +47,7 @@ struct Ws {
   CUtensorMap maps[NUM_ACTS][6];
   CUtensorMap st_maps[NUM_ACTS][4];
   CUtensorMap map_1a[4];                    // conv1a output rows: [hi, lo] box {64 ch, 256 px, 1 row}, [hi, lo] box {64, 128, 1}
-  CUtensorMap map_logits[2], map_desc[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
+  CUtensorMap map_logits[2], map_desc[2], map_semi[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float4* nimg = nullptr;  // normalised image, NHWC4 fp32
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
@@ -199,6 +199,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
     for (int b = 0; b < 2 && !rc; ++b) {
       rc = tc_make_store_map(&w.map_logits[b], w.logits, 80, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
       if (!rc) rc = tc_make_store_map(&w.map_desc[b], w.descmap, 128, w.W4, w.H4, w.W4, 1, b ? 8 : 16);
+      if (!rc) rc = tc_make_store_map(&w.map_semi[b], w.semi, 64, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
     }
     if (rc) return rc;
     w.have_tc = true;
@@ -256,14 +257,18 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   Act logit_act; logit_act.f32 = w.logits; logit_act.H = w.H8; logit_act.W = w.W8; logit_act.Wp = w.W8; logit_act.Hp = w.H8; logit_act.C = 80;
   Act desc_act;  desc_act.f32 = w.descmap; desc_act.H = w.H4; desc_act.W = w.W4; desc_act.Wp = w.W4; desc_act.Hp = w.H4; desc_act.C = 128;
   if (tc) {
-    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, w.map_logits, split, c->num_sms, st));
-    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split, c->num_sms, st));
+    // head epilogues fused: the detector head writes the exp-normalised 64 cell scores straight into `semi`,
+    // the descriptor head writes L2-normalised rows (no softmax65 / l2norm128 launches in the tcgen05 modes)
+    RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, w.map_semi, split, c->num_sms, st, 2));
+    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split, c->num_sms, st, 1));
   } else {
     RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
     RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
   }
-  RUNP("softmax65", launch_softmax65(w.logits, w.H8 * w.W8, w.semi, st));
-  RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
+  if (!tc) {
+    RUNP("softmax65", launch_softmax65(w.logits, w.H8 * w.W8, w.semi, st));
+    RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
+  }
   if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
   RUNP("heat", launch_heat(w.semi, w.H8, w.W8, w.sta, w.H4, w.W4, p->use_stability, w.heat, H, W, st));
   RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, p->border_w > 0 ? p->border_w : W, p->border_h > 0 ? p->border_h : H,

@@ -85,8 +85,9 @@ int launch_l2norm128(float* desc, int npix, cudaStream_t st);
 int tc_encode_weights(Layer& L);
 int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo);
 int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w);
+// epi_fn (fp32 outputs only): 0 raw, 1 L2-normalised channels, 2 exp-normalised (softmax-with-eps) channels 0..63
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st);
+                   int num_sms, cudaStream_t st, int epi_fn = 0);
 // post.cu
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st);

@@ -55,6 +55,8 @@ struct TcConvArgs {
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
   const float* bias;
   int out_mode;    // 0: fp16 hi plane only, 1: fp16 hi + lo planes, 2: fp32
+  int epi_fn;      // fp32 head epilogues: 0 none, 1 = L2-normalise the pixel's channels (F.normalize, sfd2.py:342),
+                   // 2 = exp / (sum_65 exp + 1e-5), channels 0..63 (sfd2.py:330-333); both need a first pass over TMEM
   int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
 };
 
@@ -327,7 +329,33 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
-      for (int ch = 0; ch < nchunks; ++ch, ++seq) {
+      float row_scale = 1.f;                      // head epilogues: per-pixel reduction over ALL channels first
+      if (a.epi_fn) {
+        float acc = 0.f;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          uint32_t v[32];
+          float x[32];
+          tmem_ld32(taddr + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+          if (a.corr) {
+            tmem_ld32(taddr + a.acc_cols + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float t = x[j] + sbias[ch * 32 + j];
+            if (ch * 32 + j < a.cout) acc += (a.epi_fn == 1) ? t * t : expf(t);
+          }
+        }
+        // one reciprocal per pixel, then multiplies (<= 1 ulp from the reference's per-element division)
+        row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
+      }
+      const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
+      for (int ch = 0; ch < nstore; ++ch, ++seq) {
         const int c0 = ch * 32;
         const int sb = seq & 1;
         uint8_t* st = wstage + sb * 4096;
@@ -351,6 +379,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int g = 0; g < 8; ++g) {
           const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + g * 4);
           x[g * 4] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
+        }
+        if (a.epi_fn == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] *= row_scale;
+        } else if (a.epi_fn == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = expf(x[j]) * row_scale;
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
@@ -548,7 +583,7 @@ int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for th
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st) {
+                   int num_sms, cudaStream_t st, int epi_fn) {
   SFD2_CHECK(in.tm != nullptr && in.hi != nullptr, SFD2_ERR_ARG, "conv_tc(%s): input has no tensor maps", L.name.c_str());
   SFD2_CHECK(in.C == L.cin && in.C % 64 == 0, SFD2_ERR_ARG, "conv_tc(%s): cin %d", L.name.c_str(), in.C);
   SFD2_CHECK(split == 1 || split == 3, SFD2_ERR_ARG, "conv_tc: split must be 1 or 3");
@@ -598,6 +633,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   }
   a.bias = L.b_dev;
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
+  a.epi_fn = out_f32_map ? epi_fn : 0;
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
   SFD2_CHECK(out_f32_map || out.tm_st, SFD2_ERR_ARG, "conv_tc(%s): output has no store maps", L.name.c_str());
   SFD2_CHECK(!res || res->tm_st, SFD2_ERR_ARG, "conv_tc(%s): residual has no store maps", L.name.c_str());

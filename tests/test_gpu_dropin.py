@@ -29,9 +29,10 @@ def test_extract_then_match_pipeline(tmp_path, oracle_state):
     ours, ref = Store(tmp_path / "f.npz", "r"), Store(tmp_path / "f_ref.npz", "r")
     for name in frames:
         a, b = ours.read(name), ref.read(name)
-        assert a["descriptors"].shape == (128, 400) and a["keypoints"].dtype == np.float64
+        n = b["keypoints"].shape[0]
+        assert 100 < n <= 400 and a["descriptors"].shape == (128, n) and a["keypoints"].dtype == np.float64
         ka, kb = set(map(tuple, np.round(a["keypoints"], 3))), set(map(tuple, np.round(b["keypoints"], 3)))
-        assert len(ka & kb) >= 398
+        assert len(ka & kb) >= n - 2
     pairs = ["a.jpg b.jpg", "a.jpg c.jpg", "b.jpg a.jpg"]
     nn = NearestNeighbor(match_confs["NNM"]["model"]).eval().to("cuda")
     with Store(tmp_path / "m.npz", "w") as ms:
@@ -42,5 +43,5 @@ def test_extract_then_match_pipeline(tmp_path, oracle_state):
     fa, fb = ours.read("a.jpg"), ours.read("b.jpg")
     refm = orc.match_hloc(fa["descriptors"][None], fb["descriptors"][None])["matches0"][0].numpy()
     assert (m_ab["matches0"] == refm).mean() > 0.995
-    assert (m_ab["matches0"] >= 0).sum() > 150          # the shifted twin matches; the unrelated frame does not
+    assert (m_ab["matches0"] >= 0).sum() > 100          # the shifted twin matches; the unrelated frame does not
     assert (ms.read(names_to_pair("a.jpg", "c.jpg"))["matches0"] >= 0).sum() < (m_ab["matches0"] >= 0).sum()
