@@ -127,6 +127,15 @@ SFD2_API int sfd2_match_batched_dev(sfd2_ctx* ctx, const float* d0_dev, const in
                            const sfd2_match_params* p, int32_t* matches0_dev, float* sim0_dev,
                            void* stream);
 
+/* One query set against many db sets in ONE grouped launch (it_loc/localize_cv2.py:705-731: a query against
+ * its <= 50 retrieved db images, each db set filtered by db_3D_ids != -1, :540-555).  db holds the db
+ * descriptor sets back to back, db_off_host[ndb+1] their row offsets (HOST array).
+ *   matches0 int32 [ndb, nq]  index into db set i (local), -1 / -2 as in sfd2_match_dev
+ *   sim0     float32 [ndb, nq] */
+SFD2_API int sfd2_match_one_to_many_dev(sfd2_ctx* ctx, const float* q_dev, int nq, const float* db_dev,
+                                        const int32_t* db_off_host, int ndb, int d, const sfd2_match_params* p,
+                                        int32_t* matches0_dev, float* sim0_dev, void* stream);
+
 /* Test / profiling hooks (not part of the reference surface). */
 /* Copy an intermediate of the LAST extracted image to host as float32:
  * "heat" [h,w], "nms" [h,w], "score" [h8*8? see DESIGN.md], "desc_map" [h4,w4,128],

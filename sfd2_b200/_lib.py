@@ -43,6 +43,8 @@ _PROTOS = {
                                   C.POINTER(MatchParams), C.c_void_p, C.c_void_p]),
     "sfd2_match_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sfd2_match_one_to_many_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_debug_fetch": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_longlong]),
     "sfd2_launch_count": (C.c_longlong, [C.c_void_p]),
     "sfd2_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -76,6 +76,7 @@ struct sfd2_ctx {
   // matcher workspace
   unsigned long long *row_key = nullptr, *col_key = nullptr; size_t key_cap = 0;
   unsigned *row2 = nullptr, *col2 = nullptr;   // second-best similarities (ratio tests)
+  int* seg_dev = nullptr; size_t seg_cap = 0;  // segment table of the one-to-many call
   __half* mhalf = nullptr; size_t mhalf_cap = 0;
   float *m_d0 = nullptr, *m_d1 = nullptr; size_t m_d0_cap = 0, m_d1_cap = 0;
   int32_t* m_out = nullptr; float* m_sim = nullptr; size_t m_out_cap = 0;
@@ -352,7 +353,7 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   for (Ws& w : c->ws) free_workspace(w);
   for (Layer& L : c->layers) free_layer(L);
   cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
-  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
+  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2); cudaFree(c->seg_dev); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
   cudaFree(c->m_out); cudaFree(c->m_sim);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -553,6 +554,63 @@ SFD2_API int sfd2_match_batched_dev(sfd2_ctx* c, const float* d0, const int32_t*
   for (int i = 0; i < npairs && !rc; ++i)
     rc = match_one(c, d0 + (size_t)off0[i] * d, off0[i + 1] - off0[i], d1 + (size_t)off1[i] * d, off1[i + 1] - off1[i],
                    d, p, matches0 + off0[i], sim0 + off0[i], static_cast<cudaStream_t>(stream));
+  c->launches += g_launches - before;
+  return rc;
+}
+
+SFD2_API int sfd2_match_one_to_many_dev(sfd2_ctx* c, const float* q, int nq, const float* db, const int32_t* db_off,
+                                        int ndb, int d, const sfd2_match_params* p, int32_t* matches0, float* sim0,
+                                        void* stream) {
+  SFD2_CHECK(c && p && q && db && db_off && matches0 && sim0, SFD2_ERR_ARG, "sfd2_match_one_to_many_dev: NULL argument");
+  SFD2_CHECK(nq >= 1 && ndb >= 1 && d == 128, SFD2_ERR_ARG, "sfd2_match_one_to_many_dev: bad shape (d must be 128)");
+  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio tests are not available in the grouped call: use sfd2_match_batched_dev");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->precision == SFD2_PREC_FP32) {   // CUDA-core mode: plain loop
+    int rc = SFD2_OK;
+    for (int i = 0; i < ndb && !rc; ++i)
+      rc = sfd2_match_dev(c, q, nq, db + (size_t)db_off[i] * d, db_off[i + 1] - db_off[i], d, p, matches0 + (size_t)i * nq,
+                          sim0 + (size_t)i * nq, stream);
+    return rc;
+  }
+  std::vector<int> seg(3 * (ndb + 1));
+  int P1 = 0;
+  for (int i = 0; i < ndb; ++i) {
+    SFD2_CHECK(db_off[i + 1] >= db_off[i], SFD2_ERR_ARG, "offsets must be non-decreasing");
+    seg[i] = db_off[i];
+    seg[(ndb + 1) + i] = P1;
+    seg[2 * (ndb + 1) + i] = db_off[i + 1] - db_off[i];
+    P1 += round_up(std::max(db_off[i + 1] - db_off[i], 1), 128);
+  }
+  seg[ndb] = db_off[ndb];
+  seg[(ndb + 1) + ndb] = P1;
+  // workspace: keys [max(nq*ndb, P1)], split planes [(nq_pad + P1) * 2 * 128] halves, segment table
+  const size_t need_keys = std::max((size_t)nq * ndb, (size_t)P1) + 128;
+  if (need_keys > c->key_cap) {
+    cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2);
+    c->row_key = c->col_key = nullptr; c->row2 = c->col2 = nullptr; c->key_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->row_key, need_keys * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->col_key, need_keys * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMalloc(&c->row2, need_keys * sizeof(unsigned)));
+    SFD2_CUDA(cudaMalloc(&c->col2, need_keys * sizeof(unsigned)));
+    c->key_cap = need_keys;
+  }
+  const size_t hneed = 2 * ((size_t)round_up(nq, 128) + P1) * 128;
+  if (hneed > c->mhalf_cap) {
+    cudaFree(c->mhalf); c->mhalf = nullptr; c->mhalf_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->mhalf, hneed * sizeof(__half)));
+    c->mhalf_cap = hneed;
+  }
+  if (seg.size() > c->seg_cap) {
+    cudaFree(c->seg_dev); c->seg_dev = nullptr; c->seg_cap = 0;
+    SFD2_CUDA(cudaMalloc(&c->seg_dev, seg.size() * sizeof(int)));
+    c->seg_cap = seg.size();
+  }
+  SFD2_CUDA(cudaMemcpyAsync(c->seg_dev, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  const long long before = g_launches;
+  const int rc = launch_match_one_to_many(q, nq, db, c->seg_dev, ndb, P1, p->precision == SFD2_PREC_TC_EXACT ? 3 : 1,
+                                          p->do_mutual_check, p->distance_threshold, c->mhalf, c->row_key, c->col_key,
+                                          matches0, sim0, c->num_sms, st);
   c->launches += g_launches - before;
   return rc;
 }

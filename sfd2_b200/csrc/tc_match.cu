@@ -50,6 +50,13 @@ constexpr int TM_MAX_STAGES = 6;
 
 struct TcMatchArgs {
   int n0, n1, tiles_m, tiles_n, split, stages, stage_bytes;
+  int do_cols;   // 1: also reduce the tile's columns (smem transpose + per-column atomics) in the same pass
+  // one-to-many: the B operand is a concatenation of nseg row segments, each padded to a multiple of 128 rows
+  // (seg_poff = padded starts, seg_len = valid rows); row keys are then kept per (segment, row): key index
+  // seg * n0 + i, column index local to the segment
+  int nseg;
+  const int* seg_poff;
+  const int* seg_len;
   unsigned long long* row_key;
   unsigned long long* col_key;
 };
@@ -143,8 +150,17 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     int buf = 0;
     uint32_t bphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int r0 = (tile / a.tiles_n) * TM_TILE, c0 = (tile % a.tiles_n) * TM_TILE;
+      const int r0 = (tile / a.tiles_n) * TM_TILE;
+      int c0 = (tile % a.tiles_n) * TM_TILE;
       const int i = r0 + q * 32 + lane;
+      int n1 = a.n1, seg = 0;
+      if (a.nseg > 0) {                         // which segment does this column block belong to?
+        int lo = 0, hi = a.nseg - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(a.seg_poff + mid) <= c0) lo = mid; else hi = mid - 1; }
+        seg = lo;
+        c0 -= __ldg(a.seg_poff + seg);          // column index local to the segment
+        n1 = __ldg(a.seg_len + seg);
+      }
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
@@ -157,12 +173,13 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         const int jbase = c0 + ch * 32;
         // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row); strict '>' keeps
         // the lowest column among equal values
-        const int cols_valid = min(32, a.n1 - jbase);
+        const int cols_valid = min(32, n1 - jbase);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float s = __uint_as_float(v[j]);
           if (j < cols_valid && s > rbest) { rbest = s; rbest_j = jbase + j; }
         }
+        if (!a.do_cols) continue;
         // column arg-max over this warp's 32 rows: transpose through smem, one column per lane
 #pragma unroll
         for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = __uint_as_float(v[j]);
@@ -178,7 +195,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         __syncwarp();
         if (besti >= 0 && lane < cols_valid) atomicMax(a.col_key + jbase + lane, m_key(best, r0 + q * 32 + besti));
       }
-      if (i < a.n0 && rbest_j >= 0) atomicMax(a.row_key + i, m_key(rbest, rbest_j));
+      if (i < a.n0 && rbest_j >= 0) atomicMax(a.row_key + (size_t)seg * a.n0 + i, m_key(rbest, rbest_j));
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
@@ -222,16 +239,126 @@ int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int
     rc = make_tmap_f16(&tB_lo, b_lo, 2, dims, strides, box);
     if (rc) return rc;
   }
-  TcMatchArgs a{};
-  a.n0 = n0; a.n1 = n1; a.tiles_m = n0p / TM_TILE; a.tiles_n = n1p / TM_TILE; a.split = split;
-  a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
-  a.stages = (split == 3) ? 3 : 6;
-  a.row_key = row_key; a.col_key = col_key;
-  const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
-  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = a.tiles_m * a.tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+  // Two passes with swapped operands: D0*D1^T reduces rows into row_key, D1*D0^T reduces ITS rows (= the columns of
+  // the first product) into col_key.  The GEMM is ~3 us of tensor work either way; what costs is the epilogue, and
+  // the row reduction is thread-local (one TMEM lane = one row) while a column reduction needs a shared-memory
+  // transpose plus 128 atomics per warp per tile.  Doing the cheap reduction twice is ~2x faster than doing both at once.
+  for (int pass = 0; pass < 2; ++pass) {
+    TcMatchArgs a{};
+    a.n0 = pass ? n1 : n0; a.n1 = pass ? n0 : n1;
+    a.tiles_m = (pass ? n1p : n0p) / TM_TILE; a.tiles_n = (pass ? n0p : n1p) / TM_TILE; a.split = split;
+    a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
+    a.stages = (split == 3) ? 3 : 6;
+    a.row_key = pass ? col_key : row_key; a.col_key = nullptr; a.do_cols = 0;
+    const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+    SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = a.tiles_m * a.tiles_n;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (pass == 0) tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+    else tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tB_hi, tB_lo, tA_hi, tA_lo, a);
+    ++g_launches;
+  }
+  SFD2_CUDA(cudaGetLastError());
+  return SFD2_OK;
+}
+
+// rows of `nseg` segments (unpadded starts `off`, padded starts `poff`) -> fp16 hi / lo rows in the padded layout
+__global__ void split_rows_seg_kernel(const float* __restrict__ src, const int* __restrict__ off,
+                                      const int* __restrict__ poff, int nseg, int total_padded,
+                                      __half* __restrict__ hi, __half* __restrict__ lo) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+  if (idx >= total_padded * 32) return;
+  const int r = idx >> 5;
+  int a = 0, b = nseg - 1;
+  while (a < b) { const int mid = (a + b + 1) >> 1; if (__ldg(poff + mid) <= r) a = mid; else b = mid - 1; }
+  const int local = r - __ldg(poff + a), len = __ldg(off + a + 1) - __ldg(off + a);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (local < len) v = __ldg(reinterpret_cast<const float4*>(src) + (size_t)(__ldg(off + a) + local) * 32 + (idx & 31));
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(x[j]);
+    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
+}
+
+// matches0[p*nq + i] = local column of segment p (or -1 / -2), sim0[p*nq + i] = best similarity
+__global__ void match_finish_seg_kernel(const unsigned long long* __restrict__ row_key,
+                                        const unsigned long long* __restrict__ col_key_padded,
+                                        const int* __restrict__ poff, int nq, int nseg, int mutual, float dist_th,
+                                        int32_t* __restrict__ matches0, float* __restrict__ sim0) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq * nseg) return;
+  const int p = t / nq, i = t - p * nq;
+  const unsigned long long k = row_key[t];
+  if (k == 0ull) { matches0[t] = -1; sim0[t] = 0.f; return; }
+  const int j = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+  const unsigned o = (unsigned)(k >> 32);
+  const float s = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+  bool ok = true;
+  if (dist_th > 0.f) ok = (2.f * (1.f - s)) <= dist_th * dist_th;
+  const bool row_ok = ok;
+  if (ok && mutual) {
+    const unsigned long long kc = col_key_padded[__ldg(poff + p) + j];
+    ok = (kc != 0ull) && ((int)(0xFFFFFFFFu - (unsigned)(kc & 0xFFFFFFFFull)) == i);
+  }
+  matches0[t] = ok ? j : (row_ok ? -2 : -1);
+  sim0[t] = s;
+}
+
+// One query set against many db sets in one grouped launch (it_loc/localize_cv2.py:705: a query against the <= 50
+// retrieved db images).  seg_dev: device ints [off(nseg+1) | poff(nseg+1) | len(nseg)]; P1 = total padded db rows.
+int launch_match_one_to_many(const float* q, int nq, const float* db, const int* seg_dev, int nseg, int P1, int split,
+                             int mutual, float dist_th, __half* ws_half, unsigned long long* row_key,
+                             unsigned long long* col_key, int32_t* matches0, float* sim0, int num_sms, cudaStream_t st) {
+  const int* off = seg_dev;
+  const int* poff = seg_dev + (nseg + 1);
+  const int* len = seg_dev + 2 * (nseg + 1);
+  SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)nq * nseg, st));
+  SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)P1, st));
+  const int nqp = round_up(nq, TM_TILE);
+  __half* a_hi = ws_half;
+  __half* a_lo = a_hi + (size_t)nqp * 128;
+  __half* b_hi = a_lo + (size_t)nqp * 128;
+  __half* b_lo = b_hi + (size_t)P1 * 128;
+  split_rows_kernel<<<cdiv(nqp * 32, 256), 256, 0, st>>>(q, nq, nqp, a_hi, a_lo);
+  split_rows_seg_kernel<<<cdiv(P1 * 32, 256), 256, 0, st>>>(db, off, poff, nseg, P1, b_hi, b_lo);
+  g_launches += 2;
+  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
+  const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
+  const uint64_t strides[1] = {256};
+  const uint64_t dq[2] = {128, (uint64_t)nqp}, dd[2] = {128, (uint64_t)P1};
+  int rc = make_tmap_f16(&tA_hi, a_hi, 2, dq, strides, box);
+  if (!rc) rc = make_tmap_f16(&tA_lo, a_lo, 2, dq, strides, box);
+  if (!rc) rc = make_tmap_f16(&tB_hi, b_hi, 2, dd, strides, box);
+  if (!rc) rc = make_tmap_f16(&tB_lo, b_lo, 2, dd, strides, box);
+  if (rc) return rc;
+  for (int pass = 0; pass < 2; ++pass) {
+    TcMatchArgs a{};
+    a.split = split;
+    a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
+    a.stages = (split == 3) ? 3 : 6;
+    a.do_cols = 0; a.col_key = nullptr;
+    if (pass == 0) {   // rows = query, columns = padded db segments -> row_key[seg * nq + i]
+      a.n0 = nq; a.n1 = P1; a.tiles_m = nqp / TM_TILE; a.tiles_n = P1 / TM_TILE;
+      a.nseg = nseg; a.seg_poff = poff; a.seg_len = len; a.row_key = row_key;
+    } else {           // rows = padded db rows, columns = query -> col_key[padded db row]
+      a.n0 = P1; a.n1 = nq; a.tiles_m = P1 / TM_TILE; a.tiles_n = nqp / TM_TILE;
+      a.nseg = 0; a.row_key = col_key;
+    }
+    const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+    SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = a.tiles_m * a.tiles_n;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (pass == 0) tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+    else tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tB_hi, tB_lo, tA_hi, tA_lo, a);
+    ++g_launches;
+  }
+  match_finish_seg_kernel<<<cdiv(nq * nseg, 256), 256, 0, st>>>(row_key, col_key, poff, nq, nseg, mutual, dist_th, matches0, sim0);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

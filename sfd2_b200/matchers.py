@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["BaseModel", "NearestNeighbor", "NearestNeighborMixin", "Matcher", "confs", "match_batched"]
+__all__ = ["BaseModel", "NearestNeighbor", "NearestNeighborMixin", "Matcher", "confs", "match_batched", "match_one_to_many"]
 
 _BLOB = None
 _CTX = {}
@@ -89,6 +89,25 @@ def match_batched(d0: torch.Tensor, off0, d1: torch.Tensor, off1, mutual=True, d
                                                  o0.ctypes.data_as(C.c_void_p), d1.data_ptr(),
                                                  o1.ctypes.data_as(C.c_void_p), npairs, d0.shape[1], C.byref(p),
                                                  m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_batched_dev")
+    m0.clamp_(min=-1)
+    return m0, s0
+
+
+def match_one_to_many(q: torch.Tensor, db: torch.Tensor, db_off, mutual=True, dist_th=None, precision="exact"):
+    """One query set q [N,128] against ndb db sets stored back to back in db (row offsets db_off, length
+    ndb+1) in ONE grouped launch - the localizer's pattern (a query against its retrieved db images).
+    -> (matches0 int32 [ndb, N] local indices or -1, sim0 float32 [ndb, N])."""
+    q, db = q.contiguous(), db.contiguous()
+    off = np.ascontiguousarray(db_off, np.int32)
+    ndb = len(off) - 1
+    dev = q.device
+    m0 = torch.full((ndb, q.shape[0]), -1, dtype=torch.int32, device=dev)
+    s0 = torch.zeros((ndb, q.shape[0]), dtype=torch.float32, device=dev)
+    p = _mparams(mutual, dist_th, None, precision)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(_lib.lib().sfd2_match_one_to_many_dev(_ctx(dev.index or 0).handle, q.data_ptr(), q.shape[0], db.data_ptr(),
+                                                     off.ctypes.data_as(C.c_void_p), ndb, q.shape[1], C.byref(p),
+                                                     m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_one_to_many_dev")
     m0.clamp_(min=-1)
     return m0, s0
 

@@ -338,3 +338,29 @@ def test_real_world_size_against_oracle(oracle_state):
     i0, i1 = np.array(hit).T
     assert np.abs(out["scores"][i0] - ref["scores"][i1]).max() <= TOL
     assert np.abs(out["descriptors"][i0] - ref["descriptors"][i1]).max() <= TOL
+
+
+@pytest.mark.parametrize("prec", ["fp32", "exact"])
+def test_one_to_many_matches_pairwise(prec):
+    """The grouped one-query-vs-many-db launch must equal the per-pair calls (ragged db sizes, incl. tiny ones)."""
+    from sfd2_b200.matchers import match_dev, match_one_to_many
+    rng = np.random.RandomState(8)
+    q, _ = synth_descriptors(31, 1000, 10)
+    sizes = [700, 128, 1, 333, 2049, 64]
+    dbs = []
+    for k, m in enumerate(sizes):
+        d = rng.randn(m, 128).astype(np.float32)
+        take = min(m, 300)
+        d[:take] = q[rng.permutation(1000)[:take]] + 0.2 * rng.randn(take, 128).astype(np.float32)
+        dbs.append(d / np.linalg.norm(d, axis=1, keepdims=True))
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    qd = torch.from_numpy(q).cuda()
+    dbd = torch.from_numpy(np.concatenate(dbs)).cuda()
+    m_all, s_all = match_one_to_many(qd, dbd, off, precision=prec)
+    assert m_all.shape == (len(sizes), 1000)
+    for k in range(len(sizes)):
+        m, s_ = match_dev(qd, dbd[off[k]:off[k + 1]], precision=prec)
+        assert torch.equal(m_all[k], m), k
+        assert torch.allclose(s_all[k], s_, atol=1e-6), k
+        ref = orc.match_hloc(q.T[None], dbs[k].T[None])["matches0"][0].numpy()
+        assert (m.cpu().numpy() == ref).mean() > 0.999
