@@ -88,7 +88,8 @@ SFD2_API int sfd2_abi_version(void);
 SFD2_API const char* sfd2_last_error(void);
 
 /* Replaces get_model(...)[0] + model.cuda()  (extract_localization.py:208-218,227).
- * `blob` is the folded weight blob made by sfd2_b200/weights.py (host memory). */
+ * `blob` is the folded weight blob made by sfd2_b200/weights.py (host memory); blob == NULL creates a
+ * matcher-only context (the matcher entry points need no network weights). */
 SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx** out);
 SFD2_API int sfd2_destroy(sfd2_ctx* ctx);
 

@@ -84,10 +84,15 @@ def check(rc, what):
 class Context:
     """Owns one native sfd2_ctx (weights + workspace) on one CUDA device."""
 
-    def __init__(self, blob: bytes, device: int):
+    def __init__(self, blob, device: int):
+        """blob: folded weight blob (bytes), or None for a matcher-only context."""
         self._h = C.c_void_p()
-        self._blob = C.create_string_buffer(blob, len(blob))
-        check(lib().sfd2_create(self._blob, len(blob), int(device), C.byref(self._h)), "sfd2_create")
+        if blob is None:
+            self._blob = None
+            check(lib().sfd2_create(None, 0, int(device), C.byref(self._h)), "sfd2_create")
+        else:
+            self._blob = C.create_string_buffer(blob, len(blob))
+            check(lib().sfd2_create(self._blob, len(blob), int(device), C.byref(self._h)), "sfd2_create")
         self.device = int(device)
 
     @property

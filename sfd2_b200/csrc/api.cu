@@ -298,13 +298,16 @@ SFD2_API int sfd2_abi_version(void) { return SFD2_ABI_VERSION; }
 SFD2_API const char* sfd2_last_error(void) { return g_err; }
 
 SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx** out) {
-  SFD2_CHECK(blob && out, SFD2_ERR_ARG, "sfd2_create: NULL argument");
+  SFD2_CHECK(out, SFD2_ERR_ARG, "sfd2_create: NULL argument");
   *out = nullptr;
-  SFD2_CHECK(nbytes >= 16 && memcmp(blob, "SFD2W001", 8) == 0, SFD2_ERR_WEIGHTS, "bad weight blob magic");
+  // blob == NULL: a matcher-only context (no network weights; extract calls fail with SFD2_ERR_WEIGHTS)
   const uint8_t* base = static_cast<const uint8_t*>(blob);
-  uint32_t nl;
-  memcpy(&nl, base + 8, 4);
-  SFD2_CHECK(nl > 0 && nl < 64 && 16 + (size_t)nl * sizeof(BlobLayer) <= nbytes, SFD2_ERR_WEIGHTS, "bad layer count %u", nl);
+  uint32_t nl = 0;
+  if (blob) {
+    SFD2_CHECK(nbytes >= 16 && memcmp(blob, "SFD2W001", 8) == 0, SFD2_ERR_WEIGHTS, "bad weight blob magic");
+    memcpy(&nl, base + 8, 4);
+    SFD2_CHECK(nl > 0 && nl < 64 && 16 + (size_t)nl * sizeof(BlobLayer) <= nbytes, SFD2_ERR_WEIGHTS, "bad layer count %u", nl);
+  }
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
@@ -334,7 +337,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
     c->layers.push_back(std::move(L));
   }
   for (const char* n : kLayerNames)
-    if (!c->lidx.count(n)) { delete c; set_error("weight blob lacks layer %s", n); return SFD2_ERR_WEIGHTS; }
+    if (blob && !c->lidx.count(n)) { delete c; set_error("weight blob lacks layer %s", n); return SFD2_ERR_WEIGHTS; }
   for (Layer& L : c->layers) {
     int rc = upload_simt(L);
     if (!rc && L.cin % 64 == 0 && L.cout > 3) rc = tc_encode_weights(L);
@@ -370,6 +373,7 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
 static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
                          float* kpts, float* scores, float* desc, int32_t* counts, void* stream, const cudaEvent_t* ready) {
   SFD2_CHECK(c && img && kpts && scores && desc && counts, SFD2_ERR_ARG, "sfd2_extract_dev: NULL argument");
+  SFD2_CHECK(!c->layers.empty(), SFD2_ERR_WEIGHTS, "this context was created without network weights (matcher only)");
   int rc = check_params(p, n, h, w);
   if (rc) return rc;
   SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "bad image dtype %d", img_dtype);

@@ -237,11 +237,7 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
 int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out, unsigned long long* cand,
                int cap, int* counter, cudaStream_t st) {
   const size_t smem = (size_t)3 * NP_N * sizeof(float) + 3 * NP_N;
-  static bool attr = false;
-  if (!attr) {
-    SFD2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  SFD2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch (cheap)
   SFD2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   dim3 grid(cdiv(W, NT_W), cdiv(H, NT_H));
   nms_kernel<<<grid, 512, smem, st>>>(heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter);

@@ -223,11 +223,7 @@ int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, 
   if (tc_out) {
     SFD2_CHECK(tm1a != nullptr, SFD2_ERR_ARG, "conv1a: store maps missing");
     const int smem = 1024 + 2 * C1_SEG * 128 + 7168 + 9 * 260 * 4;
-    static bool attr = false;
-    if (!attr) {
-      SFD2_CUDA(cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr = true;
-    }
+    SFD2_CUDA(cudaFuncSetAttribute(conv1a_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
     const int nseg = cdiv(W, C1_SEG) * H;
     conv1a_tc_kernel<<<std::min(nseg, 148 * 2), 256, smem, st>>>(nimg, H, W, L.w_simt, L.b_dev, tm1a[0], tm1a[1]);
   } else {
@@ -388,11 +384,7 @@ int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cud
   if (L.groups == 32) {
     SFD2_CHECK(L.cin == 256 && L.cout == 256 && L.k == 3 && L.stride == 1, SFD2_ERR_WEIGHTS, "gconv shape");
     const size_t smem = (9 * 8 * 256 + 256) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-      SFD2_CUDA(cudaFuncSetAttribute(gconv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
+    SFD2_CUDA(cudaFuncSetAttribute(gconv_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch (cheap)
     dim3 grid(cdiv(cdiv(in.W, 4), 8), in.H);
     gconv_f32_kernel<<<grid, 256, smem, st>>>(in.f32, in.H, in.W, in.Wp, L.w_simt, L.b_dev, out.f32, L.relu);
   } else {

@@ -183,11 +183,7 @@ int launch_conv1a_mma(const float4* nimg, int H, int W, const Layer& L, const CU
   SFD2_CHECK(L.w_hi && L.w_lo && tm1a, SFD2_ERR_ARG, "conv1a_mma: weights / store maps missing");
   Conv1aMmaArgs a{H, W, split, nimg, L.w_hi, L.w_lo, L.b_dev};
   const int smem = 1024 + 81920 + (9 * 132 + 64) * 4 + 64;
-  static bool attr = false;
-  if (!attr) {
-    SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
+  SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
   const int nseg = cdiv(W, C1M_SEG) * H;
   conv1a_mma_kernel<<<std::min(nseg, 2 * num_sms), 128, smem, st>>>(tm1a[0], tm1a[1], a);
   ++g_launches;

@@ -6,6 +6,11 @@
 // ~22 bits): split==3 issues d0_hi*d1_hi + d0_hi*d1_lo + d0_lo*d1_hi into one fp32 accumulator,
 // which reproduces the fp32 reference arg-max on real SFD2 descriptors;
 // split==1 is the single-pass fp16 variant.
+//
+// Each CTA owns a CONTIGUOUS range of tiles in row-major order and keeps the A row-block (both K halves, hi and lo
+// planes: 64 KB) resident in shared memory while it walks along the columns; only the B tiles stream through the
+// stage ring.  The first version reloaded A for every tile and was bound by L2->SM bandwidth (128 KB per 1536 MMA
+// cycles per SM, ncu: tensor pipe 42 % active).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -67,12 +72,17 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
                 const __grid_constant__ TcMatchArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* xpose = reinterpret_cast<float*>(smem + (size_t)a.stages * a.stage_bytes);  // 4 warps x 32 x 33 floats
+  const int nops = (a.split == 3) ? 2 : 1;
+  uint8_t* aslot = smem;                                       // resident A: [kb][plane] x 16 KB
+  uint8_t* bring = smem + 2 * nops * TM_OP_BYTES;              // B ring: stage = [plane] x 16 KB of one K half
+  float* xpose = reinterpret_cast<float*>(bring + (size_t)a.stages * a.stage_bytes);  // 4 warps x 32 x 33 floats
   uint64_t* full = reinterpret_cast<uint64_t*>(xpose + 4 * 32 * 33);
   uint64_t* empty = full + TM_MAX_STAGES;
   uint64_t* tfull = empty + TM_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* afull = tempty + 2;
+  uint64_t* aempty = afull + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -82,6 +92,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(afull, 1); mbar_init(aempty, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 256);
@@ -90,25 +101,33 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int num_tiles = a.tiles_m * a.tiles_n;
-  const int nops = (a.split == 3) ? 2 : 1;
+  const int per_cta = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_begin = (int)blockIdx.x * per_cta;
+  const int tile_end = min(tile_begin + per_cta, num_tiles);
 
   if (warp == 0) {
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int r0 = (tile / a.tiles_n) * TM_TILE, c0 = (tile % a.tiles_n) * TM_TILE;
+      int stage = 0, prev_mt = -1;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int mt = tile / a.tiles_n;
+        const int r0 = mt * TM_TILE, c0 = (tile - mt * a.tiles_n) * TM_TILE;
+        if (mt != prev_mt) {                    // new row-block: (re)load the resident A operand
+          mbar_wait(aempty, aphase ^ 1);
+          mbar_expect_tx(afull, (uint32_t)(2 * nops * TM_OP_BYTES));
+          for (int kb = 0; kb < 2; ++kb) {
+            tma_load_2d(aslot + (kb * nops) * TM_OP_BYTES, &tmA_hi, afull, kb * 64, r0);
+            if (a.split == 3) tma_load_2d(aslot + (kb * nops + 1) * TM_OP_BYTES, &tmA_lo, afull, kb * 64, r0);
+          }
+          aphase ^= 1;
+          prev_mt = mt;
+        }
         for (int kb = 0; kb < 2; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
-          uint8_t* sb = sa + nops * TM_OP_BYTES;
+          uint8_t* sb = bring + (size_t)stage * a.stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
-          tma_load_2d(sa, &tmA_hi, &full[stage], kb * 64, r0);
           tma_load_2d(sb, &tmB_hi, &full[stage], kb * 64, c0);
-          if (a.split == 3) {
-            tma_load_2d(sa + TM_OP_BYTES, &tmA_lo, &full[stage], kb * 64, r0);
-            tma_load_2d(sb + TM_OP_BYTES, &tmB_lo, &full[stage], kb * 64, c0);
-          }
+          if (a.split == 3) tma_load_2d(sb + TM_OP_BYTES, &tmB_lo, &full[stage], kb * 64, c0);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -116,16 +135,22 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      int stage = 0, buf = 0;
-      uint32_t phase = 0, bphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int stage = 0, buf = 0, prev_mt = -1;
+      uint32_t phase = 0, bphase = 0, aphase = 0;
+      for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int mt = tile / a.tiles_n;
+        if (mt != prev_mt) {
+          mbar_wait(afull, aphase);
+          aphase ^= 1;
+          prev_mt = mt;
+        }
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < 2; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
-          const uint32_t sb = sa + nops * TM_OP_BYTES;
+          const uint32_t sa = smem_u32(aslot + (kb * nops) * TM_OP_BYTES);
+          const uint32_t sb = smem_u32(bring + (size_t)stage * a.stage_bytes);
           const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + TM_OP_BYTES);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
@@ -141,6 +166,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[buf]);
+        // last tile of this row-block (or of the CTA): the resident A may be replaced once these MMAs are done
+        if (tile + 1 == tile_end || (tile + 1) / a.tiles_n != mt) umma_commit(aempty);
         if (++buf == 2) { buf = 0; bphase ^= 1; }
       }
     }
@@ -149,7 +176,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     float* xp = xpose + q * 32 * 33;
     int buf = 0;
     uint32_t bphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int r0 = (tile / a.tiles_n) * TM_TILE;
       int c0 = (tile % a.tiles_n) * TM_TILE;
       const int i = r0 + q * 32 + lane;
@@ -247,10 +274,11 @@ int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int
     TcMatchArgs a{};
     a.n0 = pass ? n1 : n0; a.n1 = pass ? n0 : n1;
     a.tiles_m = (pass ? n1p : n0p) / TM_TILE; a.tiles_n = (pass ? n0p : n1p) / TM_TILE; a.split = split;
-    a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
-    a.stages = (split == 3) ? 3 : 6;
+    a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
+    a.stages = 4;
     a.row_key = pass ? col_key : row_key; a.col_key = nullptr; a.do_cols = 0;
-    const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+    const size_t smem = (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)a.stages * a.stage_bytes +
+                        4 * 32 * 33 * sizeof(float) + 1024 + 256;
     SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = a.tiles_m * a.tiles_n;
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -340,8 +368,8 @@ int launch_match_one_to_many(const float* q, int nq, const float* db, const int*
   for (int pass = 0; pass < 2; ++pass) {
     TcMatchArgs a{};
     a.split = split;
-    a.stage_bytes = 2 * TM_OP_BYTES * (split == 3 ? 2 : 1);
-    a.stages = (split == 3) ? 3 : 6;
+    a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
+    a.stages = 4;
     a.do_cols = 0; a.col_key = nullptr;
     if (pass == 0) {   // rows = query, columns = padded db segments -> row_key[seg * nq + i]
       a.n0 = nq; a.n1 = P1; a.tiles_m = nqp / TM_TILE; a.tiles_n = P1 / TM_TILE;
@@ -350,7 +378,8 @@ int launch_match_one_to_many(const float* q, int nq, const float* db, const int*
       a.n0 = P1; a.n1 = nq; a.tiles_m = P1 / TM_TILE; a.tiles_n = nqp / TM_TILE;
       a.nseg = 0; a.row_key = col_key;
     }
-    const size_t smem = (size_t)a.stages * a.stage_bytes + 4 * 32 * 33 * sizeof(float) + 1024 + 256;
+    const size_t smem = (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)a.stages * a.stage_bytes +
+                        4 * 32 * 33 * sizeof(float) + 1024 + 256;
     SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = a.tiles_m * a.tiles_n;
     const int grid = tiles < num_sms ? tiles : num_sms;

@@ -17,30 +17,13 @@ from . import _lib
 
 __all__ = ["BaseModel", "NearestNeighbor", "NearestNeighborMixin", "Matcher", "confs", "match_batched", "match_one_to_many"]
 
-_BLOB = None
 _CTX = {}
 
 
 def _ctx(device_index: int) -> "_lib.Context":
-    """The matcher needs no network weights; it shares a context per device built from a
-    minimal (zero) weight blob so that workspace + stream management stay in one place."""
-    global _BLOB
+    """The matcher needs no network weights: one matcher-only native context per device (sfd2_create(NULL))."""
     if device_index not in _CTX:
-        if _BLOB is None:
-            from .weights import LAYER_ORDER, pack_blob
-            shapes = {"conv1a": (64, 3, 3, 1, 1), "conv1b": (64, 64, 3, 2, 1), "conv2a": (128, 64, 3, 1, 1),
-                      "conv2b": (128, 128, 3, 2, 1), "conv3a": (256, 128, 3, 1, 1), "conv3b": (256, 256, 3, 1, 1),
-                      "convPa0": (256, 256, 3, 2, 1), "headP": (65, 256, 3, 1, 1), "convDa0": (256, 256, 3, 1, 1),
-                      "headD": (128, 256, 3, 1, 1), "sta": (3, 256, 1, 1, 1)}
-            for i in range(3):
-                shapes[f"rb{i}c1"] = (256, 256, 1, 1, 1)
-                shapes[f"rb{i}c2"] = (256, 8, 3, 1, 32)
-                shapes[f"rb{i}c3"] = (256, 256, 1, 1, 1)
-            layers = {n: dict(w=np.zeros((shapes[n][0], shapes[n][1], shapes[n][2], shapes[n][2]), np.float32),
-                              b=np.zeros(shapes[n][0], np.float32), stride=shapes[n][3], groups=shapes[n][4], relu=0)
-                      for n in LAYER_ORDER}
-            _BLOB = pack_blob(layers)
-        _CTX[device_index] = _lib.Context(_BLOB, device_index)
+        _CTX[device_index] = _lib.Context(None, device_index)
     return _CTX[device_index]
 
 
