@@ -64,6 +64,7 @@ struct Layer {
   int cout_tc = 0;             // rows per tap in the TC packing (multiple of 16)
   CUtensorMap tm_w_hi, tm_w_lo;
   CUtensorMap tm_w_hi_half, tm_w_lo_half;  // boxes of n_mma/2 rows (2-CTA multicast)
+  CUtensorMap tm_w_hi_quarter, tm_w_lo_quarter;
 };
 
 struct TcConvLaunch;  // tc_conv.cu
@@ -124,7 +125,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_multicast, g_tc_halo, g_conv1a_mma;
+extern int g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

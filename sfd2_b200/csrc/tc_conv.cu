@@ -40,6 +40,10 @@ struct TcConvArgs {
   int Ho, Wo, tiles_x, num_tiles;
   int taps, stride, kchunks, diag;
   int n_mma, acc_cols, tmem_cols, cout, relu, split;
+  int nsplit;      // halo mode: the output channels are processed in nsplit passes of n_mma channels each, so that
+                   // main + correction accumulators of BOTH TMEM buffers fit (N=256: 2 x (128 + 128) x 2 = 512 columns)
+                   // and the epilogue of one pass overlaps the MMAs of the next; the small halo A tile is re-fetched
+  int tap_rows;    // rows per tap in the packed weights (= the layer's padded Cout)
   int corr;        // 1: the hi*lo / lo*hi passes accumulate in their own TMEM region (added in the epilogue)
   int nbuf;        // accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
   int buf_stride;  // TMEM columns per buffer = acc_cols * (1 + corr)
@@ -125,6 +129,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
+        for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
@@ -133,7 +138,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (planes == 2) tma_load_3d(slot + TC_HALO_SLOT, &tmA_lo, &fullA[sa], kc * 64, x0 - 1, y0 - 1);
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
           for (int tap = 0; tap < 9; ++tap) {
-            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.acc_cols;
+            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma;
             const int bcol = a.diag ? 0 : kc * 64;
             for (int pl = 0; pl < planes; ++pl) {
               mbar_wait(&empty[sb], phb ^ 1);
@@ -176,7 +181,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tma_load_5d(sa, &tmA_hi, &full[stage], c0, xp, cx, yp, cy);
               if (a.split == 3) tma_load_5d(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
             }
-            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.acc_cols;
+            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows;
             const int bcol = a.diag ? 0 : c0;
             if (a.mc > 1) {   // my half of the slab, delivered to both CTAs
               const int hrows = a.n_mma / 2;
@@ -202,6 +207,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t pha = 0, phb = 0, bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+        for (int nh = 0; nh < a.nsplit; ++nh) {
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -245,6 +251,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         umma_commit(&tfull[buf]);
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+        }
       }
     } else if (leader && !a.halo) {
       const uint32_t idesc = make_idesc_f16(128, a.n_mma);
@@ -299,7 +306,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t* wres = resbar + q * 2;
     int buf = 0;
     uint32_t bphase = 0;
-    const int nchunks = (a.cout + 31) / 32;
+    const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
     const int r = lane;                          // row of this warp's 32-pixel box (2 tile rows x 16 px)
     // chunk sequence number over (iteration, chunk): staging buffer = seq & 1
     auto tile_xy = [&](int it, int& x0, int& y0) {
@@ -326,6 +333,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
       int x0, y0;
       tile_xy(it, x0, y0);
+      for (int nh = 0; nh < a.nsplit; ++nh) {
+      const int cbase = nh * a.n_mma;             // first output channel of this pass (0 unless nsplit > 1)
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
@@ -377,7 +386,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          const float4 b = *reinterpret_cast<const float4*>(sbias + c0 + g * 4);
+          const float4 b = *reinterpret_cast<const float4*>(sbias + cbase + c0 + g * 4);
           x[g * 4] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
         }
         if (a.epi_fn == 1) {
@@ -437,8 +446,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(&tmO_hi, st, c0, x0, y0);
-          if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, c0, x0, y0);
+          tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
+          if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           bulk_commit();
           if (a.has_res) {                        // refill this buffer with the residual two chunks ahead
             bulk_wait_read<0>();
@@ -452,6 +461,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
       if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+      }
     }
     if (lane == 0) bulk_wait_all();               // all output bytes are in global memory before the CTA exits
   }
@@ -539,7 +549,13 @@ int tc_encode_weights(Layer& L) {
   const uint32_t hbox[2] = {64u, box[1] / 2};
   rc = make_tmap_f16(&L.tm_w_hi_half, L.w_hi, 2, dims, strides, hbox);
   if (rc) return rc;
-  return make_tmap_f16(&L.tm_w_lo_half, L.w_lo, 2, dims, strides, hbox);
+  rc = make_tmap_f16(&L.tm_w_lo_half, L.w_lo, 2, dims, strides, hbox);
+  if (rc) return rc;
+  // quarter-slab boxes: channel-split layers (two passes of Cout/2) under multicast
+  const uint32_t qbox[2] = {64u, box[1] / 4};
+  rc = make_tmap_f16(&L.tm_w_hi_quarter, L.w_hi, 2, dims, strides, qbox);
+  if (rc) return rc;
+  return make_tmap_f16(&L.tm_w_lo_quarter, L.w_lo, 2, dims, strides, qbox);
 }
 
 // Activation tensor maps: s1   stride-1 view {C, W, H}, box {64,16,8}          (per-tap loads, 1x1 layers)
@@ -579,6 +595,7 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
   return make_tmap(tm, base, 3, dims, str, box, is_f32, is_f32 ? 128 : 64);
 }
 
+int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
@@ -598,14 +615,24 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.num_tiles = a.tiles_x * cdiv(out.H, a.tile_h);
   a.taps = L.k * L.k; a.stride = L.stride; a.diag = diag ? 1 : 0;
   a.kchunks = L.cin / 64;
+  a.tap_rows = L.cout_tc;
+  a.nsplit = 1;
   a.n_mma = diag ? 64 : L.cout_tc;
   a.acc_cols = L.cout_tc;
+  // wide exact-mode 3x3 layers: two channel passes of Cout/2 so that (main + correction) x 2 buffers fit in TMEM
+  // (measured: conv3a 177 -> 152 us, conv3b 295 -> 276 us; N = 192 -> 2 x 96 was slower, so only Cout = 256 is split)
+  if (a.halo && !diag && split == 3 && L.k == 3 && L.cout_tc == 256 && L.cout == 256 && g_tc_nsplit) {
+    a.nsplit = 2;
+    a.n_mma = L.cout_tc / 2;
+    a.acc_cols = a.n_mma;
+  }
   // (block-diagonal grouped layers add mostly exact zeros, so their single accumulator is already accurate)
   a.corr = (split == 3 && L.k == 3 && !diag) ? 1 : 0;
   a.buf_stride = a.acc_cols * (1 + a.corr);
   // the epilogue reads 32-column chunks, so an 80-wide accumulator (headP) is over-read by 16 columns:
   // keep that inside the allocation
-  int over = a.corr * a.acc_cols + round_up(L.cout, 32) - a.buf_stride;
+  const int pass_ch = (a.nsplit > 1) ? a.n_mma : round_up(L.cout, 32);   // channels the epilogue reads per pass
+  int over = a.corr * a.acc_cols + pass_ch - a.buf_stride;
   if (over < 0) over = 0;
   SFD2_CHECK(a.buf_stride + over <= 512, SFD2_ERR_ARG, "conv_tc(%s): accumulator too wide", L.name.c_str());
   a.nbuf = (2 * a.buf_stride + over <= 512) ? 2 : 1;
@@ -664,8 +691,14 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const CUtensorMap& wb_hi = (a.mc > 1) ? L.tm_w_hi_half : L.tm_w_hi;
-  const CUtensorMap& wb_lo = (a.mc > 1) ? L.tm_w_lo_half : L.tm_w_lo;
+  // weight-slab boxes: full slab = n_mma rows; with multicast each CTA fetches n_mma/2 rows
+  const int box_rows = (a.mc > 1) ? a.n_mma / 2 : a.n_mma;
+  const int full_rows = diag ? 64 : L.cout_tc;
+  const int mi = (box_rows == full_rows) ? 0 : (box_rows * 2 == full_rows ? 1 : 2);
+  SFD2_CHECK(box_rows == full_rows || box_rows * 2 == full_rows || box_rows * 4 == full_rows, SFD2_ERR_ARG,
+             "conv_tc(%s): no weight map for %d-row boxes", L.name.c_str(), box_rows);
+  const CUtensorMap& wb_hi = mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter);
+  const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
   SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
