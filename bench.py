@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the SFD2 hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision exact|fast|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision exact|mixed|fast|fp32]
     python bench.py --impl reference [...]        # the reference's CPU path (oracle port) on host cores
 
 Metric (BASELINE.json): images/s of extract @1600x1200, top-4096 keypoints
@@ -330,7 +330,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_clean / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"exact": "f16x3->f32", "fast": "f16->f32", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "dtype": {"exact": "f16x3->f32", "mixed": "f16x3->f32 (descriptor head f16x1)", "fast": "f16->f32", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": f"extract 1600x1200 top-4096, batch {B} images/step/GPU resident in HBM (f32 NCHW), "
                                    f"precision={args.precision}", "image": [H, W], "topk": TOPK, "batch_per_gpu": B,
                        "l2": f"inputs cycle through a {pool_n}-image pool ({pool_n * H * W * 12 / 1e6:.0f} MB > 126 MB L2); "
@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--pool", type=int, default=16)
-    ap.add_argument("--precision", default="exact", choices=["exact", "fast", "fp32"])
+    ap.add_argument("--precision", default="exact", choices=["exact", "mixed", "fast", "fp32"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")

@@ -54,7 +54,10 @@ typedef enum {
 typedef enum {
   SFD2_PREC_FP32 = 0,     /* CUDA-core fp32 FMA (reference-grade, slow)                          */
   SFD2_PREC_TC_EXACT = 1, /* tcgen05 fp16 x3 split (a_hi*w_hi + a_hi*w_lo + a_lo*w_hi), fp32 acc */
-  SFD2_PREC_TC_FAST = 2   /* tcgen05 fp16 x1, fp32 accumulate                                    */
+  SFD2_PREC_TC_FAST = 2,  /* tcgen05 fp16 x1, fp32 accumulate                                    */
+  SFD2_PREC_TC_MIXED = 3  /* everything that feeds the heat-map (keypoint indices, scores) as TC_EXACT;
+                             the descriptor head (convDa, convDb: 35 % of the MACs) as TC_FAST - its
+                             outputs only have to meet the 1e-3 tolerance.  Matcher calls: = TC_EXACT */
 } sfd2_precision;
 
 /* image element type for sfd2_extract_* */

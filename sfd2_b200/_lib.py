@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsfd2_b200.so")
 
-PREC = {"fp32": 0, "exact": 1, "fast": 2}
+PREC = {"fp32": 0, "exact": 1, "fast": 2, "mixed": 3}
 IMG_F32_NCHW, IMG_U8_NHWC = 0, 1
 DESC_DIM = 128
 

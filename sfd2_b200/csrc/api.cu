@@ -157,6 +157,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
     while (cap2 < w.cap) cap2 <<= 1;
     SFD2_CUDA(cudaMalloc(&w.cand, (size_t)w.cap * sizeof(unsigned long long)));
     SFD2_CUDA(cudaMalloc(&w.scratch, (size_t)cap2 * sizeof(unsigned long long)));
+    SFD2_CUDA(cudaMemset(w.scratch, 0, (size_t)cap2 * sizeof(unsigned long long)));   // select_kernel's rank / arrival counters
     SFD2_CUDA(cudaMalloc(&w.counter, sizeof(int)));
     SFD2_CUDA(cudaMalloc(&w.status, sizeof(int)));
     SFD2_CUDA(cudaMemset(w.status, 0, sizeof(int)));
@@ -230,16 +231,21 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
                        float* kpts, float* scores, float* desc, int32_t* count, cudaStream_t st) {
   const int prec = p->precision;
   const bool tc = prec != SFD2_PREC_FP32;
-  const int split = (prec == SFD2_PREC_TC_EXACT) ? 3 : 1;
+  const int split = (prec == SFD2_PREC_TC_EXACT || prec == SFD2_PREC_TC_MIXED) ? 3 : 1;
+  // MIXED: the descriptor head only has to meet the 1e-3 tolerance, so it runs single-pass (hi planes only)
+  const int split_d = (prec == SFD2_PREC_TC_MIXED) ? 1 : split;
   Act* A = w.acts;
   int rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
   RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
-  auto conv = [&](const char* name, int in, int out, int res) -> int {
+  // ConvSta rides in the epilogue of the layer that produces out4 (tcgen05 modes)
+  const bool fuse_sta = tc && p->use_stability && g_fuse_sta;
+  auto conv = [&](const char* name, int in, int out, int res, int sp = 0, bool with_sta = false) -> int {
     const Layer& L = c->L(name);
     prof_begin(c, (std::string(tc ? "tc_conv:" : "conv_f32:") + name).c_str(), st);
-    const int r = tc ? launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, split, c->num_sms, st)
+    const int r = tc ? launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, sp ? sp : split, c->num_sms, st,
+                                      0, with_sta ? &c->L("sta") : nullptr, with_sta ? w.sta : nullptr)
                      : launch_conv_simt(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, st);
     prof_end(c, st);
     return r;
@@ -251,9 +257,9 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   RUN(conv("conv3b", A3A, A3B, -1));
   RUN(conv("rb0c1", A3B, T1, -1)); RUN(conv("rb0c2", T1, T2, -1)); RUN(conv("rb0c3", T2, BA, A3B));
   RUN(conv("rb1c1", BA, T1, -1));  RUN(conv("rb1c2", T1, T2, -1)); RUN(conv("rb1c3", T2, BB, BA));
-  RUN(conv("rb2c1", BB, T1, -1));  RUN(conv("rb2c2", T1, T2, -1)); RUN(conv("rb2c3", T2, BA, BB));
+  RUN(conv("rb2c1", BB, T1, -1));  RUN(conv("rb2c2", T1, T2, -1)); RUN(conv("rb2c3", T2, BA, BB, 0, fuse_sta));
   RUN(conv("convPa0", BA, PA, -1));
-  RUN(conv("convDa0", BA, DA, -1));
+  RUN(conv("convDa0", BA, DA, -1, split_d));
   // heads: fp32 outputs
   Act logit_act; logit_act.f32 = w.logits; logit_act.H = w.H8; logit_act.W = w.W8; logit_act.Wp = w.W8; logit_act.Hp = w.H8; logit_act.C = 80;
   Act desc_act;  desc_act.f32 = w.descmap; desc_act.H = w.H4; desc_act.W = w.W4; desc_act.Wp = w.W4; desc_act.Hp = w.H4; desc_act.C = 128;
@@ -261,7 +267,7 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
     // head epilogues fused: the detector head writes the exp-normalised 64 cell scores straight into `semi`,
     // the descriptor head writes L2-normalised rows (no softmax65 / l2norm128 launches in the tcgen05 modes)
     RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, w.map_semi, split, c->num_sms, st, 2));
-    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split, c->num_sms, st, 1));
+    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split_d, c->num_sms, st, 1));
   } else {
     RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
     RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
@@ -270,7 +276,7 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
     RUNP("softmax65", launch_softmax65(w.logits, w.H8 * w.W8, w.semi, st));
     RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
   }
-  if (p->use_stability) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
+  if (p->use_stability && !fuse_sta) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
   RUNP("heat", launch_heat(w.semi, w.H8, w.W8, w.sta, w.H4, w.W4, p->use_stability, w.heat, H, W, st));
   RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, p->border_w > 0 ? p->border_w : W, p->border_h > 0 ? p->border_h : H,
                          (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
@@ -287,7 +293,7 @@ static int check_params(const sfd2_extract_params* p, int n, int h, int w) {
   SFD2_CHECK(n >= 1 && h >= 16 && w >= 16, SFD2_ERR_ARG, "bad image batch %d x %d x %d (min 16x16)", n, h, w);
   SFD2_CHECK(p->nms_radius == 4, SFD2_ERR_ARG, "only nms_radius == 4 is implemented (got %d)", p->nms_radius);
   SFD2_CHECK(p->topk >= 1, SFD2_ERR_ARG, "topk must be >= 1 (capacity of the output buffers)");
-  SFD2_CHECK(p->precision >= 0 && p->precision <= 2, SFD2_ERR_ARG, "bad precision %d", p->precision);
+  SFD2_CHECK(p->precision >= 0 && p->precision <= 3, SFD2_ERR_ARG, "bad precision %d", p->precision);
   SFD2_CHECK(p->border >= 0, SFD2_ERR_ARG, "bad border");
   return SFD2_OK;
 }
@@ -313,6 +319,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_NSPLIT")) g_tc_nsplit = atoi(e) != 0;
   if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_FUSE_STA")) g_fuse_sta = atoi(e) != 0;
   const char* env_streams = getenv("SFD2_STREAMS");
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
@@ -517,7 +524,7 @@ static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int 
   if (p->precision == SFD2_PREC_FP32)
     rc = launch_match_simt(d0, n0, d1, n1, d, c->row_key, c->col_key, st);
   else
-    rc = launch_match_tc(d0, n0, d1, n1, d, p->precision == SFD2_PREC_TC_EXACT ? 3 : 1, c->mhalf, c->row_key,
+    rc = launch_match_tc(d0, n0, d1, n1, d, p->precision != SFD2_PREC_TC_FAST ? 3 : 1, c->mhalf, c->row_key,
                          c->col_key, c->num_sms, st);
   prof_end(c, st);
   if (rc) return rc;
@@ -533,7 +540,7 @@ SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d
                    int32_t* matches0, float* sim0, void* stream) {
   SFD2_CHECK(c && p && (n0 == 0 || (d0 && matches0 && sim0)) && (n1 == 0 || d1), SFD2_ERR_ARG, "sfd2_match_dev: NULL argument");
   SFD2_CHECK(n0 >= 0 && n1 >= 0 && d >= 1, SFD2_ERR_ARG, "sfd2_match_dev: bad shape %d x %d x %d", n0, n1, d);
-  SFD2_CHECK(p->precision >= 0 && p->precision <= 2, SFD2_ERR_ARG, "bad precision %d", p->precision);
+  SFD2_CHECK(p->precision >= 0 && p->precision <= 3, SFD2_ERR_ARG, "bad precision %d", p->precision);
   SFD2_CUDA(cudaSetDevice(c->device));
   int rc = ensure_match_ws(c, n0, n1);
   if (rc) return rc;
@@ -613,7 +620,7 @@ SFD2_API int sfd2_match_one_to_many_dev(sfd2_ctx* c, const float* q, int nq, con
   }
   SFD2_CUDA(cudaMemcpyAsync(c->seg_dev, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   const long long before = g_launches;
-  const int rc = launch_match_one_to_many(q, nq, db, c->seg_dev, ndb, P1, p->precision == SFD2_PREC_TC_EXACT ? 3 : 1,
+  const int rc = launch_match_one_to_many(q, nq, db, c->seg_dev, ndb, P1, p->precision != SFD2_PREC_TC_FAST ? 3 : 1,
                                           p->do_mutual_check, p->distance_threshold, c->mhalf, c->row_key, c->col_key,
                                           matches0, sim0, c->num_sms, st);
   c->launches += g_launches - before;
@@ -698,6 +705,7 @@ SFD2_API int sfd2_nms_select_dev(sfd2_ctx* c, const float* heat, int h, int w, c
   SFD2_CUDA(cudaMalloc(&status, 4));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SFD2_CUDA(cudaMemsetAsync(status, 0, 4, st));
+  SFD2_CUDA(cudaMemsetAsync(scratch, 0, (size_t)cap2 * 8, st));
   const long long before = g_launches;
   int rc = launch_nms(heat, h, w, p->conf_th, p->border, p->border_w > 0 ? p->border_w : w, p->border_h > 0 ? p->border_h : h,
                       nms_out, cand, cap, counter, st);
@@ -752,7 +760,7 @@ SFD2_API long long sfd2_debug_fetch(sfd2_ctx* c, const char* name, float* out, l
     std::vector<__half> hi(ne), lo(ne);
     if (cudaMemcpy(hi.data(), a.hi, ne * 2, cudaMemcpyDeviceToHost) != cudaSuccess ||
         cudaMemcpy(lo.data(), a.lo, ne * 2, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("copy failed"); return SFD2_ERR_CUDA; }
-    const bool use_lo = (c->last_prec == SFD2_PREC_TC_EXACT);
+    const bool use_lo = (c->last_prec == SFD2_PREC_TC_EXACT) || (c->last_prec == SFD2_PREC_TC_MIXED && it->second != DA);
     for (int y = 0; y < a.H; ++y)
       for (size_t i = 0; i < (size_t)a.W * a.C; ++i) {
         const size_t s = (size_t)y * a.Wp * a.C + i;

@@ -75,8 +75,8 @@ int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, 
                   const CUtensorMap* tm1a, int num_sms, cudaStream_t st);
 // tc_conv1a.cu
 int conv1a_mma_encode(Layer& L);
-int launch_conv1a_mma(const float4* nimg, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split, int num_sms,
-                      cudaStream_t st);
+int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
+                      int num_sms, cudaStream_t st);
 int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cudaStream_t st);
 // tc_in: 0 = fp32 input, 1 = fp16 hi+lo, 2 = fp16 hi only
 int launch_sta(const Act& in, int tc_in, const Layer& L, float* logits, cudaStream_t st);
@@ -87,8 +87,9 @@ int tc_encode_weights(Layer& L);
 int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo);
 int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w);
 // epi_fn (fp32 outputs only): 0 raw, 1 L2-normalised channels, 2 exp-normalised (softmax-with-eps) channels 0..63
+// sta / sta_out: fuse ConvSta (1x1 256 -> 3) on this layer's output into the epilogue (fp16-plane outputs only)
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st, int epi_fn = 0);
+                   int num_sms, cudaStream_t st, int epi_fn = 0, const Layer* sta = nullptr, float* sta_out = nullptr);
 // post.cu
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st);
@@ -125,7 +126,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma;
+extern int g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

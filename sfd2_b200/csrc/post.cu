@@ -81,21 +81,26 @@ int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int
 
 // ------------------------------------------------------------------------------ NMS (radius 4, 3 rounds)
 // Literal restatement of simple_nms (nets/extractor.py:20-35) on one smem tile with a 20-pixel
-// halo: each of the 5 max-pools / dilations reaches 4 px and the dependency chain is 4+8+8.
+// halo: each of the 5 max-pools / dilations reaches 4 px and the dependency chain is 4+4+4+4+4.
 // Out-of-image pixels hold -inf, which is max_pool2d's implicit padding value, and are never
-// allowed into the mask.  The tile arrays carry a 4-element apron of the pooling identity so the
-// 9-wide windows need no clamping; windows are still cut at the tile edge, so only the interior
-// (>= 20 px from the tile edge) is exact - and only the interior is written.
+// allowed into the mask.  Every stage is evaluated only where the later stages still need it: the
+// interior grown by a margin of 16 (first pool), 12, 8, 4 and 0 pixels, so no window ever leaves the
+// tile and the total pooled area is 1.9x smaller than five full-tile passes.
 //
 // Each 9-wide running max is computed in registers for 8 outputs at a time from 16 loaded values
 // with the doubling scheme m2 -> m4 -> m8 -> m9 (45 max ops and 16 smem reads per 8 outputs).
+// Row passes map consecutive lanes to consecutive ROWS and the pitch is odd, column passes map lanes to
+// consecutive columns, so every shared-memory access is conflict-free (the first version's row passes
+// walked runs of 8 floats per lane = an 8-way bank conflict on each of their 24 accesses).
+// supp_scores (= 0 where suppressed) is never materialised: it is re-derived from s and supp where read,
+// which keeps the block at 83 KB of shared memory = 2 blocks per SM.
 constexpr int NT_W = 64, NT_H = 32, NHALO = 20, NR = 4;
-constexpr int NS_W = NT_W + 2 * NHALO;  // 104 (13 runs of 8)
-constexpr int NS_H = NT_H + 2 * NHALO;  // 72  (9 runs of 8)
-constexpr int NP_W = NS_W + 2 * NR;     // 112 padded pitch
-constexpr int NP_H = NS_H + 2 * NR;     // 80
-constexpr int NP_N = NP_W * NP_H;
-__device__ __forceinline__ int nidx(int y, int x) { return (y + NR) * NP_W + x + NR; }  // tile coords -> padded index
+constexpr int NS_W = NT_W + 2 * NHALO;  // 104
+constexpr int NS_H = NT_H + 2 * NHALO;  // 72
+constexpr int NP_W = NS_W + 1;          // odd pitch
+constexpr int NP_N = NP_W * NS_H;
+constexpr int NMS_THREADS = 512;
+__device__ __forceinline__ int nidx(int y, int x) { return y * NP_W + x; }  // tile coords -> smem index
 
 template <typename T> __device__ __forceinline__ T pmax(T a, T b);
 template <> __device__ __forceinline__ float pmax<float>(float a, float b) { return fmaxf(a, b); }
@@ -114,101 +119,87 @@ __device__ __forceinline__ void run9(const T (&v)[16], T (&o)[8]) {
   for (int i = 0; i < 8; ++i) o[i] = pmax(m8[i], v[i + 8]);
 }
 
-// dst = 9x9 max of src over the tile (src/tmp/dst are padded arrays whose apron holds the identity)
-template <typename T>
-__device__ __forceinline__ void pool9(const T* __restrict__ src, T* __restrict__ tmp, T* __restrict__ dst) {
-  // row pass: work item = (row, run of 8 columns)
-  for (int it = threadIdx.x; it < NS_H * (NS_W / 8); it += blockDim.x) {
-    const int y = it / (NS_W / 8), x0 = (it - y * (NS_W / 8)) * 8;
+// horizontal 9-max of `load(idx)` into tmp, for the rows / columns a following column pass with output margin
+// `mg` needs: rows [NHALO-mg-4, NHALO+NT_H+mg+4), columns [NHALO-mg, NHALO+NT_W+mg).  Work item = (run of 8
+// columns, row); consecutive threads take consecutive rows.
+template <typename T, typename Load>
+__device__ __forceinline__ void row_pass(Load load, T* __restrict__ tmp, int mg) {
+  const int ylo = NHALO - mg - NR, nrows = NT_H + 2 * mg + 2 * NR;
+  const int xlo = NHALO - mg, nruns = (NT_W + 2 * mg) / 8;
+  for (int it = threadIdx.x; it < nrows * nruns; it += NMS_THREADS) {
+    const int k = it / nrows, y = ylo + (it - k * nrows), x0 = xlo + 8 * k;
     T v[16], o[8];
-    const T* p = src + nidx(y, x0 - NR);
+    const int p = nidx(y, x0 - NR);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = p[i];
+    for (int i = 0; i < 16; ++i) v[i] = load(p + i);
     run9(v, o);
     T* q = tmp + nidx(y, x0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) q[i] = o[i];
   }
-  __syncthreads();
-  // column pass: work item = (run of 8 rows, column); consecutive threads take consecutive columns
-  for (int it = threadIdx.x; it < (NS_H / 8) * NS_W; it += blockDim.x) {
-    const int yr = it / NS_W, x = it - yr * NS_W, y0 = yr * 8;
+}
+
+// vertical 9-max of tmp over the interior grown by `mg`; every result goes to consume(idx, value).
+// Work item = (run of 8 rows, column); consecutive threads take consecutive columns.
+template <typename T, typename Consume>
+__device__ __forceinline__ void col_pass(const T* __restrict__ tmp, Consume consume, int mg) {
+  const int ylo = NHALO - mg, nruns = (NT_H + 2 * mg) / 8;
+  const int xlo = NHALO - mg, ncols = NT_W + 2 * mg;
+  for (int it = threadIdx.x; it < nruns * ncols; it += NMS_THREADS) {
+    const int yr = it / ncols, x = xlo + (it - yr * ncols), y0 = ylo + 8 * yr;
     T v[16], o[8];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = tmp[nidx(y0 - NR + i, x)];
     run9(v, o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[nidx(y0 + i, x)] = o[i];
+    for (int i = 0; i < 8; ++i) consume(nidx(y0 + i, x), o[i]);
   }
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(NMS_THREADS, 2)
 nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int border, int bw, int bh,
            float* __restrict__ nms_out,
            unsigned long long* __restrict__ cand, int cap, int* __restrict__ counter) {
   extern __shared__ float sm[];
   float* s = sm;             // scores (-inf outside the image)
-  float* t = sm + NP_N;      // row-pass scratch
-  float* u = sm + 2 * NP_N;  // pooled scores / suppressed scores
-  unsigned char* m = reinterpret_cast<unsigned char*>(sm + 3 * NP_N);  // max_mask
-  unsigned char* tb = m + NP_N;                                        // dilation scratch
+  float* u = sm + NP_N;      // row-pass scratch of the float pools
+  unsigned char* m = reinterpret_cast<unsigned char*>(sm + 2 * NP_N);  // max_mask
+  unsigned char* tb = m + NP_N;                                        // row-pass scratch of the dilations
   unsigned char* supp = tb + NP_N;                                     // supp_mask
   const int X0 = blockIdx.x * NT_W - NHALO, Y0 = blockIdx.y * NT_H - NHALO;
-  for (int i = threadIdx.x; i < NP_N; i += blockDim.x) {
-    const int py = i / NP_W, px = i - py * NP_W;
-    const int ty = py - NR, tx = px - NR;
+  for (int i = threadIdx.x; i < NS_W * NS_H; i += NMS_THREADS) {
+    const int ty = i / NS_W, tx = i - ty * NS_W;
     const int y = Y0 + ty, x = X0 + tx;
-    const bool in_tile = ty >= 0 && ty < NS_H && tx >= 0 && tx < NS_W;
-    s[i] = (in_tile && y >= 0 && y < H && x >= 0 && x < W) ? __ldg(heat + (size_t)y * W + x) : -CUDART_INF_F;
-    t[i] = -CUDART_INF_F;   // aprons of the scratch arrays: identity of max
-    u[i] = -CUDART_INF_F;
-    m[i] = 0; tb[i] = 0; supp[i] = 0;
+    s[nidx(ty, tx)] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(heat + (size_t)y * W + x) : -CUDART_INF_F;
   }
   __syncthreads();
-  pool9<float>(s, t, u);                                               // max_pool(scores)
-  for (int it = threadIdx.x; it < NS_H * NS_W; it += blockDim.x) {
-    const int y = it / NS_W, x = it - y * NS_W, i = nidx(y, x);
-    m[i] = (s[i] != -CUDART_INF_F) && (s[i] == u[i]);
-  }
+  // max_mask = scores == max_pool(scores), on the interior + 16
+  row_pass<float>([&](int id) { return s[id]; }, u, 16);
   __syncthreads();
+  col_pass<float>(u, [&](int id, float o) { const float sv = s[id]; m[id] = (sv != -CUDART_INF_F) && (sv == o); }, 16);
+  __syncthreads();
+#pragma unroll 1
   for (int round = 0; round < 2; ++round) {
-    pool9<unsigned char>(m, tb, supp);                                 // supp_mask = max_pool(max_mask) > 0
-    for (int it = threadIdx.x; it < NS_H * NS_W; it += blockDim.x) {
-      const int y = it / NS_W, x = it - y * NS_W, i = nidx(y, x);
-      const float sv = s[i];
-      t[i] = (supp[i] && sv != -CUDART_INF_F) ? 0.f : sv;              // supp_scores (kept in t)
-    }
+    const int mg = round == 0 ? 12 : 4;
+    // supp_mask = max_pool(max_mask) > 0, on the interior + mg
+    row_pass<unsigned char>([&](int id) { return m[id]; }, tb, mg);
     __syncthreads();
-    // max_pool(supp_scores): row pass t -> u, column pass u -> compare in place
-    for (int it = threadIdx.x; it < NS_H * (NS_W / 8); it += blockDim.x) {
-      const int y = it / (NS_W / 8), x0 = (it - y * (NS_W / 8)) * 8;
-      float v[16], o[8];
-      const float* p = t + nidx(y, x0 - NR);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = p[i];
-      run9(v, o);
-      float* q = u + nidx(y, x0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = o[i];
-    }
+    col_pass<unsigned char>(tb, [&](int id, unsigned char o) { supp[id] = o; }, mg);
     __syncthreads();
-    for (int it = threadIdx.x; it < (NS_H / 8) * NS_W; it += blockDim.x) {
-      const int yr = it / NS_W, x = it - yr * NS_W, y0 = yr * 8;
-      float v[16], o[8];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = u[nidx(y0 - NR + i, x)];
-      run9(v, o);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int id = nidx(y0 + i, x);
-        if (s[id] != -CUDART_INF_F && t[id] == o[i] && !supp[id]) m[id] = 1;   // max_mask |= new_max & ~supp
-      }
-    }
+    // new_max_mask = supp_scores == max_pool(supp_scores), supp_scores = supp ? 0 : scores; on the interior + mg - 4
+    auto supp_score = [&](int id) { const float sv = s[id]; return (supp[id] && sv != -CUDART_INF_F) ? 0.f : sv; };
+    row_pass<float>(supp_score, u, mg - 4);
+    __syncthreads();
+    col_pass<float>(u, [&](int id, float o) {
+      const float sv = s[id];
+      const unsigned char sp = supp[id];
+      const float tv = (sp && sv != -CUDART_INF_F) ? 0.f : sv;
+      if (sv != -CUDART_INF_F && tv == o && !sp) m[id] = 1;           // max_mask |= new_max & ~supp
+    }, mg - 4);
     __syncthreads();
   }
   // output + candidate compaction for the tile interior
-  for (int i = threadIdx.x; i < NT_W * NT_H; i += blockDim.x) {
+  for (int i = threadIdx.x; i < NT_W * NT_H; i += NMS_THREADS) {
     const int ty = i / NT_W, tx = i - ty * NT_W;
     const int y = blockIdx.y * NT_H + ty, x = blockIdx.x * NT_W + tx;
     const bool in_img = (y < H && x < W);
@@ -236,11 +227,11 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
 // image size in its multi-scale loop, nets/extractor.py:181-182); pass W / H for the single-scale case
 int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out, unsigned long long* cand,
                int cap, int* counter, cudaStream_t st) {
-  const size_t smem = (size_t)3 * NP_N * sizeof(float) + 3 * NP_N;
+  const size_t smem = (size_t)2 * NP_N * sizeof(float) + 3 * NP_N;
   SFD2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch (cheap)
   SFD2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   dim3 grid(cdiv(W, NT_W), cdiv(H, NT_H));
-  nms_kernel<<<grid, 512, smem, st>>>(heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter);
+  nms_kernel<<<grid, NMS_THREADS, smem, st>>>(heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
@@ -254,24 +245,32 @@ int launch_nms(const float* heat, int H, int W, float conf_th, int border, int b
 // every thread owns one candidate, streams all keys through shared memory, counts, and - if its
 // rank is below K - writes its (x, y), score straight to row `rank`.  No sort, no single-CTA tail;
 // O(n^2) compares spread over the whole GPU (n ~ 6k: 39 M compares).
-constexpr int SEL_THREADS = 256, SEL_CHUNK = 2048;
+constexpr int SEL_THREADS = 256, SEL_CHUNK = 1024, SEL_Y = 8;
 
+// grid = (candidate chunks of 256, SEL_Y key ranges): block (bx, by) counts, for its 256 candidates, the keys
+// greater than each among the key chunks by, by + SEL_Y, ... and adds the partial ranks into `rank_buf`; the
+// last block to arrive for a candidate chunk (per-chunk arrival counter) reads the complete ranks and writes the
+// output rows.  The n^2 compares thus spread over ~n/256 x min(SEL_Y, n/1024) CTAs instead of n/256.
+// rank_buf [cap] and arrive [gridDim.x] are zero on entry and are left zero (the finishing block resets them).
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* __restrict__ counter, int W, int topk,
               float* __restrict__ kpts, float* __restrict__ scores, int32_t* __restrict__ count_out,
-              int* __restrict__ status) {
+              int* __restrict__ status, int* __restrict__ rank_buf, int* __restrict__ arrive) {
   __shared__ unsigned long long keys[SEL_CHUNK];
+  __shared__ int is_last;
   int n = *counter;
   if (n > cap) {                       // more candidates than the workspace holds: report, keep what fits
-    if (blockIdx.x == 0 && threadIdx.x == 0) *status = SFD2_ERR_OVERFLOW;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *status = SFD2_ERR_OVERFLOW;
     n = cap;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = (topk > 0 && topk < n) ? topk : n;
-  if (blockIdx.x * SEL_THREADS >= n) return;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *count_out = (topk > 0 && topk < n) ? topk : n;
+  const int nchunks = (n + SEL_CHUNK - 1) / SEL_CHUNK;
+  const int active_y = min(nchunks, (int)gridDim.y);
+  if (blockIdx.x * SEL_THREADS >= n || (int)blockIdx.y >= active_y) return;
   const int i = blockIdx.x * SEL_THREADS + threadIdx.x;
   const unsigned long long mine = (i < n) ? cand[i] : 0xFFFFFFFFFFFFFFFFull;
   int rank = 0;
-  for (int c0 = 0; c0 < n; c0 += SEL_CHUNK) {
+  for (int c0 = blockIdx.y * SEL_CHUNK; c0 < n; c0 += gridDim.y * SEL_CHUNK) {
     const int cn = min(SEL_CHUNK, n - c0);
     __syncthreads();
     for (int j = threadIdx.x; j < cn; j += SEL_THREADS) keys[j] = cand[c0 + j];
@@ -284,6 +283,17 @@ select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* _
     for (; j < cn; ++j) r0 += keys[j] > mine;
     rank += r0 + r1 + r2 + r3;
   }
+  if (active_y > 1) {
+    if (i < n && rank) atomicAdd(&rank_buf[i], rank);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&arrive[blockIdx.x], 1) == active_y - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    rank = (i < n) ? atomicExch(&rank_buf[i], 0) : 0;      // complete rank; leave the buffer zero for the next call
+    if (threadIdx.x == 0) arrive[blockIdx.x] = 0;
+  }
   const int k = (topk > 0 && topk < n) ? topk : n;
   if (i < n && rank < k) {
     const unsigned lin = 0xFFFFFFFFu - (unsigned)(mine & 0xFFFFFFFFull);
@@ -293,10 +303,13 @@ select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* _
   }
 }
 
+// scratch: >= (cap + cdiv(cap, 256)) ints, zero-initialised once by the owner (the kernel leaves it zero)
 int launch_select(unsigned long long* cand, int cap, const int* counter, int W, int topk, float* kpts, float* scores,
                   int32_t* count_out, int* status, unsigned long long* scratch, cudaStream_t st) {
-  (void)scratch;
-  select_kernel<<<cdiv(cap, SEL_THREADS), SEL_THREADS, 0, st>>>(cand, cap, counter, W, topk, kpts, scores, count_out, status);
+  int* rank_buf = reinterpret_cast<int*>(scratch);
+  int* arrive = rank_buf + cap;
+  dim3 grid(cdiv(cap, SEL_THREADS), SEL_Y);
+  select_kernel<<<grid, SEL_THREADS, 0, st>>>(cand, cap, counter, W, topk, kpts, scores, count_out, status, rank_buf, arrive);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

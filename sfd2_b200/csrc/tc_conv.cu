@@ -62,6 +62,13 @@ struct TcConvArgs {
   int epi_fn;      // fp32 head epilogues: 0 none, 1 = L2-normalise the pixel's channels (F.normalize, sfd2.py:342),
                    // 2 = exp / (sum_65 exp + 1e-5), channels 0..63 (sfd2.py:330-333); both need a first pass over TMEM
   int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
+  // fused ConvSta (1x1 256 -> 3, nets/sfd2.py:303,345) on this layer's OUTPUT (rb2c3 = out4): the epilogue already
+  // holds every output pixel's 256 channels in registers chunk by chunk, so the three dot products cost 96 FMAs per
+  // chunk and save re-reading the 123 MB activation in a separate kernel.  Computed in fp32 on the value the
+  // planes carry (hi + lo), like the standalone sta_kernel.
+  const float* sta_w;   // [256][64-padded] fp32 (Layer::w_simt of "sta"); NULL = not fused
+  float* sta_out;       // [Ho*Wo][3]
+  float sta_b[3];
 };
 
 constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
@@ -69,6 +76,8 @@ constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
 constexpr int TC_HALO_SLOT = 23 * 1024;                                // per plane, 1024-aligned
 constexpr int TC_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 px x 128 B)
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
+constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
+constexpr int TC_STA_BYTES = 256 * 16;          // fused ConvSta weights, one float4 per input channel
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -90,6 +99,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
+  float4* ssta = reinterpret_cast<float4*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // only if a.sta_w
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -107,6 +117,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   for (int i = threadIdx.x; i < (int)(TC_BIAS_BYTES / sizeof(float)); i += blockDim.x)
     sbias[i] = (i < ((a.cout + 31) / 32) * 32) ? __ldg(a.bias + i) : 0.f;
+  if (a.sta_w)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+      ssta[i] = make_float4(__ldg(a.sta_w + i * 64), __ldg(a.sta_w + i * 64 + 1), __ldg(a.sta_w + i * 64 + 2), 0.f);
   tc_fence_before();
   __syncthreads();
   if (a.mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
@@ -364,6 +377,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
       }
       const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
+      float sta0 = a.sta_b[0], sta1 = a.sta_b[1], sta2 = a.sta_b[2];
       for (int ch = 0; ch < nstore; ++ch, ++seq) {
         const int c0 = ch * 32;
         const int sb = seq & 1;
@@ -441,6 +455,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
+            if (a.sta_w) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float xr = __half2float(hi[j]) + __half2float(lo[j]);
+                const float4 w = ssta[cbase + c0 + j];
+                sta0 = fmaf(xr, w.x, sta0); sta1 = fmaf(xr, w.y, sta1); sta2 = fmaf(xr, w.z, sta2);
+              }
+            }
+          } else if (a.sta_w) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float xr = __half2float(hi[j]);
+              const float4 w = ssta[cbase + c0 + j];
+              sta0 = fmaf(xr, w.x, sta0); sta1 = fmaf(xr, w.y, sta1); sta2 = fmaf(xr, w.z, sta2);
+            }
           }
         }
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
@@ -461,6 +490,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
       if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+      if (a.sta_w) {                              // (nsplit == 1 here) this lane's pixel: TMEM lane q*32 + r of the tile
+        const int py = y0 + r / a.tile_w, px = x0 + r % a.tile_w;
+        if (py < a.Ho && px < a.Wo) {
+          float* o = a.sta_out + ((size_t)py * a.Wo + px) * 3;
+          o[0] = sta0; o[1] = sta1; o[2] = sta2;
+        }
+      }
       }
     }
     if (lane == 0) bulk_wait_all();               // all output bytes are in global memory before the CTA exits
@@ -472,6 +508,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------ host side
+int g_fuse_sta = 1;       // SFD2_FUSE_STA=0: run ConvSta as its own kernel (sta_kernel) instead of in rb2c3's epilogue
 int g_tc_multicast = 1;   // SFD2_TC_MULTICAST=0 in the environment disables the 2-CTA weight multicast
 
 PFN_encodeTiled get_encode_tiled() {
@@ -600,7 +637,7 @@ int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for th
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st, int epi_fn) {
+                   int num_sms, cudaStream_t st, int epi_fn, const Layer* sta, float* sta_out) {
   SFD2_CHECK(in.tm != nullptr && in.hi != nullptr, SFD2_ERR_ARG, "conv_tc(%s): input has no tensor maps", L.name.c_str());
   SFD2_CHECK(in.C == L.cin && in.C % 64 == 0, SFD2_ERR_ARG, "conv_tc(%s): cin %d", L.name.c_str(), in.C);
   SFD2_CHECK(split == 1 || split == 3, SFD2_ERR_ARG, "conv_tc: split must be 1 or 3");
@@ -643,7 +680,11 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.b_bytes = a.n_mma * 128;
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;
-  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + 512;   // alignment slack, staging, bias, barriers
+  const bool fuse_sta = sta && sta_out;
+  SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w_simt),
+             SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
+  // alignment slack, staging, bias, barriers (+ the fused ConvSta weights)
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (fuse_sta ? TC_STA_BYTES : 0);
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
@@ -662,6 +703,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
   a.epi_fn = out_f32_map ? epi_fn : 0;
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
+  a.sta_w = fuse_sta ? sta->w_simt : nullptr;
+  a.sta_out = fuse_sta ? sta_out : nullptr;
+  for (int i = 0; i < 3; ++i) a.sta_b[i] = fuse_sta ? sta->b[i] : 0.f;
+  SFD2_CHECK(!fuse_sta || a.nsplit == 1, SFD2_ERR_ARG, "conv_tc(%s): fused ConvSta needs a single channel pass", L.name.c_str());
   SFD2_CHECK(out_f32_map || out.tm_st, SFD2_ERR_ARG, "conv_tc(%s): output has no store maps", L.name.c_str());
   SFD2_CHECK(!res || res->tm_st, SFD2_ERR_ARG, "conv_tc(%s): residual has no store maps", L.name.c_str());
   SFD2_CHECK(L.cout <= 256, SFD2_ERR_ARG, "conv_tc(%s): cout > 256", L.name.c_str());

@@ -1,16 +1,20 @@
-// conv1a (3 -> 64 channels, 3x3, nets/sfd2.py:268) on the tensor cores.
+// conv1a (3 -> 64 channels, 3x3, nets/sfd2.py:268) on the tensor cores, with the RGB normalisation
+// (nets/extractor.py:14-17,104) fused into its operand producer.
 //
 // K = 27 is too thin for a TMA-fed implicit GEMM, and on the CUDA cores the layer is bound by the FP32
 // FMA pipe (3.3 GFMA per 1600x1200 image; 3-register FFMA issues every other cycle per SM sub-partition:
 // 0.26 ms measured for the register-tiled kernel in simt_conv.cu).  Here the CUDA cores only build the
 // im2col operand - for a 128-pixel row segment, row r of the A tile holds the 27 normalised inputs of pixel r
-// (K order = tap-major, channel-minor; padded to 64 with zeros) as fp16 hi / lo planes in the same
+// (K order = tap-major, channel-minor; padded to 32 with zeros) as fp16 hi / lo planes in the same
 // 128-byte-swizzled K-major layout TMA would produce - and one thread issues the tcgen05 MMAs
 // (M = 128 pixels, N = 64 channels, K = 32: 2 steps per pass, 3 passes in exact mode).  The epilogue is the usual
-// TMEM -> bias + ReLU -> fp16 hi/lo -> swizzled staging tile -> TMA store.
+// TMEM -> bias + ReLU -> fp16 hi/lo -> swizzled staging tile -> TMA store; the staging tile IS the A tile
+// (the MMAs have finished reading it by then), which keeps the block at 54 KB of shared memory.
 //
-// One 128-thread block = one segment at a time, persistent over segments; 2 blocks per SM overlap each other's
-// build / MMA / epilogue phases.
+// One 128-thread block = one segment at a time, persistent over segments; the phases of a segment are a serial
+// latency chain (load -> build -> MMA -> TMEM read -> store), so 4 blocks per SM overlap each other's phases and
+// each block prefetches the raw pixels of its next segment into registers while its MMAs run.  The layer's floor
+// is the 491 MB write of the hi + lo planes.
 #include <algorithm>
 
 #include "common.cuh"
@@ -21,34 +25,34 @@ namespace sfd2 {
 using namespace ptx;
 
 constexpr int C1M_SEG = 128;
+constexpr int C1M_COLS = C1M_SEG + 2;          // segment + 1-pixel apron
+constexpr int C1M_ITEMS = 9 * C1M_COLS;        // (row, channel, column) values of a segment's input patch
+constexpr int C1M_PER_THREAD = (C1M_ITEMS + 127) / 128;   // 10
 
 struct Conv1aMmaArgs {
-  int H, W, split;
-  const float4* nimg;      // normalised image, NHWC4 fp32
+  int H, W, split, img_dtype;
+  const void* img;         // raw image: f32 NCHW in [0,1] or u8 NHWC
   const __half* w_hi;      // [64 co][64 k] fp16, k = tap*3 + c (27 used)
   const __half* w_lo;
   const float* bias;       // [64]
 };
 
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(128, 4)
 conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                   const __grid_constant__ Conv1aMmaArgs a) {
   extern __shared__ uint8_t smem_raw_c1[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_c1) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA_hi = base;                 // [128 px][128 B]   (K 0..31 live, 32..63 zero)
+  uint8_t* sA_hi = base;                 // [128 px][128 B]: im2col rows (K 0..31), then the output tile [128 px][64 ch]
   uint8_t* sA_lo = base + 16384;
   uint8_t* sB_hi = base + 32768;         // [64 co][128 B]
   uint8_t* sB_lo = base + 40960;
-  uint8_t* t_hi = base + 49152;          // output staging [128 px][64 ch] fp16
-  uint8_t* t_lo = base + 65536;
-  float* patch = reinterpret_cast<float*>(base + 81920);   // [3 rows][3 ch][132]
+  float* patch = reinterpret_cast<float*>(base + 49152);   // [3 rows][3 ch][132]
   float* sbias = patch + 9 * 132;                          // [64]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + 64);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  // one-time setup: zero the A tiles (K 32..63 stay zero), stage the weight tiles (swizzled), bias, TMEM, barrier
-  for (int i = tid; i < 32768 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sA_hi)[i] = make_uint4(0, 0, 0, 0);
+  // one-time setup: stage the weight tiles (swizzled), bias, TMEM, barrier
   for (int i = tid; i < 64 * 8; i += blockDim.x) {          // 64 rows x 8 chunks of 16 B
     const int n = i >> 3, j = i & 7;
     const int dst = n * 128 + ((j ^ (n & 7)) << 4);
@@ -58,25 +62,56 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   if (tid < 64) sbias[tid] = __ldg(a.bias + tid);
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(slot, 64);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *slot;
   const uint32_t idesc = make_idesc_f16(128, 64);
   const int segs_x = (a.W + C1M_SEG - 1) / C1M_SEG, nseg = segs_x * a.H;
+  const size_t plane = (size_t)a.H * a.W;
   uint32_t phase = 0;
   const int r = tid;                                        // pixel of the segment = A row = TMEM lane
+
+  // raw (un-normalised) input values of a segment's patch: item i = (ky*3 + c) * 130 + col, this thread owns
+  // items tid, tid + 128, ...; out-of-image positions are flagged and become the conv's zero padding
+  float raw[C1M_PER_THREAD];
+  unsigned inb = 0;
+  auto prefetch = [&](int seg) {
+    const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1M_SEG;
+    inb = 0;
+#pragma unroll
+    for (int t = 0; t < C1M_PER_THREAD; ++t) {
+      const int i = tid + 128 * t;
+      const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
+      const int ky = kyc / 3, c = kyc - ky * 3;
+      const int iy = y + ky - 1, ix = x0 + col - 1;
+      raw[t] = 0.f;
+      if (i < C1M_ITEMS && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+        inb |= 1u << t;
+        if (a.img_dtype == SFD2_IMG_F32_NCHW) raw[t] = __ldg(reinterpret_cast<const float*>(a.img) + (size_t)c * plane + (size_t)iy * a.W + ix);
+        else raw[t] = (float)__ldg(reinterpret_cast<const unsigned char*>(a.img) + ((size_t)iy * a.W + ix) * 3 + c);
+      }
+    }
+  };
+  if ((int)blockIdx.x < nseg) prefetch(blockIdx.x);
+
   for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
     const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1M_SEG;
-    for (int i = tid; i < 3 * (C1M_SEG + 2); i += blockDim.x) {
-      const int ky = i / (C1M_SEG + 2), col = i - ky * (C1M_SEG + 2);
-      const int iy = y + ky - 1, ix = x0 + col - 1;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) v = __ldg(a.nimg + (size_t)iy * a.W + ix);
-      patch[(ky * 3 + 0) * 132 + col] = v.x;
-      patch[(ky * 3 + 1) * 132 + col] = v.y;
-      patch[(ky * 3 + 2) * 132 + col] = v.z;
+    // normalise exactly like the reference ((x - mean) / std, IEEE division; u8 / 255 first) and stage the patch
+#pragma unroll
+    for (int t = 0; t < C1M_PER_THREAD; ++t) {
+      const int i = tid + 128 * t;
+      if (i < C1M_ITEMS) {
+        const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
+        const int c = kyc % 3;
+        const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
+        const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
+        const float x = (a.img_dtype == SFD2_IMG_F32_NCHW) ? raw[t] : __fdiv_rn(raw[t], 255.0f);
+        patch[kyc * 132 + col] = ((inb >> t) & 1u) ? __fdiv_rn(__fsub_rn(x, mean), stdv) : 0.f;
+      }
     }
+    if (tid == 0) bulk_wait_read<0>();                      // the previous segment's stores have read the A / staging tiles
     __syncthreads();
     // im2col row of pixel r: k = (ky*3 + kx)*3 + c, 27 values + 5 zeros = 4 chunks of 8 halfs per plane
     {
@@ -115,9 +150,9 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         for (int k = 0; k < 2; ++k) umma_f16(tmem, desc_advance_k(da_lo, k), desc_advance_k(db_hi, k), idesc, 1u);
       }
       umma_commit(bar);
-      bulk_wait_read<0>();                                  // previous segment's stores have read the staging tiles
     }
     __syncwarp();
+    if (seg + (int)gridDim.x < nseg) prefetch(seg + gridDim.x);   // loads fly while the MMAs run and the epilogue drains
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
@@ -136,20 +171,20 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
         const float2 hf = __half22float2(hi[j]);
         lo[j] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
       }
-      if (ch == 0) __syncthreads();                         // thread 0's bulk_wait_read is done: tiles may be overwritten
+      // the MMAs are complete (barrier above), so the A tiles are free to become the output staging tiles
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int dst = r * 128 + (((ch * 4 + g) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(t_hi + dst) = reinterpret_cast<const uint4*>(hi)[g];
-        if (a.split == 3) *reinterpret_cast<uint4*>(t_lo + dst) = reinterpret_cast<const uint4*>(lo)[g];
+        *reinterpret_cast<uint4*>(sA_hi + dst) = reinterpret_cast<const uint4*>(hi)[g];
+        if (a.split == 3) *reinterpret_cast<uint4*>(sA_lo + dst) = reinterpret_cast<const uint4*>(lo)[g];
       }
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();                                        // staging complete; TMEM + patch + A tiles reusable
+    __syncthreads();                                        // staging complete; TMEM + patch reusable
     if (tid == 0) {
-      tma_store_3d(&tm_hi, t_hi, 0, x0, y);
-      if (a.split == 3) tma_store_3d(&tm_lo, t_lo, 0, x0, y);   // the single-pass mode never reads lo planes
+      tma_store_3d(&tm_hi, sA_hi, 0, x0, y);
+      if (a.split == 3) tma_store_3d(&tm_lo, sA_lo, 0, x0, y);   // the single-pass mode never reads lo planes
       bulk_commit();
     }
   }
@@ -178,14 +213,14 @@ int conv1a_mma_encode(Layer& L) {
 }
 
 // tm1a: [hi, lo] store maps of the conv1a output with box {64 ch, 128 px, 1 row}
-int launch_conv1a_mma(const float4* nimg, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split, int num_sms,
-                      cudaStream_t st) {
+int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
+                      int num_sms, cudaStream_t st) {
   SFD2_CHECK(L.w_hi && L.w_lo && tm1a, SFD2_ERR_ARG, "conv1a_mma: weights / store maps missing");
-  Conv1aMmaArgs a{H, W, split, nimg, L.w_hi, L.w_lo, L.b_dev};
-  const int smem = 1024 + 81920 + (9 * 132 + 64) * 4 + 64;
+  Conv1aMmaArgs a{H, W, split, img_dtype, img, L.w_hi, L.w_lo, L.b_dev};
+  const int smem = 1024 + 49152 + (9 * 132 + 64) * 4 + 64;
   SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
   const int nseg = cdiv(W, C1M_SEG) * H;
-  conv1a_mma_kernel<<<std::min(nseg, 2 * num_sms), 128, smem, st>>>(tm1a[0], tm1a[1], a);
+  conv1a_mma_kernel<<<std::min(nseg, 4 * num_sms), 128, smem, st>>>(tm1a[0], tm1a[1], a);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

@@ -28,8 +28,9 @@ class ResSegNetV2(torch.nn.Module):
     .eval(), .cuda(), .load_state_dict(ckpt['model'], strict=False); the forward
     pass itself lives on the device inside the native context.
 
-    precision: 'exact' (tcgen05 fp16x3 split, parity default), 'fast' (tcgen05
-    fp16x1) or 'fp32' (CUDA-core reference mode)."""
+    precision: 'exact' (tcgen05 fp16x3 split, parity default), 'mixed' (heat-map path
+    as 'exact', descriptor head single-pass: same keypoints/scores, descriptors within
+    1e-3), 'fast' (tcgen05 fp16x1) or 'fp32' (CUDA-core reference mode)."""
 
     def __init__(self, outdim=128, require_feature=False, require_stability=False, ms_detector=True,
                  precision="exact"):
