@@ -66,10 +66,14 @@ struct TcConvArgs {
   // holds every output pixel's 256 channels in registers chunk by chunk, so the three dot products cost 96 FMAs per
   // chunk and save re-reading the 123 MB activation in a separate kernel.  Computed in fp32 on the value the
   // planes carry (hi + lo), like the standalone sta_kernel.
-  const float* sta_w;   // [256][64-padded] fp32 (Layer::w_simt of "sta"); NULL = not fused
-  float* sta_out;       // [Ho*Wo][3]
+  float* sta_out;       // [Ho*Wo][3]; NULL = not fused
   float sta_b[3];
 };
+
+// ConvSta weights [256 ci][3] travel as a kernel parameter: every lane reads the same element at the same time, which
+// is exactly what the constant bank behind __grid_constant__ parameters serves in one broadcast; shared memory has no
+// 3 KB to spare (rb2c3's two 96 KB stages + staging fill the 227 KB to within 400 bytes).
+struct TcStaW { float w[256 * 3]; };
 
 constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
 constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
@@ -77,14 +81,13 @@ constexpr int TC_HALO_SLOT = 23 * 1024;                                // per pl
 constexpr int TC_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 px x 128 B)
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
-constexpr int TC_STA_BYTES = 256 * 16;          // fused ConvSta weights, one float4 per input channel
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
-               const __grid_constant__ TcConvArgs a) {
+               const __grid_constant__ TcConvArgs a, const __grid_constant__ TcStaW sw) {
   const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
   extern __shared__ uint8_t smem_raw[];
@@ -99,7 +102,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
-  float4* ssta = reinterpret_cast<float4*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // only if a.sta_w
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -117,9 +119,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   for (int i = threadIdx.x; i < (int)(TC_BIAS_BYTES / sizeof(float)); i += blockDim.x)
     sbias[i] = (i < ((a.cout + 31) / 32) * 32) ? __ldg(a.bias + i) : 0.f;
-  if (a.sta_w)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x)
-      ssta[i] = make_float4(__ldg(a.sta_w + i * 64), __ldg(a.sta_w + i * 64 + 1), __ldg(a.sta_w + i * 64 + 2), 0.f);
   tc_fence_before();
   __syncthreads();
   if (a.mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
@@ -455,20 +454,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
-            if (a.sta_w) {
+            if (a.sta_out) {
+              const float* w = sw.w + (cbase + c0) * 3;
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const float xr = __half2float(hi[j]) + __half2float(lo[j]);
-                const float4 w = ssta[cbase + c0 + j];
-                sta0 = fmaf(xr, w.x, sta0); sta1 = fmaf(xr, w.y, sta1); sta2 = fmaf(xr, w.z, sta2);
+                sta0 = fmaf(xr, w[3 * j], sta0); sta1 = fmaf(xr, w[3 * j + 1], sta1); sta2 = fmaf(xr, w[3 * j + 2], sta2);
               }
             }
-          } else if (a.sta_w) {
+          } else if (a.sta_out) {
+            const float* w = sw.w + (cbase + c0) * 3;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float xr = __half2float(hi[j]);
-              const float4 w = ssta[cbase + c0 + j];
-              sta0 = fmaf(xr, w.x, sta0); sta1 = fmaf(xr, w.y, sta1); sta2 = fmaf(xr, w.z, sta2);
+              sta0 = fmaf(xr, w[3 * j], sta0); sta1 = fmaf(xr, w[3 * j + 1], sta1); sta2 = fmaf(xr, w[3 * j + 2], sta2);
             }
           }
         }
@@ -490,7 +489,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
       if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
-      if (a.sta_w) {                              // (nsplit == 1 here) this lane's pixel: TMEM lane q*32 + r of the tile
+      if (a.sta_out) {                            // (nsplit == 1 here) this lane's pixel: TMEM lane q*32 + r of the tile
         const int py = y0 + r / a.tile_w, px = x0 + r % a.tile_w;
         if (py < a.Ho && px < a.Wo) {
           float* o = a.sta_out + ((size_t)py * a.Wo + px) * 3;
@@ -681,10 +680,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;
   const bool fuse_sta = sta && sta_out;
-  SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w_simt),
+  SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w.size() == 768),
              SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
-  // alignment slack, staging, bias, barriers (+ the fused ConvSta weights)
-  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (fuse_sta ? TC_STA_BYTES : 0);
+  // alignment slack, staging, bias, barriers
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
@@ -703,8 +702,16 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
   a.epi_fn = out_f32_map ? epi_fn : 0;
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
-  a.sta_w = fuse_sta ? sta->w_simt : nullptr;
   a.sta_out = fuse_sta ? sta_out : nullptr;
+  static const TcStaW kNoSta{};
+  TcStaW* swp = nullptr;
+  TcStaW sw_local;
+  if (fuse_sta) {          // OIHW [3][256][1][1] -> [ci][3]
+    for (int ci = 0; ci < 256; ++ci)
+      for (int c = 0; c < 3; ++c) sw_local.w[ci * 3 + c] = sta->w[(size_t)c * 256 + ci];
+    swp = &sw_local;
+  }
+  const TcStaW& sw = swp ? *swp : kNoSta;
   for (int i = 0; i < 3; ++i) a.sta_b[i] = fuse_sta ? sta->b[i] : 0.f;
   SFD2_CHECK(!fuse_sta || a.nsplit == 1, SFD2_ERR_ARG, "conv_tc(%s): fused ConvSta needs a single channel pass", L.name.c_str());
   SFD2_CHECK(out_f32_map || out.tm_st, SFD2_ERR_ARG, "conv_tc(%s): output has no store maps", L.name.c_str());
@@ -744,7 +751,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
              "conv_tc(%s): no weight map for %d-row boxes", L.name.c_str(), box_rows);
   const CUtensorMap& wb_hi = mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter);
   const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
-  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a));
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a, sw));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

@@ -48,23 +48,72 @@ __global__ void split_rows_kernel(const float* __restrict__ src, int n, int n_pa
   reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
 }
 
+// both operands of a pair in one launch, plus the reset of the arg-max keys (saves two launches and two memsets)
+__global__ void split_rows2_kernel(const float* __restrict__ src0, int n0, int n0p, __half* __restrict__ hi0,
+                                   __half* __restrict__ lo0, const float* __restrict__ src1, int n1, int n1p,
+                                   __half* __restrict__ hi1, __half* __restrict__ lo1,
+                                   unsigned long long* __restrict__ key0, unsigned long long* __restrict__ key1) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
+  if (idx >= (n0p + n1p) * 32) return;
+  const bool second = idx >= n0p * 32;
+  if (second) idx -= n0p * 32;
+  const float* src = second ? src1 : src0;
+  const int n = second ? n1 : n0;
+  __half* hi = second ? hi1 : hi0;
+  __half* lo = second ? lo1 : lo0;
+  unsigned long long* key = second ? key1 : key0;
+  const int r = idx >> 5;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < n) {
+    v = __ldg(reinterpret_cast<const float4*>(src) + idx);
+    if ((idx & 31) == 0) key[r] = 0ull;
+  }
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __align__(8) __half h[4];
+  __align__(8) __half l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j] = __float2half_rn(x[j]);
+    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+  }
+  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
+  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
+}
+
 constexpr int TM_TILE = 128;
 constexpr int TM_OP_BYTES = 128 * 128;  // 128 rows x 64 fp16
 constexpr int TM_THREADS = 192;
 constexpr int TM_MAX_STAGES = 6;
 
+// One launch runs BOTH products: pass 0 = D0 * D1^T reduces its rows into p[0].row_key (the row arg-max), pass 1 =
+// D1 * D0^T reduces ITS rows (= the columns of the first product) into p[1].row_key (the column arg-max).  The GEMM is
+// ~3 us of tensor work either way; what costs is the epilogue, and a row reduction is thread-local (one TMEM lane = one
+// row) while a column reduction needs a shared-memory transpose plus 128 atomics per warp per tile - doing the cheap
+// reduction twice is ~2x faster than doing both at once.  The tiles of the two passes form one list that is cut into
+// contiguous per-CTA ranges, so there is one launch, one ramp and one tail.
+struct TcMatchPass {
+  int n0, n1, tiles_m, tiles_n;   // rows / columns of this pass's product and its tile grid
+  unsigned long long* row_key;
+};
 struct TcMatchArgs {
-  int n0, n1, tiles_m, tiles_n, split, stages, stage_bytes;
-  int do_cols;   // 1: also reduce the tile's columns (smem transpose + per-column atomics) in the same pass
-  // one-to-many: the B operand is a concatenation of nseg row segments, each padded to a multiple of 128 rows
-  // (seg_poff = padded starts, seg_len = valid rows); row keys are then kept per (segment, row): key index
+  TcMatchPass p[2];
+  int split, stages, stage_bytes;
+  // one-to-many (pass 0 only): the B operand is a concatenation of nseg row segments, each padded to a multiple of
+  // 128 rows (seg_poff = padded starts, seg_len = valid rows); row keys are then kept per (segment, row): key index
   // seg * n0 + i, column index local to the segment
   int nseg;
   const int* seg_poff;
   const int* seg_len;
-  unsigned long long* row_key;
-  unsigned long long* col_key;
 };
+
+__device__ __forceinline__ void tm_decode(const TcMatchArgs& a, int tile, int& pass, int& mt, int& nt) {
+  const int t0 = a.p[0].tiles_m * a.p[0].tiles_n;
+  pass = tile >= t0 ? 1 : 0;
+  const int t = pass ? tile - t0 : tile;
+  const int tn = a.p[pass].tiles_n;
+  mt = t / tn;
+  nt = t - mt * tn;
+}
 
 __global__ void __launch_bounds__(TM_THREADS, 1)
 tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -75,8 +124,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   const int nops = (a.split == 3) ? 2 : 1;
   uint8_t* aslot = smem;                                       // resident A: [kb][plane] x 16 KB
   uint8_t* bring = smem + 2 * nops * TM_OP_BYTES;              // B ring: stage = [plane] x 16 KB of one K half
-  float* xpose = reinterpret_cast<float*>(bring + (size_t)a.stages * a.stage_bytes);  // 4 warps x 32 x 33 floats
-  uint64_t* full = reinterpret_cast<uint64_t*>(xpose + 4 * 32 * 33);
+  uint64_t* full = reinterpret_cast<uint64_t*>(bring + (size_t)a.stages * a.stage_bytes);
   uint64_t* empty = full + TM_MAX_STAGES;
   uint64_t* tfull = empty + TM_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -100,34 +148,40 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = a.tiles_m * a.tiles_n;
+  const int num_tiles = a.p[0].tiles_m * a.p[0].tiles_n + a.p[1].tiles_m * a.p[1].tiles_n;
   const int per_cta = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * per_cta;
   const int tile_end = min(tile_begin + per_cta, num_tiles);
 
   if (warp == 0) {
     if (elect_one()) {
-      int stage = 0, prev_mt = -1;
+      int stage = 0, prev_rb = -1;
       uint32_t phase = 0, aphase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int mt = tile / a.tiles_n;
-        const int r0 = mt * TM_TILE, c0 = (tile - mt * a.tiles_n) * TM_TILE;
-        if (mt != prev_mt) {                    // new row-block: (re)load the resident A operand
+        int pass, mt, nt;
+        tm_decode(a, tile, pass, mt, nt);
+        const int rb = pass ? a.p[0].tiles_m + mt : mt;       // row-block id over both passes
+        const int r0 = mt * TM_TILE, c0 = nt * TM_TILE;
+        const CUtensorMap* ah = pass ? &tmB_hi : &tmA_hi;
+        const CUtensorMap* al = pass ? &tmB_lo : &tmA_lo;
+        const CUtensorMap* bh = pass ? &tmA_hi : &tmB_hi;
+        const CUtensorMap* bl = pass ? &tmA_lo : &tmB_lo;
+        if (rb != prev_rb) {                    // new row-block: (re)load the resident A operand
           mbar_wait(aempty, aphase ^ 1);
           mbar_expect_tx(afull, (uint32_t)(2 * nops * TM_OP_BYTES));
           for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(aslot + (kb * nops) * TM_OP_BYTES, &tmA_hi, afull, kb * 64, r0);
-            if (a.split == 3) tma_load_2d(aslot + (kb * nops + 1) * TM_OP_BYTES, &tmA_lo, afull, kb * 64, r0);
+            tma_load_2d(aslot + (kb * nops) * TM_OP_BYTES, ah, afull, kb * 64, r0);
+            if (a.split == 3) tma_load_2d(aslot + (kb * nops + 1) * TM_OP_BYTES, al, afull, kb * 64, r0);
           }
           aphase ^= 1;
-          prev_mt = mt;
+          prev_rb = rb;
         }
         for (int kb = 0; kb < 2; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sb = bring + (size_t)stage * a.stage_bytes;
           mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
-          tma_load_2d(sb, &tmB_hi, &full[stage], kb * 64, c0);
-          if (a.split == 3) tma_load_2d(sb + TM_OP_BYTES, &tmB_lo, &full[stage], kb * 64, c0);
+          tma_load_2d(sb, bh, &full[stage], kb * 64, c0);
+          if (a.split == 3) tma_load_2d(sb + TM_OP_BYTES, bl, &full[stage], kb * 64, c0);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -135,14 +189,16 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      int stage = 0, buf = 0, prev_mt = -1;
+      int stage = 0, buf = 0, prev_rb = -1;
       uint32_t phase = 0, bphase = 0, aphase = 0;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        const int mt = tile / a.tiles_n;
-        if (mt != prev_mt) {
+        int pass, mt, nt;
+        tm_decode(a, tile, pass, mt, nt);
+        const int rb = pass ? a.p[0].tiles_m + mt : mt;
+        if (rb != prev_rb) {
           mbar_wait(afull, aphase);
           aphase ^= 1;
-          prev_mt = mt;
+          prev_rb = rb;
         }
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
@@ -155,33 +211,41 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + TM_OP_BYTES);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
 #pragma unroll 1
-          for (int pass = 0; pass < a.split; ++pass) {
-            const uint64_t da = (pass == 2) ? da_lo : da_hi;
-            const uint64_t db = (pass == 1) ? db_lo : db_hi;
+          for (int pass_k = 0; pass_k < a.split; ++pass_k) {
+            const uint64_t da = (pass_k == 2) ? da_lo : da_hi;
+            const uint64_t db = (pass_k == 1) ? db_lo : db_hi;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(dcol, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb == 0 && pass == 0 && k == 0) ? 0u : 1u);
+              umma_f16(dcol, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb == 0 && pass_k == 0 && k == 0) ? 0u : 1u);
           }
           umma_commit(&empty[stage]);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull[buf]);
         // last tile of this row-block (or of the CTA): the resident A may be replaced once these MMAs are done
-        if (tile + 1 == tile_end || (tile + 1) / a.tiles_n != mt) umma_commit(aempty);
+        bool last_of_rb = (tile + 1 == tile_end);
+        if (!last_of_rb) {
+          int p2, m2, n2;
+          tm_decode(a, tile + 1, p2, m2, n2);
+          last_of_rb = (p2 ? a.p[0].tiles_m + m2 : m2) != rb;
+        }
+        if (last_of_rb) umma_commit(aempty);
         if (++buf == 2) { buf = 0; bphase ^= 1; }
       }
     }
   } else {
     const int q = warp & 3;
-    float* xp = xpose + q * 32 * 33;
     int buf = 0;
     uint32_t bphase = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
-      const int r0 = (tile / a.tiles_n) * TM_TILE;
-      int c0 = (tile % a.tiles_n) * TM_TILE;
+      int pass, mt, nt;
+      tm_decode(a, tile, pass, mt, nt);
+      const int r0 = mt * TM_TILE;
+      int c0 = nt * TM_TILE;
       const int i = r0 + q * 32 + lane;
-      int n1 = a.n1, seg = 0;
-      if (a.nseg > 0) {                         // which segment does this column block belong to?
+      const int rows = a.p[pass].n0;
+      int n1 = a.p[pass].n1, seg = 0;
+      if (pass == 0 && a.nseg > 0) {            // which segment does this column block belong to?
         int lo = 0, hi = a.nseg - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(a.seg_poff + mid) <= c0) lo = mid; else hi = mid - 1; }
         seg = lo;
@@ -191,12 +255,19 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
+      // the whole 128-column row of this lane in one go: four loads in flight, one wait (the epilogue, not the
+      // MMAs, bounds this kernel, and each tcgen05.ld -> wait round trip used to be paid four times per tile)
+      uint32_t v[4][32];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) tmem_ld32(taddr + ch * 32, v[ch]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);   // the accumulator is in registers: the MMAs of tile + 2 may start
       float rbest = -CUDART_INF_F;              // plain float compares in the loops; keys are built once per tile
       int rbest_j = -1;
+#pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
         const int jbase = c0 + ch * 32;
         // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row).  A running
         // "if (s > best)" chain is 128 dependent compare/select steps per tile and made the epilogue slower than
@@ -204,8 +275,13 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         // indices that attain it - lowest column wins among equal values, every step is independent.
         const int cols_valid = min(32, n1 - jbase);
         float f[32];
+        if (cols_valid >= 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = (j < cols_valid) ? __uint_as_float(v[j]) : -CUDART_INF_F;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ch][j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = (j < cols_valid) ? __uint_as_float(v[ch][j]) : -CUDART_INF_F;
+        }
         float m16[16], m8[8], m4[4];
 #pragma unroll
         for (int j = 0; j < 16; ++j) m16[j] = fmaxf(f[2 * j], f[2 * j + 1]);
@@ -225,26 +301,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           rbest = cmax;
           rbest_j = jbase + min(min(i4[0], i4[1]), min(i4[2], i4[3]));
         }
-        if (!a.do_cols) continue;
-        // column arg-max over this warp's 32 rows: transpose through smem, one column per lane
-#pragma unroll
-        for (int j = 0; j < 32; ++j) xp[lane * 33 + j] = __uint_as_float(v[j]);
-        __syncwarp();
-        const int rows_valid = min(32, a.n0 - (r0 + q * 32));
-        float best = -CUDART_INF_F;
-        int besti = -1;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const float s = xp[r * 33 + lane];
-          if (r < rows_valid && s > best) { best = s; besti = r; }
-        }
-        __syncwarp();
-        if (besti >= 0 && lane < cols_valid) atomicMax(a.col_key + jbase + lane, m_key(best, r0 + q * 32 + besti));
       }
-      if (i < a.n0 && rbest_j >= 0) atomicMax(a.row_key + (size_t)seg * a.n0 + i, m_key(rbest, rbest_j));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (i < rows && rbest_j >= 0) atomicMax(a.p[pass].row_key + (size_t)seg * rows + i, m_key(rbest, rbest_j));
       if (++buf == 2) { buf = 0; bphase ^= 1; }
     }
   }
@@ -253,21 +311,26 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
+static size_t tm_smem_bytes(int split, int stages) {
+  return (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES * (split == 3 ? 2 : 1) + 1024 + 256;
+}
+
 // ws_half must hold 2 * (n0_pad + n1_pad) * 128 halves (n*_pad = n* rounded up to 128)
 int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int split, __half* ws_half,
                     unsigned long long* row_key, unsigned long long* col_key, int num_sms, cudaStream_t st) {
   SFD2_CHECK(d == 128, SFD2_ERR_ARG, "match_tc: descriptor dim must be 128 (got %d)", d);
-  SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)(n0 > 0 ? n0 : 1), st));
-  SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)(n1 > 0 ? n1 : 1), st));
-  if (n0 <= 0 || n1 <= 0) return SFD2_OK;
+  if (n0 <= 0 || n1 <= 0) {   // degenerate: every row is unmatched
+    SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)(n0 > 0 ? n0 : 1), st));
+    SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)(n1 > 0 ? n1 : 1), st));
+    return SFD2_OK;
+  }
   const int n0p = round_up(n0, TM_TILE), n1p = round_up(n1, TM_TILE);
   __half* a_hi = ws_half;
   __half* a_lo = a_hi + (size_t)n0p * 128;
   __half* b_hi = a_lo + (size_t)n0p * 128;
   __half* b_lo = b_hi + (size_t)n1p * 128;
-  split_rows_kernel<<<cdiv(n0p * 32, 256), 256, 0, st>>>(d0, n0, n0p, a_hi, a_lo);
-  split_rows_kernel<<<cdiv(n1p * 32, 256), 256, 0, st>>>(d1, n1, n1p, b_hi, b_lo);
-  g_launches += 2;
+  split_rows2_kernel<<<cdiv((n0p + n1p) * 32, 256), 256, 0, st>>>(d0, n0, n0p, a_hi, a_lo, d1, n1, n1p, b_hi, b_lo, row_key, col_key);
+  ++g_launches;
   CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
   const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
   const uint64_t strides[1] = {256};
@@ -285,26 +348,18 @@ int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int
     rc = make_tmap_f16(&tB_lo, b_lo, 2, dims, strides, box);
     if (rc) return rc;
   }
-  // Two passes with swapped operands: D0*D1^T reduces rows into row_key, D1*D0^T reduces ITS rows (= the columns of
-  // the first product) into col_key.  The GEMM is ~3 us of tensor work either way; what costs is the epilogue, and
-  // the row reduction is thread-local (one TMEM lane = one row) while a column reduction needs a shared-memory
-  // transpose plus 128 atomics per warp per tile.  Doing the cheap reduction twice is ~2x faster than doing both at once.
-  for (int pass = 0; pass < 2; ++pass) {
-    TcMatchArgs a{};
-    a.n0 = pass ? n1 : n0; a.n1 = pass ? n0 : n1;
-    a.tiles_m = (pass ? n1p : n0p) / TM_TILE; a.tiles_n = (pass ? n0p : n1p) / TM_TILE; a.split = split;
-    a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
-    a.stages = 4;
-    a.row_key = pass ? col_key : row_key; a.col_key = nullptr; a.do_cols = 0;
-    const size_t smem = (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)a.stages * a.stage_bytes +
-                        4 * 32 * 33 * sizeof(float) + 1024 + 256;
-    SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = a.tiles_m * a.tiles_n;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    if (pass == 0) tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
-    else tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tB_hi, tB_lo, tA_hi, tA_lo, a);
-    ++g_launches;
-  }
+  TcMatchArgs a{};
+  a.p[0] = TcMatchPass{n0, n1, n0p / TM_TILE, n1p / TM_TILE, row_key};
+  a.p[1] = TcMatchPass{n1, n0, n1p / TM_TILE, n0p / TM_TILE, col_key};
+  a.split = split;
+  a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
+  a.stages = 4;
+  const size_t smem = tm_smem_bytes(split, a.stages);
+  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = 2 * a.p[0].tiles_m * a.p[0].tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+  ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
 }
@@ -384,28 +439,21 @@ int launch_match_one_to_many(const float* q, int nq, const float* db, const int*
   if (!rc) rc = make_tmap_f16(&tB_hi, b_hi, 2, dd, strides, box);
   if (!rc) rc = make_tmap_f16(&tB_lo, b_lo, 2, dd, strides, box);
   if (rc) return rc;
-  for (int pass = 0; pass < 2; ++pass) {
-    TcMatchArgs a{};
-    a.split = split;
-    a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
-    a.stages = 4;
-    a.do_cols = 0; a.col_key = nullptr;
-    if (pass == 0) {   // rows = query, columns = padded db segments -> row_key[seg * nq + i]
-      a.n0 = nq; a.n1 = P1; a.tiles_m = nqp / TM_TILE; a.tiles_n = P1 / TM_TILE;
-      a.nseg = nseg; a.seg_poff = poff; a.seg_len = len; a.row_key = row_key;
-    } else {           // rows = padded db rows, columns = query -> col_key[padded db row]
-      a.n0 = P1; a.n1 = nq; a.tiles_m = P1 / TM_TILE; a.tiles_n = nqp / TM_TILE;
-      a.nseg = 0; a.row_key = col_key;
-    }
-    const size_t smem = (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)a.stages * a.stage_bytes +
-                        4 * 32 * 33 * sizeof(float) + 1024 + 256;
-    SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = a.tiles_m * a.tiles_n;
-    const int grid = tiles < num_sms ? tiles : num_sms;
-    if (pass == 0) tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
-    else tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tB_hi, tB_lo, tA_hi, tA_lo, a);
-    ++g_launches;
-  }
+  TcMatchArgs a{};
+  a.split = split;
+  a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
+  a.stages = 4;
+  // pass 0: rows = query, columns = padded db segments -> row_key[seg * nq + i];
+  // pass 1: rows = padded db rows, columns = query -> col_key[padded db row]
+  a.p[0] = TcMatchPass{nq, P1, nqp / TM_TILE, P1 / TM_TILE, row_key};
+  a.p[1] = TcMatchPass{P1, nq, P1 / TM_TILE, nqp / TM_TILE, col_key};
+  a.nseg = nseg; a.seg_poff = poff; a.seg_len = len;
+  const size_t smem = tm_smem_bytes(split, a.stages);
+  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = 2 * a.p[0].tiles_m * a.p[0].tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+  ++g_launches;
   match_finish_seg_kernel<<<cdiv(nq * nseg, 256), 256, 0, st>>>(row_key, col_key, poff, nq, nseg, mutual, dist_th, matches0, sim0);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
