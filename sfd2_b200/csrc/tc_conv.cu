@@ -24,6 +24,8 @@
 //
 // Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
 // issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -33,7 +35,8 @@ using namespace ptx;
 
 constexpr int TC_TILE_H = 8, TC_TILE_W = 16;
 constexpr int TC_A_BYTES = 128 * 128;  // 128 pixels x 64 fp16
-constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_STAGES = 12;   // ring slots; the 8 KB slabs of the grouped layers need the depth: a slab feeds only
+                                    // 4-8 N=64 MMAs (~130-260 cycles) while an L2 -> smem TMA round trip is ~1000
 constexpr int TC_THREADS = 192;
 
 struct TcConvArgs {
@@ -62,6 +65,10 @@ struct TcConvArgs {
   int epi_fn;      // fp32 head epilogues: 0 none, 1 = L2-normalise the pixel's channels (F.normalize, sfd2.py:342),
                    // 2 = exp / (sum_65 exp + 1e-5), channels 0..63 (sfd2.py:330-333); both need a first pass over TMEM
   int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
+  int prefetch;    // producer issues TMA L2 prefetches one tile ahead (A operand) / for the current tile (residual):
+                   // the memory-bound 1x1 layers run only 2 ring stages (96 KB each in exact mode), i.e. half a tile
+                   // of lookahead, and the residual is requested two 32-channel chunks before it is needed - both
+                   // less than one HBM round trip.  The prefetch puts those lines into L2 a full tile earlier.
   // fused ConvSta (1x1 256 -> 3, nets/sfd2.py:303,345) on this layer's OUTPUT (rb2c3 = out4): the epilogue already
   // holds every output pixel's 256 channels in registers chunk by chunk, so the three dot products cost 96 FMAs per
   // chunk and save re-reading the 123 MB activation in a separate kernel.  Computed in fp32 on the value the
@@ -87,6 +94,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
+               const __grid_constant__ CUtensorMap tmP_hi, const __grid_constant__ CUtensorMap tmP_lo,
                const __grid_constant__ TcConvArgs a, const __grid_constant__ TcStaW sw) {
   const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
@@ -141,6 +149,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
+        if (a.prefetch && it + 1 < a.iters && tile + (int)gridDim.x < a.num_tiles) {   // next tile's halo boxes -> L2
+          const int tn = tile + (int)gridDim.x;
+          const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            tma_prefetch_3d(&tmA_hi, kc * 64, xn - 1, yn - 1);
+            if (planes == 2) tma_prefetch_3d(&tmA_lo, kc * 64, xn - 1, yn - 1);
+          }
+        }
         for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
@@ -175,6 +191,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
+        if (a.prefetch && tile < a.num_tiles) {
+          if (a.has_res)                        // this tile's residual (the epilogue needs it about one tile from now)
+            for (int c = 0; c < a.cout; c += 64) {
+              tma_prefetch_3d(&tmP_hi, c, x0, y0);
+              if (a.has_res == 2) tma_prefetch_3d(&tmP_lo, c, x0, y0);
+            }
+          const int tn = tile + (int)gridDim.x;
+          if (it + 1 < a.iters && tn < a.num_tiles) {   // next tile's A boxes
+            const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
+            if (a.taps == 1 && a.stride == 1) {
+              for (int kc = 0; kc < a.kchunks; ++kc) {
+                tma_prefetch_3d(&tmA_hi, kc * 64, xn, yn);
+                if (a.split == 3) tma_prefetch_3d(&tmA_lo, kc * 64, xn, yn);
+              }
+            } else if (a.stride == 2) {                 // the four parity planes cover all nine taps' boxes but for
+              for (int pp = 0; pp < 4; ++pp)            // one leading row / column (a neighbouring tile's lines)
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                  tma_prefetch_5d(&tmA_hi, kc * 64, pp & 1, xn, pp >> 1, yn);
+                  if (a.split == 3) tma_prefetch_5d(&tmA_lo, kc * 64, pp & 1, xn, pp >> 1, yn);
+                }
+            }
+          }
+        }
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -454,20 +493,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
-            if (a.sta_out) {
-              const float* w = sw.w + (cbase + c0) * 3;
+          }
+          if (a.sta_out) {
+            // the three ConvSta dot products on x (fp32; hi + lo carries 22 of its 24 bits, and the 3-class argmax
+            // downstream is insensitive at that level - the standalone sta_kernel reads the planes instead)
+            const float4* w4 = reinterpret_cast<const float4*>(sw.w) + ((cbase + c0) * 3) / 4;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float xr = __half2float(hi[j]) + __half2float(lo[j]);
-                sta0 = fmaf(xr, w[3 * j], sta0); sta1 = fmaf(xr, w[3 * j + 1], sta1); sta2 = fmaf(xr, w[3 * j + 2], sta2);
-              }
-            }
-          } else if (a.sta_out) {
-            const float* w = sw.w + (cbase + c0) * 3;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float xr = __half2float(hi[j]);
-              sta0 = fmaf(xr, w[3 * j], sta0); sta1 = fmaf(xr, w[3 * j + 1], sta1); sta2 = fmaf(xr, w[3 * j + 2], sta2);
+            for (int g = 0; g < 8; ++g) {             // 4 channels x 3 classes = 3 float4 of the [ci][3] table
+              const float4 wa = w4[3 * g], wb = w4[3 * g + 1], wc = w4[3 * g + 2];
+              const float x0v = x[4 * g], x1v = x[4 * g + 1], x2v = x[4 * g + 2], x3v = x[4 * g + 3];
+              sta0 = fmaf(x0v, wa.x, sta0); sta1 = fmaf(x0v, wa.y, sta1); sta2 = fmaf(x0v, wa.z, sta2);
+              sta0 = fmaf(x1v, wa.w, sta0); sta1 = fmaf(x1v, wb.x, sta1); sta2 = fmaf(x1v, wb.y, sta2);
+              sta0 = fmaf(x2v, wb.z, sta0); sta1 = fmaf(x2v, wb.w, sta1); sta2 = fmaf(x2v, wc.x, sta2);
+              sta0 = fmaf(x3v, wc.y, sta0); sta1 = fmaf(x3v, wc.z, sta1); sta2 = fmaf(x3v, wc.w, sta2);
             }
           }
         }
@@ -632,6 +670,7 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
+int g_tc_prefetch = 1;    // SFD2_TC_PREFETCH=0: no TMA L2 prefetches
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
@@ -693,6 +732,8 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     a.a_slot_bytes = (split == 3 ? 2 : 1) * TC_HALO_SLOT;
     a.a_slots = 2;
     int bs = (smem_max - smem_fixed - a.a_slots * a.a_slot_bytes) / a.b_bytes;
+    const int max_bs = getenv("SFD2_TC_BSTAGES") ? atoi(getenv("SFD2_TC_BSTAGES")) : TC_MAX_STAGES;
+    if (bs > max_bs) bs = max_bs;
     if (bs > TC_MAX_STAGES) bs = TC_MAX_STAGES;
     SFD2_CHECK(bs >= 2, SFD2_ERR_ARG, "conv_tc(%s): weight ring does not fit", L.name.c_str());
     a.b_stages = bs;
@@ -702,6 +743,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
   a.epi_fn = out_f32_map ? epi_fn : 0;
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
+  a.prefetch = g_tc_prefetch;
   a.sta_out = fuse_sta ? sta_out : nullptr;
   static const TcStaW kNoSta{};
   TcStaW* swp = nullptr;
@@ -722,6 +764,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& o_lo = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so + 1];
   const CUtensorMap& r_hi = res ? res->tm_st[0] : o_hi;
   const CUtensorMap& r_lo = res ? res->tm_st[1] : o_lo;
+  // residual as {64 ch, 16 px, 8 rows} boxes (its stride-1 load views) for the L2 prefetch
+  SFD2_CHECK(!res || res->tm, SFD2_ERR_ARG, "conv_tc(%s): residual has no load maps", L.name.c_str());
+  const CUtensorMap& p_hi = res ? res->tm[0] : o_hi;
+  const CUtensorMap& p_lo = res ? res->tm[1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (a.halo ? 4 : (L.stride == 2 ? 2 : 0));
@@ -751,7 +797,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
              "conv_tc(%s): no weight map for %d-row boxes", L.name.c_str(), box_rows);
   const CUtensorMap& wb_hi = mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter);
   const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
-  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a, sw));
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, p_hi, p_lo, a, sw));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
