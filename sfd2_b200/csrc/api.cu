@@ -243,6 +243,11 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   const bool fuse_sta = tc && p->use_stability && g_fuse_sta;
   auto conv = [&](const char* name, int in, int out, int res, int sp = 0, bool with_sta = false) -> int {
     const Layer& L = c->L(name);
+    // the fused ConvSta accumulates with atomicAdd (two epilogue warps per pixel): start from zero
+    if (with_sta && cudaMemsetAsync(w.sta, 0, (size_t)w.H4 * w.W4 * 3 * sizeof(float), st) != cudaSuccess) {
+      set_error("cudaMemsetAsync(sta) failed");
+      return SFD2_ERR_CUDA;
+    }
     prof_begin(c, (std::string(tc ? "tc_conv:" : "conv_f32:") + name).c_str(), st);
     const int r = tc ? launch_conv_tc(A[in], L, A[out], res >= 0 ? &A[res] : nullptr, nullptr, sp ? sp : split, c->num_sms, st,
                                       0, with_sta ? &c->L("sta") : nullptr, with_sta ? w.sta : nullptr)

@@ -22,8 +22,11 @@
 //   the B operand (the kernel is L2-bandwidth bound otherwise).  A stage is released to the
 //   producers only when BOTH CTAs' MMAs have consumed it (multicast tcgen05.commit).
 //
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
-// issuer (one elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
+// issuer (one elected lane), warps 2..9 = epilogue: TMEM lane quarter = warp % 4, and the two warps
+// of a quarter take alternate 32-channel chunks (the epilogue of a chunk is a serial chain of
+// tcgen05.ld -> convert -> st.shared -> proxy fence -> TMA store, so two chains per scheduler
+// overlap each other's latencies; with one warp per quarter the 1x1 layers were bound by it).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -37,7 +40,8 @@ constexpr int TC_TILE_H = 8, TC_TILE_W = 16;
 constexpr int TC_A_BYTES = 128 * 128;  // 128 pixels x 64 fp16
 constexpr int TC_MAX_STAGES = 12;   // ring slots; the 8 KB slabs of the grouped layers need the depth: a slab feeds only
                                     // 4-8 N=64 MMAs (~130-260 cycles) while an L2 -> smem TMA round trip is ~1000
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TC_EPI_WARPS = 8;
 
 struct TcConvArgs {
   int Ho, Wo, tiles_x, num_tiles;
@@ -85,7 +89,7 @@ struct TcStaW { float w[256 * 3]; };
 constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
 constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
 constexpr int TC_HALO_SLOT = 23 * 1024;                                // per plane, 1024-aligned
-constexpr int TC_STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 px x 128 B)
+constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 4096;   // one (32 px x 128 B) staging tile per epilogue warp
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
 
@@ -106,7 +110,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* resbar = tempty + 2;                                         // [4 warps][2 buffers]
+  uint64_t* resbar = tempty + 2;                                         // [8 epilogue warps]
   uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
@@ -120,8 +124,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
     for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    for (int i = 0; i < 8; ++i) mbar_init(&resbar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
+    for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -346,40 +350,38 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     // Per 32-channel chunk: TMEM -> registers -> (+bias, +residual, ReLU, fp16 hi/lo split) -> this warp's
     // swizzled staging tile in smem -> ONE TMA store per plane (box {32 ch, 16 px, 2 rows}).  TMA clips
     // partial tiles and writes full lines; the threads never touch global memory (per-lane 16-byte
     // stores at a 512-byte stride cost ~8k LSU cycles per tile in the first version and bounded every 1x1
-    // layer).  Residual tiles arrive the same way (TMA load into the staging buffer, two chunks ahead).
+    // layer).  Residual tiles arrive the same way (TMA load into the staging tile, one own chunk ahead).
+    // Warp (q, h) owns TMEM lanes 32q.. and the chunks h, h + 2, h + 4, ... of every channel pass.
+    const int ew = warp - 2;
     const int q = warp & 3;
-    uint8_t* wstage = staging + q * 2 * 4096;
-    uint64_t* wres = resbar + q * 2;
+    const int h = ew >> 2;
+    uint8_t* st = staging + ew * 4096;
+    uint64_t* wres = resbar + ew;
     int buf = 0;
     uint32_t bphase = 0;
     const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
+    const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
     const int r = lane;                          // row of this warp's 32-pixel box (2 tile rows x 16 px)
-    // chunk sequence number over (iteration, chunk): staging buffer = seq & 1
     auto tile_xy = [&](int it, int& x0, int& y0) {
       const int tile = blockIdx.x + it * gridDim.x;
       x0 = (tile % a.tiles_x) * a.tile_w;
       y0 = (tile / a.tiles_x) * a.tile_h + a.epi_rows * q;
     };
-    auto issue_res = [&](int it, int ch, int sb) {   // lane 0 only
-      if (it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
+    auto issue_res = [&](int it, int ch) {        // lane 0 only
+      if (ch >= nstore || it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
       int x0, y0;
       tile_xy(it, x0, y0);
-      uint8_t* dst = wstage + sb * 4096;
-      mbar_expect_tx(&wres[sb], a.has_res == 2 ? 4096u : 2048u);
-      tma_load_3d(dst, &tmR_hi, &wres[sb], ch * 32, x0, y0);
-      if (a.has_res == 2) tma_load_3d(dst + 2048, &tmR_lo, &wres[sb], ch * 32, x0, y0);
+      mbar_expect_tx(wres, a.has_res == 2 ? 4096u : 2048u);
+      tma_load_3d(st, &tmR_hi, wres, ch * 32, x0, y0);
+      if (a.has_res == 2) tma_load_3d(st + 2048, &tmR_lo, wres, ch * 32, x0, y0);
     };
-    uint32_t seq = 0;
-    uint32_t rphase[2] = {0u, 0u};
-    if (a.has_res && lane == 0) {                 // prefetch the residual of the first two chunks
-      issue_res(0, 0, 0);
-      if (nchunks > 1) issue_res(0, 1, 1); else issue_res(1, 0, 1);
-    }
+    uint32_t rphase = 0u;
+    if (a.has_res && lane == 0) issue_res(0, h);  // the residual of this warp's first chunk
     for (int it = 0; it < a.iters; ++it) {
       if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
       int x0, y0;
@@ -414,17 +416,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // one reciprocal per pixel, then multiplies (<= 1 ulp from the reference's per-element division)
         row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
       }
-      const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
-      float sta0 = a.sta_b[0], sta1 = a.sta_b[1], sta2 = a.sta_b[2];
-      for (int ch = 0; ch < nstore; ++ch, ++seq) {
+      // fused ConvSta: each warp of a pair sums its own chunks; the pair's two partial sums meet in global memory
+      // (atomicAdd on a zeroed map: two addends, so the result does not depend on their order)
+      float sta0 = h ? 0.f : a.sta_b[0], sta1 = h ? 0.f : a.sta_b[1], sta2 = h ? 0.f : a.sta_b[2];
+      for (int ch = h; ch < nstore; ch += 2) {
         const int c0 = ch * 32;
-        const int sb = seq & 1;
-        uint8_t* st = wstage + sb * 4096;
         uint32_t v[32];
         float x[32];
         tmem_ld32(taddr + c0, v);
-        if (!a.has_res) {                         // the store issued from this buffer two chunks ago must have
-          if (lane == 0) bulk_wait_read<1>();     // finished reading it (with a residual, issue_res waited already)
+        if (!a.has_res) {                         // this warp's previous store must have finished reading the
+          if (lane == 0) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
           __syncwarp();
         }
         tmem_ld_wait();
@@ -450,8 +451,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
-          mbar_wait(&wres[sb], rphase[sb]);
-          rphase[sb] ^= 1u;
+          mbar_wait(wres, rphase);
+          rphase ^= 1u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 h = *reinterpret_cast<const uint4*>(st + r * 64 + ((g ^ sw64) << 4));
@@ -515,11 +516,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
           if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           bulk_commit();
-          if (a.has_res) {                        // refill this buffer with the residual two chunks ahead
+          if (a.has_res) {                        // refill the tile with the residual of this warp's next chunk
             bulk_wait_read<0>();
-            int nit = it, nch = ch + 2;
-            while (nch >= nchunks) { nch -= nchunks; ++nit; }
-            issue_res(nit, nch, sb);
+            if (ch + 2 < nstore) issue_res(it, ch + 2); else issue_res(it + 1, h);
           }
         }
       }
@@ -531,7 +530,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int py = y0 + r / a.tile_w, px = x0 + r % a.tile_w;
         if (py < a.Ho && px < a.Wo) {
           float* o = a.sta_out + ((size_t)py * a.Wo + px) * 3;
-          o[0] = sta0; o[1] = sta1; o[2] = sta2;
+          atomicAdd(o, sta0); atomicAdd(o + 1, sta1); atomicAdd(o + 2, sta2);
         }
       }
       }
@@ -670,7 +669,7 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
-int g_tc_prefetch = 1;    // SFD2_TC_PREFETCH=0: no TMA L2 prefetches
+int g_tc_prefetch = 0;    // SFD2_TC_PREFETCH=1: TMA L2 prefetches one tile ahead (measured: slower)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
