@@ -28,6 +28,7 @@
 // tcgen05.ld -> convert -> st.shared -> proxy fence -> TMA store, so two chains per scheduler
 // overlap each other's latencies; with one warp per quarter the 1x1 layers were bound by it).
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -51,6 +52,13 @@ struct TcConvArgs {
                    // main + correction accumulators of BOTH TMEM buffers fit (N=256: 2 x (128 + 128) x 2 = 512 columns)
                    // and the epilogue of one pass overlaps the MMAs of the next; the small halo A tile is re-fetched
   int tap_rows;    // rows per tap in the packed weights (= the layer's padded Cout)
+  int cat;         // grouped layers, exact mode ("diag-cat"): the weight slab of a (tap, 64-channel chunk) is the
+                   // N-concatenation [w_hi | w_lo] (128 rows), so ONE N=128 MMA per K step yields a_hi*w_hi (columns
+                   // 0..63 of the chunk's 128 accumulator columns) and a_hi*w_lo (columns 64..127); a_lo*w_hi is an
+                   // N=64 MMA on the slab's first 64 rows into columns 64..127.  N=64 MMAs are bound by the 4 KB
+                   // A-operand read (32 cycles for 16 cycles of math), so two A reads per K step instead of three cut
+                   // the layer's tensor time by a third.  The 256 output channels run as two channel passes of two
+                   // chunks (2 x 128 columns per buffer, double-buffered); chunks are independent, nothing is re-read.
   int corr;        // 1: the hi*lo / lo*hi passes accumulate in their own TMEM region (added in the epilogue)
   int nbuf;        // accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
   int buf_stride;  // TMEM columns per buffer = acc_cols * (1 + corr)
@@ -61,6 +69,11 @@ struct TcConvArgs {
   // halo row (1280 B).  The swizzle is a function of the absolute smem address, so the shifted views decode
   // correctly (profiles/r1_umma_halo_probe.log).  A and B then use separate rings.
   int halo, a_slots, a_slot_bytes, b_stages;
+  // geometry of the A box in split-ring ("halo") mode: 3x3 layers {10 px, 18 rows} at origin (x0-1, y0-1), nine taps;
+  // 1x1 layers run through the same path with a plain {8 px, 16 rows} box, one tap: their A operand comes from HBM and
+  // is used once, the weights come from L2 and are reused by every tile, so A gets a ring as deep as a whole tile
+  // (4 chunks) and the weight slabs a shallow one - the combined (A + B) stages left room for only two in flight
+  int hw, hoff, a_plane_bytes, a_plane_off;
   int tile_w, tile_h, epi_rows, ring_bytes;
   int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
@@ -157,22 +170,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const int tn = tile + (int)gridDim.x;
           const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
           for (int kc = 0; kc < a.kchunks; ++kc) {
-            tma_prefetch_3d(&tmA_hi, kc * 64, xn - 1, yn - 1);
-            if (planes == 2) tma_prefetch_3d(&tmA_lo, kc * 64, xn - 1, yn - 1);
+            tma_prefetch_3d(&tmA_hi, kc * 64, xn - a.hoff, yn - a.hoff);
+            if (planes == 2) tma_prefetch_3d(&tmA_lo, kc * 64, xn - a.hoff, yn - a.hoff);
           }
         }
         for (int nh = 0; nh < a.nsplit; ++nh)
-        for (int kc = 0; kc < a.kchunks; ++kc) {
+        for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
-          mbar_expect_tx(&fullA[sa], (uint32_t)(planes * TC_HALO_BYTES));
-          tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - 1, y0 - 1);
-          if (planes == 2) tma_load_3d(slot + TC_HALO_SLOT, &tmA_lo, &fullA[sa], kc * 64, x0 - 1, y0 - 1);
+          mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
+          tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+          if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
-          for (int tap = 0; tap < 9; ++tap) {
-            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma;
+          for (int tap = 0; tap < a.taps; ++tap) {
+            const int brow = a.cat ? (tap * 4 + kc) * 128 : (a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
             const int bcol = a.diag ? 0 : kc * 64;
-            for (int pl = 0; pl < planes; ++pl) {
+            for (int pl = 0; pl < (a.cat ? 1 : planes); ++pl) {
               mbar_wait(&empty[sb], phb ^ 1);
               uint8_t* bs = bring + (size_t)sb * a.b_bytes;
               mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
@@ -256,7 +269,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
     if (leader && a.halo) {
-      const uint32_t idesc = make_idesc_f16(128, a.n_mma);
+      const uint32_t idesc = make_idesc_f16(128, a.cat ? 64 : a.n_mma);
+      const uint32_t idesc_cat = make_idesc_f16(128, 128);
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
       int sa = 0, sb = 0, buf = 0;
       uint32_t pha = 0, phb = 0, bphase = 0;
@@ -265,17 +279,33 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int nh = 0; nh < a.nsplit; ++nh) {
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
-        for (int kc = 0; kc < a.kchunks; ++kc) {
+        for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&fullA[sa], pha);
           tc_fence_after();
           const uint32_t abase = smem_u32(smem + (size_t)sa * a.a_slot_bytes);
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? kc * 64 : 0));
-          const uint32_t ccol = a.corr ? dcol + (uint32_t)a.acc_cols : dcol;
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t off = (uint32_t)(((tap / 3) * TC_HALO_W + (tap % 3)) * 128);
-            const uint64_t da_hi = make_desc_sw128_sbo(abase + off, TC_HALO_W * 128);
-            const uint64_t da_lo = make_desc_sw128_sbo(abase + TC_HALO_SLOT + off, TC_HALO_W * 128);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.cat ? (kc & 1) * 128 : (a.diag ? kc * 64 : 0)));
+          const uint32_t ccol = a.cat ? dcol + 64u : (a.corr ? dcol + (uint32_t)a.acc_cols : dcol);
+          for (int tap = 0; tap < a.taps; ++tap) {
+            const uint32_t off = (uint32_t)(((tap / 3) * a.hw + (tap % 3)) * 128);
+            const uint64_t da_hi = make_desc_sw128_sbo(abase + off, (uint32_t)a.hw * 128);
+            const uint64_t da_lo = make_desc_sw128_sbo(abase + (uint32_t)a.a_plane_off + off, (uint32_t)a.hw * 128);
             const bool first = (tap == 0) && (a.diag || kc == 0);
+            if (a.cat) {
+              // one [w_hi | w_lo] slab: a_hi x both (N = 128: main | correction), then a_lo x w_hi (N = 64) into the
+              // correction columns - which the N = 128 MMA of this tap has already initialised when tap == 0
+              mbar_wait(&full[sb], phb);
+              tc_fence_after();
+              const uint64_t dbc = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(dbc, k), idesc_cat, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(dbc, k), idesc, 1u);
+              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+              if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
+              continue;
+            }
             // weight slab, hi plane: main product, then (exact mode) a_lo * w_hi into the correction accumulator
             mbar_wait(&full[sb], phb);
             tc_fence_after();
@@ -421,9 +451,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       float sta0 = h ? 0.f : a.sta_b[0], sta1 = h ? 0.f : a.sta_b[1], sta2 = h ? 0.f : a.sta_b[2];
       for (int ch = h; ch < nstore; ch += 2) {
         const int c0 = ch * 32;
+        // accumulator column of channel c0: diag-cat keeps [main 64 | correction 64] per 64-channel chunk
+        const uint32_t tcol = a.cat ? (uint32_t)((c0 >> 6) * 128 + (c0 & 63)) : (uint32_t)c0;
+        const uint32_t coff = a.cat ? 64u : (uint32_t)a.acc_cols;
         uint32_t v[32];
         float x[32];
-        tmem_ld32(taddr + c0, v);
+        tmem_ld32(taddr + tcol, v);
         if (!a.has_res) {                         // this warp's previous store must have finished reading the
           if (lane == 0) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
           __syncwarp();
@@ -432,7 +465,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         if (a.corr) {
-          tmem_ld32(taddr + a.acc_cols + c0, v);
+          tmem_ld32(taddr + tcol + coff, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(v[j]);
@@ -611,6 +644,23 @@ int tc_encode_weights(Layer& L) {
   SFD2_CUDA(cudaMalloc(&L.w_lo, lo.size() * sizeof(__half)));
   SFD2_CUDA(cudaMemcpy(L.w_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
   SFD2_CUDA(cudaMemcpy(L.w_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  if (diag) {   // diag-cat slabs: row (tap*4 + kc)*128 + r = w_hi row (tap, kc*64 + r) for r < 64, w_lo row (.., r - 64) else
+    std::vector<__half> cat((size_t)taps * 4 * 128 * 64);
+    for (int t = 0; t < taps; ++t)
+      for (int kc = 0; kc < 4; ++kc)
+        for (int r = 0; r < 128; ++r) {
+          const std::vector<__half>& src = r < 64 ? hi : lo;
+          memcpy(&cat[(((size_t)t * 4 + kc) * 128 + r) * 64], &src[((size_t)t * 256 + kc * 64 + (r & 63)) * 64], 64 * sizeof(__half));
+        }
+    SFD2_CUDA(cudaMalloc(&L.w_cat, cat.size() * sizeof(__half)));
+    SFD2_CUDA(cudaMemcpy(L.w_cat, cat.data(), cat.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    const uint64_t cdims[2] = {64, (uint64_t)taps * 4 * 128};
+    const uint64_t cstr[1] = {128};
+    const uint32_t cbox[2] = {64u, 128u}, chalf[2] = {64u, 64u};
+    int rc = make_tmap_f16(&L.tm_w_cat, L.w_cat, 2, cdims, cstr, cbox);
+    if (!rc) rc = make_tmap_f16(&L.tm_w_cat_half, L.w_cat, 2, cdims, cstr, chalf);
+    if (rc) return rc;
+  }
   const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
   const uint64_t strides[1] = {(uint64_t)cols * 2};
   const uint32_t box[2] = {64u, (uint32_t)(diag ? 64 : L.cout_tc)};
@@ -634,7 +684,14 @@ int tc_encode_weights(Layer& L) {
 // Activation tensor maps: s1   stride-1 view {C, W, H}, box {64,16,8}          (per-tap loads, 1x1 layers)
 //                         s2   stride-2 view {C, 2, Wp/2, 2, Hp/2}, box {64,1,16,1,8}
 //                         halo stride-1 view {C, W, H}, box {64,10,18}          (one load per chunk, 3x3 layers)
-int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo) {
+int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo, CUtensorMap* t8x16) {
+  if (t8x16) {   // {64 ch, 8 px, 16 rows}: the A box of the 1x1 layers in split-ring mode
+    const uint64_t dims[3] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H};
+    const uint64_t str[2] = {(uint64_t)t.C * 2, (uint64_t)t.Wp * t.C * 2};
+    const uint32_t box[3] = {64u, 8u, 16u};
+    int rc = make_tmap_f16(t8x16, base, 3, dims, str, box);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[3] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H};
     const uint64_t str[2] = {(uint64_t)t.C * 2, (uint64_t)t.Wp * t.C * 2};
@@ -669,6 +726,8 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
+int g_tc_split1x1 = 1;    // SFD2_TC_SPLIT1X1=0: 1x1 layers through the combined (A + B) stage ring
+int g_tc_diagcat = 1;     // SFD2_TC_DIAGCAT=0: grouped layers in exact mode as three N=64 MMAs per K step (no [w_hi | w_lo] slabs)
 int g_tc_prefetch = 0;    // SFD2_TC_PREFETCH=1: TMA L2 prefetches one tile ahead (measured: slower)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
 
@@ -681,7 +740,12 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const bool diag = (L.groups == 32);
   TcConvArgs a{};
   a.Ho = out.H; a.Wo = out.W;
-  a.halo = (g_tc_halo && L.k == 3 && L.stride == 1) ? 1 : 0;
+  const bool split1 = g_tc_split1x1 && L.k == 1 && L.stride == 1 && !diag;
+  a.halo = ((g_tc_halo && L.k == 3 && L.stride == 1) || split1) ? 1 : 0;
+  a.hw = split1 ? 8 : TC_HALO_W;
+  a.hoff = split1 ? 0 : 1;
+  a.a_plane_bytes = split1 ? 8 * 16 * 128 : TC_HALO_BYTES;
+  a.a_plane_off = split1 ? 8 * 16 * 128 : TC_HALO_SLOT;
   a.tile_w = a.halo ? 8 : TC_TILE_W;
   a.tile_h = a.halo ? 16 : TC_TILE_H;
   a.epi_rows = a.halo ? 4 : 2;
@@ -703,6 +767,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   // (block-diagonal grouped layers add mostly exact zeros, so their single accumulator is already accurate)
   a.corr = (split == 3 && L.k == 3 && !diag) ? 1 : 0;
   a.buf_stride = a.acc_cols * (1 + a.corr);
+  if (a.halo && diag && split == 3 && g_tc_diagcat && L.w_cat) {   // see TcConvArgs::cat
+    a.cat = 1; a.nsplit = 2; a.n_mma = 128; a.acc_cols = 128; a.corr = 1;
+    a.buf_stride = 256;
+  }
   // the epilogue reads 32-column chunks, so an 80-wide accumulator (headP) is over-read by 16 columns:
   // keep that inside the allocation
   const int pass_ch = (a.nsplit > 1) ? a.n_mma : round_up(L.cout, 32);   // channels the epilogue reads per pass
@@ -728,8 +796,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.stages = stages;
   a.ring_bytes = stages * a.stage_bytes;
   if (a.halo) {
-    a.a_slot_bytes = (split == 3 ? 2 : 1) * TC_HALO_SLOT;
+    a.a_slot_bytes = (split == 3 ? 2 : 1) * a.a_plane_off;
     a.a_slots = 2;
+    if (split1)   // a whole tile of A in flight if two weight slabs still fit beside it
+      while (a.a_slots < 4 && a.a_slots < a.kchunks && (a.a_slots + 1) * a.a_slot_bytes + 2 * a.b_bytes <= smem_max - smem_fixed) ++a.a_slots;
     int bs = (smem_max - smem_fixed - a.a_slots * a.a_slot_bytes) / a.b_bytes;
     const int max_bs = getenv("SFD2_TC_BSTAGES") ? atoi(getenv("SFD2_TC_BSTAGES")) : TC_MAX_STAGES;
     if (bs > max_bs) bs = max_bs;
@@ -761,15 +831,15 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const int so = a.halo ? 2 : 0;   // store maps: [hi, lo] with 16x2 boxes, then [hi, lo] with 8x4 boxes
   const CUtensorMap& o_hi = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so];
   const CUtensorMap& o_lo = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so + 1];
-  const CUtensorMap& r_hi = res ? res->tm_st[0] : o_hi;
-  const CUtensorMap& r_lo = res ? res->tm_st[1] : o_lo;
+  const CUtensorMap& r_hi = res ? res->tm_st[so] : o_hi;       // residual boxes have the epilogue warps' pixel shape
+  const CUtensorMap& r_lo = res ? res->tm_st[so + 1] : o_lo;
   // residual as {64 ch, 16 px, 8 rows} boxes (its stride-1 load views) for the L2 prefetch
   SFD2_CHECK(!res || res->tm, SFD2_ERR_ARG, "conv_tc(%s): residual has no load maps", L.name.c_str());
   const CUtensorMap& p_hi = res ? res->tm[0] : o_hi;
   const CUtensorMap& p_lo = res ? res->tm[1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const CUtensorMap* tmA = in.tm + (a.halo ? 4 : (L.stride == 2 ? 2 : 0));
+  const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
   a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
@@ -790,11 +860,12 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   cfg.numAttrs = 1;
   // weight-slab boxes: full slab = n_mma rows; with multicast each CTA fetches n_mma/2 rows
   const int box_rows = (a.mc > 1) ? a.n_mma / 2 : a.n_mma;
-  const int full_rows = diag ? 64 : L.cout_tc;
+  const int full_rows = a.cat ? 128 : (diag ? 64 : L.cout_tc);
   const int mi = (box_rows == full_rows) ? 0 : (box_rows * 2 == full_rows ? 1 : 2);
   SFD2_CHECK(box_rows == full_rows || box_rows * 2 == full_rows || box_rows * 4 == full_rows, SFD2_ERR_ARG,
              "conv_tc(%s): no weight map for %d-row boxes", L.name.c_str(), box_rows);
-  const CUtensorMap& wb_hi = mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter);
+  const CUtensorMap& wb_hi = a.cat ? (mi == 0 ? L.tm_w_cat : L.tm_w_cat_half)
+                                   : (mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter));
   const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
   SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, p_hi, p_lo, a, sw));
   ++g_launches;

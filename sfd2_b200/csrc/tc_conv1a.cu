@@ -77,24 +77,17 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   // items tid, tid + 128, ...; out-of-image positions are flagged and become the conv's zero padding
   float raw[C1M_PER_THREAD];
   unsigned inb = 0;
-  // the items' (row, channel, column) do not depend on the segment: decode them once (kyc in bits 8.., column in 0..7)
-  int meta[C1M_PER_THREAD];
-#pragma unroll
-  for (int t = 0; t < C1M_PER_THREAD; ++t) {
-    const int i = tid + 128 * t;
-    const int kyc = i / C1M_COLS;
-    meta[t] = (i < C1M_ITEMS) ? ((kyc << 8) | (i - kyc * C1M_COLS)) : -1;
-  }
   auto prefetch = [&](int seg) {
     const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1M_SEG;
     inb = 0;
 #pragma unroll
     for (int t = 0; t < C1M_PER_THREAD; ++t) {
-      const int kyc = meta[t] >> 8, col = meta[t] & 255;
+      const int i = tid + 128 * t;
+      const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
       const int ky = kyc / 3, c = kyc - ky * 3;
       const int iy = y + ky - 1, ix = x0 + col - 1;
       raw[t] = 0.f;
-      if (meta[t] >= 0 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+      if (i < C1M_ITEMS && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
         inb |= 1u << t;
         if (a.img_dtype == SFD2_IMG_F32_NCHW) raw[t] = __ldg(reinterpret_cast<const float*>(a.img) + (size_t)c * plane + (size_t)iy * a.W + ix);
         else raw[t] = (float)__ldg(reinterpret_cast<const unsigned char*>(a.img) + ((size_t)iy * a.W + ix) * 3 + c);
@@ -108,8 +101,9 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
     // normalise exactly like the reference ((x - mean) / std, IEEE division; u8 / 255 first) and stage the patch
 #pragma unroll
     for (int t = 0; t < C1M_PER_THREAD; ++t) {
-      if (meta[t] >= 0) {
-        const int kyc = meta[t] >> 8, col = meta[t] & 255;
+      const int i = tid + 128 * t;
+      if (i < C1M_ITEMS) {
+        const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
         const int c = kyc % 3;
         const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
         const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
