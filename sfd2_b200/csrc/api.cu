@@ -44,7 +44,7 @@ struct Ws {
   int wsH = 0, wsW = 0;
   bool have_f32 = false, have_tc = false;
   Act acts[NUM_ACTS];
-  CUtensorMap maps[NUM_ACTS][10];
+  CUtensorMap maps[NUM_ACTS][8];
   CUtensorMap st_maps[NUM_ACTS][4];
   CUtensorMap map_1a[4];                    // conv1a output rows: [hi, lo] box {64 ch, 256 px, 1 row}, [hi, lo] box {64, 128, 1}
   CUtensorMap map_logits[2], map_desc[2], map_semi[2];   // fp32 head outputs (TMA store views: 16x2 and 8x4 boxes)
@@ -178,9 +178,9 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       SFD2_CUDA(cudaMalloc(&a.lo, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.hi, 0, a.elems() * sizeof(__half)));
       SFD2_CUDA(cudaMemset(a.lo, 0, a.elems() * sizeof(__half)));
-      int rc = tc_make_act_maps(a, a.hi, &w.maps[i][0], &w.maps[i][2], &w.maps[i][4], &w.maps[i][6], &w.maps[i][8]);
+      int rc = tc_make_act_maps(a, a.hi, &w.maps[i][0], &w.maps[i][2], &w.maps[i][4], &w.maps[i][6]);
       if (rc) return rc;
-      rc = tc_make_act_maps(a, a.lo, &w.maps[i][1], &w.maps[i][3], &w.maps[i][5], &w.maps[i][7], &w.maps[i][9]);
+      rc = tc_make_act_maps(a, a.lo, &w.maps[i][1], &w.maps[i][3], &w.maps[i][5], &w.maps[i][7]);
       if (rc) return rc;
       a.tm = w.maps[i];
       for (int b = 0; b < 2 && !rc; ++b) {
@@ -328,7 +328,6 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_PREFETCH")) g_tc_prefetch = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_DIAGCAT")) g_tc_diagcat = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_SPLIT1X1")) g_tc_split1x1 = atoi(e) != 0;
-  if (const char* e = getenv("SFD2_TC_S2HALO")) g_tc_s2halo = atoi(e) != 0;
   const char* env_streams = getenv("SFD2_STREAMS");
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
@@ -797,7 +796,7 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin,
   in.H = h; in.W = w; in.C = cin; in.Hp = round_up(h, 2); in.Wp = round_up(w, 2);
   out.H = conv_out(h, stride); out.W = conv_out(w, stride); out.C = cout; out.Hp = round_up(out.H, 2); out.Wp = round_up(out.W, 2);
   const int outC_f32 = round_up(cout, 16);
-  CUtensorMap maps[10];
+  CUtensorMap maps[8];
   float* yf = nullptr;
   std::vector<float> xin(in.elems(), 0.f);
   for (int yy = 0; yy < h; ++yy) memcpy(xin.data() + (size_t)yy * in.Wp * cin, x + (size_t)yy * w * cin, (size_t)w * cin * 4);
@@ -819,8 +818,8 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* c, const float* x, int h, int w, int cin,
     DBG_CUDA(cudaMalloc(&in.lo, in.elems() * 2));
     DBG_CUDA(cudaMemcpy(in.hi, hi.data(), in.elems() * 2, cudaMemcpyHostToDevice));
     DBG_CUDA(cudaMemcpy(in.lo, lo.data(), in.elems() * 2, cudaMemcpyHostToDevice));
-    rc = tc_make_act_maps(in, in.hi, &maps[0], &maps[2], &maps[4], &maps[6], &maps[8]);
-    if (!rc) rc = tc_make_act_maps(in, in.lo, &maps[1], &maps[3], &maps[5], &maps[7], &maps[9]);
+    rc = tc_make_act_maps(in, in.hi, &maps[0], &maps[2], &maps[4], &maps[6]);
+    if (!rc) rc = tc_make_act_maps(in, in.lo, &maps[1], &maps[3], &maps[5], &maps[7]);
     in.tm = maps;
     Act o2 = out; o2.Wp = out.W; o2.Hp = out.H; o2.C = outC_f32;
     DBG_CUDA(cudaMalloc(&yf, o2.elems() * 4));

@@ -42,7 +42,7 @@ struct Act {
   __half* hi = nullptr;  // TC modes: x ~ hi (+ lo)
   __half* lo = nullptr;
   int H = 0, W = 0, C = 0, Hp = 0, Wp = 0;
-  const CUtensorMap* tm = nullptr;     // [s1_hi, s1_lo, s2_hi, s2_lo, halo_hi, halo_lo, t8x16_hi, t8x16_lo, s2halo_hi, s2halo_lo] TMA load views
+  const CUtensorMap* tm = nullptr;     // [s1_hi, s1_lo, s2_hi, s2_lo, halo_hi, halo_lo, t8x16_hi, t8x16_lo] TMA load views
   const CUtensorMap* tm_st = nullptr;  // [hi, lo] 16x2-pixel boxes, [hi, lo] 8x4-pixel boxes: TMA store views
   size_t elems() const { return (size_t)Hp * Wp * C; }
 };
@@ -87,7 +87,7 @@ int launch_l2norm128(float* desc, int npix, cudaStream_t st);
 // tc_conv.cu
 int tc_encode_weights(Layer& L);
 int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo,
-                     CUtensorMap* t8x16 = nullptr, CUtensorMap* s2halo = nullptr);
+                     CUtensorMap* t8x16 = nullptr);
 int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w);
 // epi_fn (fp32 outputs only): 0 raw, 1 L2-normalised channels, 2 exp-normalised (softmax-with-eps) channels 0..63
 // sta / sta_out: fuse ConvSta (1x1 256 -> 3) on this layer's output into the epilogue (fp16-plane outputs only)
@@ -129,7 +129,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_prefetch, g_tc_diagcat, g_tc_split1x1, g_tc_s2halo;
+extern int g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_prefetch, g_tc_diagcat, g_tc_split1x1;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

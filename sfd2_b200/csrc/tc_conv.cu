@@ -74,10 +74,6 @@ struct TcConvArgs {
   // is used once, the weights come from L2 and are reused by every tile, so A gets a ring as deep as a whole tile
   // (4 chunks) and the weight slabs a shallow one - the combined (A + B) stages left room for only two in flight
   int hw, hoff, a_plane_bytes, a_plane_off;
-  // stride-2 3x3 layers in split-ring mode: the nine taps read only FOUR distinct boxes, one per parity plane of the
-  // [Hp/2][2][Wp/2][2][C] view - plane (py, px), box {9 px, 17 rows} at plane origin (x0-1, y0-1) - and a tap is
-  // that box shifted by (ky != 0, kx != 0).  Four A loads of 153 pixel rows per chunk instead of nine of 128.
-  int s2h;
   int tile_w, tile_h, epi_rows, ring_bytes;
   int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
@@ -102,10 +98,6 @@ struct TcConvArgs {
 // is exactly what the constant bank behind __grid_constant__ parameters serves in one broadcast; shared memory has no
 // 3 KB to spare (rb2c3's two 96 KB stages + staging fill the 227 KB to within 400 bytes).
 struct TcStaW { float w[256 * 3]; };
-
-// stride-2 parity planes: plane pp = py*2 + px serves taps S2 order[s2_start(pp) .. s2_start(pp+1))
-__device__ __forceinline__ int s2_start(int pp) { return pp == 0 ? 0 : (pp == 1 ? 1 : (pp == 2 ? 3 : (pp == 3 ? 5 : 9))); }
-__device__ __forceinline__ int s2_tap(int ti) { return (int)((0x862071534ull >> (4 * ti)) & 0xFull); }   // 4 | 3 5 | 1 7 | 0 2 6 8
 
 constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
 constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
@@ -174,7 +166,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        if (a.prefetch && !a.s2h && it + 1 < a.iters && tile + (int)gridDim.x < a.num_tiles) {   // next tile's halo boxes -> L2
+        if (a.prefetch && it + 1 < a.iters && tile + (int)gridDim.x < a.num_tiles) {   // next tile's halo boxes -> L2
           const int tn = tile + (int)gridDim.x;
           const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
           for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -184,21 +176,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
-          for (int pp = 0; pp < (a.s2h ? 4 : 1); ++pp) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
           mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
-          if (a.s2h) {
-            tma_load_5d(slot, &tmA_hi, &fullA[sa], kc * 64, pp & 1, x0 - 1, pp >> 1, y0 - 1);
-            if (planes == 2) tma_load_5d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, pp & 1, x0 - 1, pp >> 1, y0 - 1);
-          } else {
-            tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
-            if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
-          }
+          tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+          if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
-          const int t0 = a.s2h ? s2_start(pp) : 0, t1 = a.s2h ? s2_start(pp + 1) : a.taps;
-          for (int ti = t0; ti < t1; ++ti) {
-            const int tap = a.s2h ? s2_tap(ti) : ti;
+          for (int tap = 0; tap < a.taps; ++tap) {
             const int brow = a.cat ? (tap * 4 + kc) * 128 : (a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
             const int bcol = a.diag ? 0 : kc * 64;
             for (int pl = 0; pl < (a.cat ? 1 : planes); ++pl) {
@@ -214,7 +198,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               }
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
-          }
           }
         }
       }
@@ -297,21 +280,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
-          for (int pp = 0; pp < (a.s2h ? 4 : 1); ++pp) {
           mbar_wait(&fullA[sa], pha);
           tc_fence_after();
           const uint32_t abase = smem_u32(smem + (size_t)sa * a.a_slot_bytes);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.cat ? (kc & 1) * 128 : (a.diag ? kc * 64 : 0)));
           const uint32_t ccol = a.cat ? dcol + 64u : (a.corr ? dcol + (uint32_t)a.acc_cols : dcol);
-          const int t0 = a.s2h ? s2_start(pp) : 0, t1 = a.s2h ? s2_start(pp + 1) : a.taps;
-          for (int ti = t0; ti < t1; ++ti) {
-            const int tap = a.s2h ? s2_tap(ti) : ti;
-            // stride 1: the tap's pixel shift inside the halo box; stride 2: 0 / 1 plane pixel per axis
-            const uint32_t off = a.s2h ? (uint32_t)((((tap / 3) ? 1 : 0) * a.hw + ((tap % 3) ? 1 : 0)) * 128)
-                                       : (uint32_t)(((tap / 3) * a.hw + (tap % 3)) * 128);
+          for (int tap = 0; tap < a.taps; ++tap) {
+            const uint32_t off = (uint32_t)(((tap / 3) * a.hw + (tap % 3)) * 128);
             const uint64_t da_hi = make_desc_sw128_sbo(abase + off, (uint32_t)a.hw * 128);
             const uint64_t da_lo = make_desc_sw128_sbo(abase + (uint32_t)a.a_plane_off + off, (uint32_t)a.hw * 128);
-            const bool first = (ti == 0) && (a.diag || kc == 0);
+            const bool first = (tap == 0) && (a.diag || kc == 0);
             if (a.cat) {
               // one [w_hi | w_lo] slab: a_hi x both (N = 128: main | correction), then a_lo x w_hi (N = 64) into the
               // correction columns - which the N = 128 MMA of this tap has already initialised when tap == 0
@@ -353,9 +331,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
           }
-          umma_commit(&emptyA[sa]);             // A box free once all of its taps have read it
+          umma_commit(&emptyA[sa]);             // halo tile free once all nine taps have read it
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
-          }
         }
         umma_commit(&tfull[buf]);
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
@@ -707,15 +684,7 @@ int tc_encode_weights(Layer& L) {
 // Activation tensor maps: s1   stride-1 view {C, W, H}, box {64,16,8}          (per-tap loads, 1x1 layers)
 //                         s2   stride-2 view {C, 2, Wp/2, 2, Hp/2}, box {64,1,16,1,8}
 //                         halo stride-1 view {C, W, H}, box {64,10,18}          (one load per chunk, 3x3 layers)
-int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo, CUtensorMap* t8x16,
-                     CUtensorMap* s2halo) {
-  if (s2halo) {  // one parity plane of the stride-2 view: {64 ch, 1, 9 px, 1, 17 rows}
-    const uint64_t dims[5] = {(uint64_t)t.C, 2, (uint64_t)t.Wp / 2, 2, (uint64_t)t.Hp / 2};
-    const uint64_t str[4] = {(uint64_t)t.C * 2, (uint64_t)t.C * 4, (uint64_t)t.Wp * t.C * 2, (uint64_t)t.Wp * t.C * 4};
-    const uint32_t box[5] = {64u, 1u, 9u, 1u, 17u};
-    int rc = make_tmap_f16(s2halo, base, 5, dims, str, box);
-    if (rc) return rc;
-  }
+int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensorMap* s2, CUtensorMap* halo, CUtensorMap* t8x16) {
   if (t8x16) {   // {64 ch, 8 px, 16 rows}: the A box of the 1x1 layers in split-ring mode
     const uint64_t dims[3] = {(uint64_t)t.C, (uint64_t)t.W, (uint64_t)t.H};
     const uint64_t str[2] = {(uint64_t)t.C * 2, (uint64_t)t.Wp * t.C * 2};
@@ -757,8 +726,7 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
-int g_tc_s2halo = 1;      // SFD2_TC_S2HALO=0: stride-2 3x3 layers with one A load per tap (nine 128-pixel boxes per chunk)
-int g_tc_split1x1 = 0;    // SFD2_TC_SPLIT1X1=1: 1x1 layers with split A / B rings (measured: no gain)
+int g_tc_split1x1 = 1;    // SFD2_TC_SPLIT1X1=0: 1x1 layers through the combined (A + B) stage ring
 int g_tc_diagcat = 1;     // SFD2_TC_DIAGCAT=0: grouped layers in exact mode as three N=64 MMAs per K step (no [w_hi | w_lo] slabs)
 int g_tc_prefetch = 0;    // SFD2_TC_PREFETCH=1: TMA L2 prefetches one tile ahead (measured: slower)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
@@ -773,13 +741,11 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   TcConvArgs a{};
   a.Ho = out.H; a.Wo = out.W;
   const bool split1 = g_tc_split1x1 && L.k == 1 && L.stride == 1 && !diag;
-  const bool s2h = g_tc_s2halo && L.k == 3 && L.stride == 2 && !diag;
-  a.halo = ((g_tc_halo && L.k == 3 && L.stride == 1) || split1 || s2h) ? 1 : 0;
-  a.s2h = s2h ? 1 : 0;
-  a.hw = split1 ? 8 : (s2h ? 9 : TC_HALO_W);
+  a.halo = ((g_tc_halo && L.k == 3 && L.stride == 1) || split1) ? 1 : 0;
+  a.hw = split1 ? 8 : TC_HALO_W;
   a.hoff = split1 ? 0 : 1;
-  a.a_plane_bytes = split1 ? 8 * 16 * 128 : (s2h ? 9 * 17 * 128 : TC_HALO_BYTES);
-  a.a_plane_off = split1 ? 8 * 16 * 128 : (s2h ? 20 * 1024 : TC_HALO_SLOT);
+  a.a_plane_bytes = split1 ? 8 * 16 * 128 : TC_HALO_BYTES;
+  a.a_plane_off = split1 ? 8 * 16 * 128 : TC_HALO_SLOT;
   a.tile_w = a.halo ? 8 : TC_TILE_W;
   a.tile_h = a.halo ? 16 : TC_TILE_H;
   a.epi_rows = a.halo ? 4 : 2;
@@ -834,7 +800,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     a.a_slots = 2;
     if (split1)   // a whole tile of A in flight if two weight slabs still fit beside it
       while (a.a_slots < 4 && a.a_slots < a.kchunks && (a.a_slots + 1) * a.a_slot_bytes + 2 * a.b_bytes <= smem_max - smem_fixed) ++a.a_slots;
-    if (s2h && 3 * a.a_slot_bytes + 3 * a.b_bytes <= smem_max - smem_fixed) a.a_slots = 3;   // three of the four parity planes
     int bs = (smem_max - smem_fixed - a.a_slots * a.a_slot_bytes) / a.b_bytes;
     const int max_bs = getenv("SFD2_TC_BSTAGES") ? atoi(getenv("SFD2_TC_BSTAGES")) : TC_MAX_STAGES;
     if (bs > max_bs) bs = max_bs;
@@ -874,7 +839,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& p_lo = res ? res->tm[1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : (s2h ? 8 : 4)) : (L.stride == 2 ? 2 : 0));
+  const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
   a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
