@@ -325,7 +325,6 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_NSPLIT")) g_tc_nsplit = atoi(e) != 0;
   if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;
   if (const char* e = getenv("SFD2_FUSE_STA")) g_fuse_sta = atoi(e) != 0;
-  if (const char* e = getenv("SFD2_TC_PREFETCH")) g_tc_prefetch = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_DIAGCAT")) g_tc_diagcat = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_SPLIT1X1")) g_tc_split1x1 = atoi(e) != 0;
   const char* env_streams = getenv("SFD2_STREAMS");

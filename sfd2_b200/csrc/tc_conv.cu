@@ -82,10 +82,6 @@ struct TcConvArgs {
   int epi_fn;      // fp32 head epilogues: 0 none, 1 = L2-normalise the pixel's channels (F.normalize, sfd2.py:342),
                    // 2 = exp / (sum_65 exp + 1e-5), channels 0..63 (sfd2.py:330-333); both need a first pass over TMEM
   int has_res;     // residual planes to add: 0 none, 1 hi, 2 hi + lo
-  int prefetch;    // producer issues TMA L2 prefetches one tile ahead (A operand) / for the current tile (residual):
-                   // the memory-bound 1x1 layers run only 2 ring stages (96 KB each in exact mode), i.e. half a tile
-                   // of lookahead, and the residual is requested two 32-channel chunks before it is needed - both
-                   // less than one HBM round trip.  The prefetch puts those lines into L2 a full tile earlier.
   // fused ConvSta (1x1 256 -> 3, nets/sfd2.py:303,345) on this layer's OUTPUT (rb2c3 = out4): the epilogue already
   // holds every output pixel's 256 channels in registers chunk by chunk, so the three dot products cost 96 FMAs per
   // chunk and save re-reading the 123 MB activation in a separate kernel.  Computed in fp32 on the value the
@@ -111,7 +107,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
-               const __grid_constant__ CUtensorMap tmP_hi, const __grid_constant__ CUtensorMap tmP_lo,
                const __grid_constant__ TcConvArgs a, const __grid_constant__ TcStaW sw) {
   const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
@@ -166,14 +161,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        if (a.prefetch && it + 1 < a.iters && tile + (int)gridDim.x < a.num_tiles) {   // next tile's halo boxes -> L2
-          const int tn = tile + (int)gridDim.x;
-          const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
-          for (int kc = 0; kc < a.kchunks; ++kc) {
-            tma_prefetch_3d(&tmA_hi, kc * 64, xn - a.hoff, yn - a.hoff);
-            if (planes == 2) tma_prefetch_3d(&tmA_lo, kc * 64, xn - a.hoff, yn - a.hoff);
-          }
-        }
         for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
@@ -208,29 +195,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         const int tile = blockIdx.x + it * gridDim.x;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        if (a.prefetch && tile < a.num_tiles) {
-          if (a.has_res)                        // this tile's residual (the epilogue needs it about one tile from now)
-            for (int c = 0; c < a.cout; c += 64) {
-              tma_prefetch_3d(&tmP_hi, c, x0, y0);
-              if (a.has_res == 2) tma_prefetch_3d(&tmP_lo, c, x0, y0);
-            }
-          const int tn = tile + (int)gridDim.x;
-          if (it + 1 < a.iters && tn < a.num_tiles) {   // next tile's A boxes
-            const int yn = (tn / a.tiles_x) * a.tile_h, xn = (tn % a.tiles_x) * a.tile_w;
-            if (a.taps == 1 && a.stride == 1) {
-              for (int kc = 0; kc < a.kchunks; ++kc) {
-                tma_prefetch_3d(&tmA_hi, kc * 64, xn, yn);
-                if (a.split == 3) tma_prefetch_3d(&tmA_lo, kc * 64, xn, yn);
-              }
-            } else if (a.stride == 2) {                 // the four parity planes cover all nine taps' boxes but for
-              for (int pp = 0; pp < 4; ++pp)            // one leading row / column (a neighbouring tile's lines)
-                for (int kc = 0; kc < a.kchunks; ++kc) {
-                  tma_prefetch_5d(&tmA_hi, kc * 64, pp & 1, xn, pp >> 1, yn);
-                  if (a.split == 3) tma_prefetch_5d(&tmA_lo, kc * 64, pp & 1, xn, pp >> 1, yn);
-                }
-            }
-          }
-        }
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < a.kchunks; ++kc) {
@@ -726,9 +690,8 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
-int g_tc_split1x1 = 1;    // SFD2_TC_SPLIT1X1=0: 1x1 layers through the combined (A + B) stage ring
+int g_tc_split1x1 = 0;    // SFD2_TC_SPLIT1X1=1: 1x1 layers with split A / B rings (measured: c1 63 -> 68 us)
 int g_tc_diagcat = 1;     // SFD2_TC_DIAGCAT=0: grouped layers in exact mode as three N=64 MMAs per K step (no [w_hi | w_lo] slabs)
-int g_tc_prefetch = 0;    // SFD2_TC_PREFETCH=1: TMA L2 prefetches one tile ahead (measured: slower)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
@@ -812,7 +775,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.out_mode = out_f32_map ? 2 : (split == 3 ? 1 : 0);
   a.epi_fn = out_f32_map ? epi_fn : 0;
   a.has_res = res ? (split == 3 ? 2 : 1) : 0;
-  a.prefetch = g_tc_prefetch;
   a.sta_out = fuse_sta ? sta_out : nullptr;
   static const TcStaW kNoSta{};
   TcStaW* swp = nullptr;
@@ -833,10 +795,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& o_lo = out_f32_map ? out_f32_map[a.halo] : out.tm_st[so + 1];
   const CUtensorMap& r_hi = res ? res->tm_st[so] : o_hi;       // residual boxes have the epilogue warps' pixel shape
   const CUtensorMap& r_lo = res ? res->tm_st[so + 1] : o_lo;
-  // residual as {64 ch, 16 px, 8 rows} boxes (its stride-1 load views) for the L2 prefetch
-  SFD2_CHECK(!res || res->tm, SFD2_ERR_ARG, "conv_tc(%s): residual has no load maps", L.name.c_str());
-  const CUtensorMap& p_hi = res ? res->tm[0] : o_hi;
-  const CUtensorMap& p_lo = res ? res->tm[1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
@@ -867,7 +825,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& wb_hi = a.cat ? (mi == 0 ? L.tm_w_cat : L.tm_w_cat_half)
                                    : (mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter));
   const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
-  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, p_hi, p_lo, a, sw));
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a, sw));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
