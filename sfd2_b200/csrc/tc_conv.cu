@@ -52,6 +52,7 @@ struct TcConvArgs {
                    // main + correction accumulators of BOTH TMEM buffers fit (N=256: 2 x (128 + 128) x 2 = 512 columns)
                    // and the epilogue of one pass overlaps the MMAs of the next; the small halo A tile is re-fetched
   int tap_rows;    // rows per tap in the packed weights (= the layer's padded Cout)
+  int ncat;        // per-tap ring, exact mode, N <= 64 with a correction accumulator: see the MMA issuer
   int cat;         // grouped layers, exact mode ("diag-cat"): the weight slab of a (tap, 64-channel chunk) is the
                    // N-concatenation [w_hi | w_lo] (128 rows), so ONE N=128 MMA per K step yields a_hi*w_hi (columns
                    // 0..63 of the chunk's 128 accumulator columns) and a_hi*w_lo (columns 64..127); a_lo*w_hi is an
@@ -304,6 +305,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
     } else if (leader && !a.halo) {
       const uint32_t idesc = make_idesc_f16(128, a.n_mma);
+      const uint32_t idesc_ncat = make_idesc_f16(128, 2 * a.n_mma);
       int stage = 0;
       uint32_t phase = 0;
       int buf = 0;
@@ -321,6 +323,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + a.b_bytes);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? (kb % a.kchunks) * 64 : 0));
           const bool first = a.diag ? (kb < a.kchunks) : (kb == 0);
+          if (a.ncat) {
+            // narrow layers (N <= 64): an SMEM-operand MMA at M = 128 costs ~64 cycles whatever N <= 128 is (measured:
+            // 67 cycles at N = 64), so a_hi x w_hi and a_hi x w_lo go out as ONE MMA over the adjacent [w_hi | w_lo]
+            // slabs of the stage - it fills the main columns and, right behind them, the correction columns
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db_hi, k), idesc_ncat, (first && k == 0) ? 0u : 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16(dcol + (uint32_t)a.acc_cols, desc_advance_k(da_lo, k), desc_advance_k(db_hi, k), idesc, 1u);
+          } else
 #pragma unroll 1
           for (int pass = 0; pass < a.split; ++pass) {
             const uint64_t da = (pass == 2) ? da_lo : da_hi;
@@ -734,6 +747,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     a.cat = 1; a.nsplit = 2; a.n_mma = 128; a.acc_cols = 128; a.corr = 1;
     a.buf_stride = 256;
   }
+  a.ncat = (g_tc_diagcat && !a.halo && !diag && split == 3 && a.corr && a.nsplit == 1 && a.n_mma == 64 && a.acc_cols == 64) ? 1 : 0;
   // the epilogue reads 32-column chunks, so an 80-wide accumulator (headP) is over-read by 16 columns:
   // keep that inside the allocation
   const int pass_ch = (a.nsplit > 1) ? a.n_mma : round_up(L.cout, 32);   // channels the epilogue reads per pass

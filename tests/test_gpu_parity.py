@@ -34,6 +34,7 @@ CONV_CASES = [  # H, W, cin, cout, k, stride, groups, relu
     (40, 56, 64, 64, 3, 1, 1, 1), (41, 57, 64, 128, 3, 2, 1, 1), (24, 40, 128, 256, 3, 1, 1, 1),
     (24, 40, 256, 256, 1, 1, 1, 1), (40, 56, 256, 256, 3, 2, 1, 1), (30, 34, 256, 65, 3, 1, 1, 0),
     (30, 34, 256, 128, 3, 1, 1, 0), (24, 40, 256, 256, 3, 1, 32, 1), (17, 19, 64, 64, 3, 1, 1, 1),
+    (41, 57, 64, 64, 3, 2, 1, 1),      # conv1b's shape class: stride 2, N = 64 ([w_hi | w_lo] single-MMA path in exact mode)
 ]
 
 
