@@ -1,5 +1,7 @@
 """Summarise an .ncu-rep into a small markdown table (committed under profiles/).
-    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_summary.md "title" """
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_ncu_summary.md "title" [traffic.json precision]
+With the two optional arguments the average DRAM bytes (read + write) per tc_conv_kernel launch of the capture are
+stored in traffic.json under the precision key (bench.py's roofline.traffic)."""
 import csv, io, subprocess, sys
 
 rep, out, title = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else sys.argv[1])
@@ -33,3 +35,18 @@ with open(out, "w") as f:
             cells.append(v)
         f.write(f"| {i} | " + " | ".join(cells) + " |\n")
 print("wrote", out)
+if len(sys.argv) > 5:
+    import json, os
+    tj_path, prec = sys.argv[4], sys.argv[5]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for r in data:
+        if "tc_conv_kernel" in r[ki]:
+            tot += float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+            n += 1
+    tj = json.load(open(tj_path)) if os.path.exists(tj_path) else {}
+    tj[prec] = {"tc_conv_bytes_per_launch": tot / max(n, 1), "launches": n, "source": os.path.basename(rep),
+                "metric": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full"}
+    json.dump(tj, open(tj_path, "w"), indent=1)
+    print("traffic", prec, tot / max(n, 1))
