@@ -11,9 +11,12 @@
 // TMEM -> bias + ReLU -> fp16 hi/lo -> swizzled staging tile -> TMA store; the staging tile IS the A tile
 // (the MMAs have finished reading it by then), which keeps the block at 54 KB of shared memory.
 //
-// One 128-thread block = one segment at a time, persistent over segments; the phases of a segment are a serial
+// One 128-thread block owns a 128-pixel-wide column strip over a range of rows and walks DOWN it: the three
+// input rows of an output row live in a ring of three row buffers, so every step normalises and splits only the
+// ONE new row (390 values per block instead of 1170), once, into packed (hi, lo) half pairs - the im2col build
+// is then 27 shared loads and 32 byte-permutes per pixel, no conversions.  The phases of a step are a serial
 // latency chain (load -> build -> MMA -> TMEM read -> store), so 4 blocks per SM overlap each other's phases and
-// each block prefetches the raw pixels of its next segment into registers while its MMAs run.  The layer's floor
+// each block prefetches the raw pixels of its next row into registers while its MMAs run.  The layer's floor
 // is the 491 MB write of the hi + lo planes.
 #include <algorithm>
 
@@ -26,11 +29,13 @@ using namespace ptx;
 
 constexpr int C1M_SEG = 128;
 constexpr int C1M_COLS = C1M_SEG + 2;          // segment + 1-pixel apron
-constexpr int C1M_ITEMS = 9 * C1M_COLS;        // (row, channel, column) values of a segment's input patch
-constexpr int C1M_PER_THREAD = (C1M_ITEMS + 127) / 128;   // 10
+constexpr int C1M_ROW_ITEMS = 3 * C1M_COLS;    // (channel, column) values of one input row of the strip
+constexpr int C1M_PER_THREAD = (C1M_ROW_ITEMS + 127) / 128;   // 4
+constexpr int C1M_PITCH = 132;                 // words per (row slot, channel)
 
 struct Conv1aMmaArgs {
   int H, W, split, img_dtype;
+  int rows_per_block;      // output rows a block walks through
   const void* img;         // raw image: f32 NCHW in [0,1] or u8 NHWC
   const __half* w_hi;      // [64 co][64 k] fp16, k = tap*3 + c (27 used)
   const __half* w_lo;
@@ -46,8 +51,8 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   uint8_t* sA_lo = base + 16384;
   uint8_t* sB_hi = base + 32768;         // [64 co][128 B]
   uint8_t* sB_lo = base + 40960;
-  float* patch = reinterpret_cast<float*>(base + 49152);   // [3 rows][3 ch][132]
-  float* sbias = patch + 9 * 132;                          // [64]
+  uint32_t* patch = reinterpret_cast<uint32_t*>(base + 49152);   // [3 row slots][3 ch][132]: lo half << 16 | hi half
+  float* sbias = reinterpret_cast<float*>(patch + 9 * C1M_PITCH);   // [64]
   uint64_t* bar = reinterpret_cast<uint64_t*>(sbias + 64);
   uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
 
@@ -68,64 +73,80 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   tc_fence_after();
   const uint32_t tmem = *slot;
   const uint32_t idesc = make_idesc_f16(128, 64);
-  const int segs_x = (a.W + C1M_SEG - 1) / C1M_SEG, nseg = segs_x * a.H;
+  const int segs_x = (a.W + C1M_SEG - 1) / C1M_SEG;
+  const int x0 = ((int)blockIdx.x % segs_x) * C1M_SEG;
+  const int ya = ((int)blockIdx.x / segs_x) * a.rows_per_block, yb = min(ya + a.rows_per_block, a.H);
   const size_t plane = (size_t)a.H * a.W;
   uint32_t phase = 0;
   const int r = tid;                                        // pixel of the segment = A row = TMEM lane
 
-  // raw (un-normalised) input values of a segment's patch: item i = (ky*3 + c) * 130 + col, this thread owns
-  // items tid, tid + 128, ...; out-of-image positions are flagged and become the conv's zero padding
+  // One input row of the strip = 390 (channel, column) items; this thread owns items tid, tid + 128, ...
+  // fetch(): raw (un-normalised) values into registers, out-of-image positions flagged (they become the conv's
+  // zero padding); stash(): normalise exactly like the reference ((x - mean) / std, IEEE division; u8 / 255
+  // first), split into fp16 hi / lo once, and store the packed pair into row slot `rs` of the ring.
   float raw[C1M_PER_THREAD];
   unsigned inb = 0;
-  auto prefetch = [&](int seg) {
-    const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1M_SEG;
+  auto fetch = [&](int iy) {
     inb = 0;
 #pragma unroll
     for (int t = 0; t < C1M_PER_THREAD; ++t) {
       const int i = tid + 128 * t;
-      const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
-      const int ky = kyc / 3, c = kyc - ky * 3;
-      const int iy = y + ky - 1, ix = x0 + col - 1;
+      const int c = i / C1M_COLS, col = i - c * C1M_COLS;
+      const int ix = x0 + col - 1;
       raw[t] = 0.f;
-      if (i < C1M_ITEMS && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+      if (i < C1M_ROW_ITEMS && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
         inb |= 1u << t;
         if (a.img_dtype == SFD2_IMG_F32_NCHW) raw[t] = __ldg(reinterpret_cast<const float*>(a.img) + (size_t)c * plane + (size_t)iy * a.W + ix);
         else raw[t] = (float)__ldg(reinterpret_cast<const unsigned char*>(a.img) + ((size_t)iy * a.W + ix) * 3 + c);
       }
     }
   };
-  if ((int)blockIdx.x < nseg) prefetch(blockIdx.x);
-
-  for (int seg = blockIdx.x; seg < nseg; seg += gridDim.x) {
-    const int y = seg / segs_x, x0 = (seg - y * segs_x) * C1M_SEG;
-    // normalise exactly like the reference ((x - mean) / std, IEEE division; u8 / 255 first) and stage the patch
+  auto stash = [&](int rs) {
 #pragma unroll
     for (int t = 0; t < C1M_PER_THREAD; ++t) {
       const int i = tid + 128 * t;
-      if (i < C1M_ITEMS) {
-        const int kyc = i / C1M_COLS, col = i - kyc * C1M_COLS;
-        const int c = kyc % 3;
+      if (i < C1M_ROW_ITEMS) {
+        const int c = i / C1M_COLS, col = i - c * C1M_COLS;
         const float mean = (c == 0) ? 0.485f : (c == 1 ? 0.456f : 0.406f);
         const float stdv = (c == 0) ? 0.229f : (c == 1 ? 0.224f : 0.225f);
         const float x = (a.img_dtype == SFD2_IMG_F32_NCHW) ? raw[t] : __fdiv_rn(raw[t], 255.0f);
-        patch[kyc * 132 + col] = ((inb >> t) & 1u) ? __fdiv_rn(__fsub_rn(x, mean), stdv) : 0.f;
+        const float v = ((inb >> t) & 1u) ? __fdiv_rn(__fsub_rn(x, mean), stdv) : 0.f;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        patch[(rs * 3 + c) * C1M_PITCH + col] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
       }
     }
-    if (tid == 0) bulk_wait_read<0>();                      // the previous segment's stores have read the A / staging tiles
+  };
+  if (ya >= yb) goto done;                                  // (uniform per block)
+  // ring slot of input row iy = (iy - (ya - 1)) % 3: rows ya-1 and ya go in first, row ya+1 is fetched for the first step
+  fetch(ya - 1); stash(0);
+  fetch(ya);     stash(1);
+  fetch(ya + 1);
+  {
+  int s0 = 0;                                               // slot of input row y-1; rows y, y+1 follow cyclically
+  for (int y = ya; y < yb; ++y) {
+    const int s1 = (s0 + 1 == 3) ? 0 : s0 + 1, s2 = (s1 + 1 == 3) ? 0 : s1 + 1;
+    stash(s2);                                              // row y+1 (its slot was last read two steps ago)
+    if (tid == 0) bulk_wait_read<0>();                      // the previous step's stores have read the A / staging tiles
     __syncthreads();
     // im2col row of pixel r: k = (ky*3 + kx)*3 + c, 27 values + 5 zeros = 4 chunks of 8 halfs per plane
     {
-      __align__(16) __half hi[32];
-      __align__(16) __half lo[32];
+      uint32_t w[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        float v = 0.f;
+        w[k] = 0u;
         if (k < 27) {
           const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-          v = patch[(ky * 3 + c) * 132 + r + kx];
+          const int rs = (ky == 0) ? s0 : (ky == 1 ? s1 : s2);
+          w[k] = patch[(rs * 3 + c) * C1M_PITCH + r + kx];
         }
-        hi[k] = __float2half_rn(v);
-        lo[k] = __float2half_rn(v - __half2float(hi[k]));
+      }
+      __align__(16) uint32_t hi[16];
+      __align__(16) uint32_t lo[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        hi[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x5410);   // the two low halves  (k = 2j, 2j+1)
+        lo[j] = __byte_perm(w[2 * j], w[2 * j + 1], 0x7632);   // the two high halves
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -152,7 +173,7 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
       umma_commit(bar);
     }
     __syncwarp();
-    if (seg + (int)gridDim.x < nseg) prefetch(seg + gridDim.x);   // loads fly while the MMAs run and the epilogue drains
+    if (y + 1 < yb) fetch(y + 2);                           // loads fly while the MMAs run and the epilogue drains
     mbar_wait(bar, phase);
     phase ^= 1u;
     tc_fence_after();
@@ -181,13 +202,16 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();                                        // staging complete; TMEM + patch reusable
+    __syncthreads();                                        // staging complete; TMEM + the oldest row slot reusable
     if (tid == 0) {
       tma_store_3d(&tm_hi, sA_hi, 0, x0, y);
       if (a.split == 3) tma_store_3d(&tm_lo, sA_lo, 0, x0, y);   // the single-pass mode never reads lo planes
       bulk_commit();
     }
+    s0 = s1;
   }
+  }
+done:
   if (tid == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
@@ -216,11 +240,15 @@ int conv1a_mma_encode(Layer& L) {
 int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
                       int num_sms, cudaStream_t st) {
   SFD2_CHECK(L.w_hi && L.w_lo && tm1a, SFD2_ERR_ARG, "conv1a_mma: weights / store maps missing");
-  Conv1aMmaArgs a{H, W, split, img_dtype, img, L.w_hi, L.w_lo, L.b_dev};
-  const int smem = 1024 + 49152 + (9 * 132 + 64) * 4 + 64;
+  // one wave of 4 resident blocks per SM: column strips x row ranges
+  const int segs_x = cdiv(W, C1M_SEG);
+  int rows_per_block = cdiv(H * segs_x, 4 * num_sms);
+  if (rows_per_block < 4) rows_per_block = std::min(4, H);   // the two extra rows a block loads amortise over its range
+  const int blocks = segs_x * cdiv(H, rows_per_block);
+  Conv1aMmaArgs a{H, W, split, img_dtype, rows_per_block, img, L.w_hi, L.w_lo, L.b_dev};
+  const int smem = 1024 + 49152 + (9 * C1M_PITCH + 64) * 4 + 64;
   SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
-  const int nseg = cdiv(W, C1M_SEG) * H;
-  conv1a_mma_kernel<<<std::min(nseg, 4 * num_sms), 128, smem, st>>>(tm1a[0], tm1a[1], a);
+  conv1a_mma_kernel<<<blocks, 128, smem, st>>>(tm1a[0], tm1a[1], a);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

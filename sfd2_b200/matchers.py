@@ -44,8 +44,9 @@ def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, rat
     n0, d = d0.shape
     n1 = d1.shape[0]
     dev = d0.device
-    m0 = torch.full((n0,), -1, dtype=torch.int32, device=dev)
-    s0 = torch.zeros((n0,), dtype=torch.float32, device=dev)
+    # match_finish_kernel writes every one of the n0 rows (also when d1 is empty), so no fill kernels are needed
+    m0 = torch.empty((n0,), dtype=torch.int32, device=dev)
+    s0 = torch.empty((n0,), dtype=torch.float32, device=dev)
     if n0 == 0:
         return m0, s0
     p = _mparams(mutual, dist_th, ratio_th, precision, ratio_mode)
