@@ -77,7 +77,7 @@ int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, 
                   const CUtensorMap* tm1a, int num_sms, cudaStream_t st);
 // tc_conv1a.cu
 int conv1a_mma_encode(Layer& L);
-int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const Act& out, int split,
+int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
                       int num_sms, cudaStream_t st);
 int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cudaStream_t st);
 // tc_in: 0 = fp32 input, 1 = fp16 hi+lo, 2 = fp16 hi only

@@ -213,7 +213,7 @@ int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, 
   SFD2_CHECK(L.cin == 3 && L.cout == 64 && L.k == 3, SFD2_ERR_WEIGHTS, "conv1a: unexpected layer shape");
   SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "unknown image dtype %d", img_dtype);
   // tcgen05 modes: one kernel normalises, builds the im2col operand and runs the MMAs (tc_conv1a.cu)
-  if (tc_out && g_conv1a_mma) return launch_conv1a_mma(img, img_dtype, H, W, L, out, tc_out, num_sms, st);
+  if (tc_out && g_conv1a_mma) return launch_conv1a_mma(img, img_dtype, H, W, L, tm1a + 2, tc_out, num_sms, st);
   if (img_dtype == SFD2_IMG_F32_NCHW) norm_kernel<SFD2_IMG_F32_NCHW><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
   else norm_kernel<SFD2_IMG_U8_NHWC><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
   // L.w_simt is [tap][ci][cout_pad = 64] fp32 = exactly the [27][64] table the kernels stage in smem

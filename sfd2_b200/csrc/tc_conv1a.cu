@@ -8,11 +8,8 @@
 // (K order = tap-major, channel-minor; padded to 32 with zeros) as fp16 hi / lo planes in the same
 // 128-byte-swizzled K-major layout TMA would produce - and one thread issues the tcgen05 MMAs
 // (M = 128 pixels, N = 64 channels, K = 32: 2 steps per pass, 3 passes in exact mode).  The epilogue is the usual
-// TMEM -> bias + ReLU -> fp16 hi/lo -> swizzled staging tile; the staging tile IS the A tile (the MMAs have
-// finished reading it by then), which keeps the block at 54 KB of shared memory.  The tile then leaves through plain
-// coalesced 16-byte stores (4 pixel rows = 512 contiguous bytes per warp instruction) rather than a TMA store: this
-// layer is nothing but a 491 MB write, and with TMA stores every step had to wait until the previous 32 KB tile had
-// been drained before it could rebuild the A tile (3.4 TB/s); ordinary stores are fire-and-forget.
+// TMEM -> bias + ReLU -> fp16 hi/lo -> swizzled staging tile -> TMA store; the staging tile IS the A tile
+// (the MMAs have finished reading it by then), which keeps the block at 54 KB of shared memory.
 //
 // One 128-thread block owns a 128-pixel-wide column strip over a range of rows and walks DOWN it: the three
 // input rows of an output row live in a ring of three row buffers, so every step normalises and splits only the
@@ -43,13 +40,11 @@ struct Conv1aMmaArgs {
   const __half* w_hi;      // [64 co][64 k] fp16, k = tap*3 + c (27 used)
   const __half* w_lo;
   const float* bias;       // [64]
-  __half* out_hi;          // conv1a output planes, pixel (y, x) at (y*Wp + x)*64
-  __half* out_lo;
-  int Wp;
 };
 
 __global__ void __launch_bounds__(128, 4)
-conv1a_mma_kernel(const __grid_constant__ Conv1aMmaArgs a) {
+conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                  const __grid_constant__ Conv1aMmaArgs a) {
   extern __shared__ uint8_t smem_raw_c1[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_c1) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA_hi = base;                 // [128 px][128 B]: im2col rows (K 0..31), then the output tile [128 px][64 ch]
@@ -132,7 +127,8 @@ conv1a_mma_kernel(const __grid_constant__ Conv1aMmaArgs a) {
   for (int y = ya; y < yb; ++y) {
     const int s1 = (s0 + 1 == 3) ? 0 : s0 + 1, s2 = (s1 + 1 == 3) ? 0 : s1 + 1;
     stash(s2);                                              // row y+1 (its slot was last read two steps ago)
-    __syncthreads();                                        // (also: the previous step's copy-out has read the staging tiles)
+    if (tid == 0) bulk_wait_read<0>();                      // the previous step's stores have read the A / staging tiles
+    __syncthreads();
     // im2col row of pixel r: k = (ky*3 + kx)*3 + c, 27 values + 5 zeros = 4 chunks of 8 halfs per plane
     {
       uint32_t w[32];
@@ -204,26 +200,19 @@ conv1a_mma_kernel(const __grid_constant__ Conv1aMmaArgs a) {
         if (a.split == 3) *reinterpret_cast<uint4*>(sA_lo + dst) = reinterpret_cast<const uint4*>(lo)[g];
       }
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();                                        // staging complete; TMEM + the oldest row slot reusable
-    // copy-out: chunk p of tile row `row` holds channels 8*(p ^ (row & 7)) .. +7 of pixel x0 + row
-    {
-      const size_t gbase = ((size_t)y * a.Wp + x0) * 64;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int idx = it * 128 + tid, row = idx >> 3, p = idx & 7;
-        if (x0 + row < a.W) {
-          const size_t g = gbase + (size_t)row * 64 + ((p ^ (row & 7)) << 3);
-          *reinterpret_cast<uint4*>(a.out_hi + g) = *reinterpret_cast<const uint4*>(sA_hi + row * 128 + (p << 4));
-          if (a.split == 3)                                 // the single-pass mode never reads lo planes
-            *reinterpret_cast<uint4*>(a.out_lo + g) = *reinterpret_cast<const uint4*>(sA_lo + row * 128 + (p << 4));
-        }
-      }
+    if (tid == 0) {
+      tma_store_3d(&tm_hi, sA_hi, 0, x0, y);
+      if (a.split == 3) tma_store_3d(&tm_lo, sA_lo, 0, x0, y);   // the single-pass mode never reads lo planes
+      bulk_commit();
     }
     s0 = s1;
   }
   }
 done:
+  if (tid == 0) bulk_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 64);
@@ -247,18 +236,19 @@ int conv1a_mma_encode(Layer& L) {
   return SFD2_OK;
 }
 
-int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const Act& out, int split,
+// tm1a: [hi, lo] store maps of the conv1a output with box {64 ch, 128 px, 1 row}
+int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
                       int num_sms, cudaStream_t st) {
-  SFD2_CHECK(L.w_hi && L.w_lo && out.hi && out.lo, SFD2_ERR_ARG, "conv1a_mma: weights / output planes missing");
+  SFD2_CHECK(L.w_hi && L.w_lo && tm1a, SFD2_ERR_ARG, "conv1a_mma: weights / store maps missing");
   // one wave of 4 resident blocks per SM: column strips x row ranges
   const int segs_x = cdiv(W, C1M_SEG);
   int rows_per_block = cdiv(H * segs_x, 4 * num_sms);
   if (rows_per_block < 4) rows_per_block = std::min(4, H);   // the two extra rows a block loads amortise over its range
   const int blocks = segs_x * cdiv(H, rows_per_block);
-  Conv1aMmaArgs a{H, W, split, img_dtype, rows_per_block, img, L.w_hi, L.w_lo, L.b_dev, out.hi, out.lo, out.Wp};
+  Conv1aMmaArgs a{H, W, split, img_dtype, rows_per_block, img, L.w_hi, L.w_lo, L.b_dev};
   const int smem = 1024 + 49152 + (9 * C1M_PITCH + 64) * 4 + 64;
   SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
-  conv1a_mma_kernel<<<blocks, 128, smem, st>>>(a);
+  conv1a_mma_kernel<<<blocks, 128, smem, st>>>(tm1a[0], tm1a[1], a);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
