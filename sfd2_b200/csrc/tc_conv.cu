@@ -102,6 +102,7 @@ constexpr int TC_HALO_SLOT = 23 * 1024;                                // per pl
 constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 4096;   // one (32 px x 128 B) staging tile per epilogue warp
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
+constexpr int TC_EXCH_BYTES = 2 * TC_EPI_WARPS * 32 * 4;   // head epilogues: partial-sum exchange between paired warps
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -123,6 +124,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
+  float* exch = reinterpret_cast<float*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -398,30 +400,71 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
-      float row_scale = 1.f;                      // head epilogues: per-pixel reduction over ALL channels first
       if (a.epi_fn) {
-        float acc = 0.f;
-        for (int ch = 0; ch < nchunks; ++ch) {
-          uint32_t v[32];
-          float x[32];
-          tmem_ld32(taddr + ch * 32, v);
-          tmem_ld_wait();
+        // Head epilogues (fp32 output, <= 128 channels = at most two own chunks per warp): every pixel needs a reduction
+        // over ALL its channels before anything can be written (sum x^2 for F.normalize, sfd2.py:342; sum_65 exp for the
+        // detector, sfd2.py:330-333).  Each warp reads only its own chunks, keeps them in registers, and the two warps
+        // of a lane quarter exchange their partial sums through shared memory (named barrier per quarter) - the
+        // accumulator is read exactly once and handed back to the MMA issuer before any store is staged.
+        float xo[2][32];
+        float part = 0.f;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-          if (a.corr) {
-            tmem_ld32(taddr + a.acc_cols + ch * 32, v);
+        for (int ci = 0; ci < 2; ++ci) {
+          const int ch = h + 2 * ci;
+          if (ch < nchunks) {
+            uint32_t v[32];
+            tmem_ld32(taddr + ch * 32, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(v[j]);
-          }
+            for (int j = 0; j < 32; ++j) xo[ci][j] = __uint_as_float(v[j]);
+            if (a.corr) {
+              tmem_ld32(taddr + a.acc_cols + ch * 32, v);
+              tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = x[j] + sbias[ch * 32 + j];
-            if (ch * 32 + j < a.cout) acc += (a.epi_fn == 1) ? t * t : expf(t);
+              for (int j = 0; j < 32; ++j) xo[ci][j] += __uint_as_float(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float t = xo[ci][j] + sbias[ch * 32 + j];
+              xo[ci][j] = t;
+              if (ch * 32 + j < a.cout) part += (a.epi_fn == 1) ? t * t : expf(t);
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);   // this warp's share of the accumulator is in registers
+        float* ex = exch + ((it & 1) * TC_EPI_WARPS + ew) * 32;    // double-buffered by tile parity
+        ex[lane] = part;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this lane quarter
+        const float acc = part + exch[((it & 1) * TC_EPI_WARPS + (ew ^ 4)) * 32 + lane];
         // one reciprocal per pixel, then multiplies (<= 1 ulp from the reference's per-element division)
-        row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
+        const float row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int ch = h + 2 * ci;
+          if (ch < nstore) {
+            if (lane == 0) bulk_wait_read<0>();     // this warp's previous store has read the staging tile
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float t = (a.epi_fn == 1) ? xo[ci][j] * row_scale : expf(xo[ci][j]) * row_scale;
+              xo[ci][j] = a.relu ? fmaxf(t, 0.f) : t;
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g)               // fp32 rows of 128 B, SWIZZLE_128B
+              *reinterpret_cast<float4*>(st + r * 128 + ((g ^ (r & 7)) << 4)) =
+                  make_float4(xo[ci][g * 4], xo[ci][g * 4 + 1], xo[ci][g * 4 + 2], xo[ci][g * 4 + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmO_hi, st, cbase + ch * 32, x0, y0);
+              bulk_commit();
+            }
+          }
+        }
+        if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
+        continue;
       }
       // fused ConvSta: each warp of a pair sums its own chunks; the pair's two partial sums meet in global memory
       // (atomicAdd on a zeroed map: two addends, so the result does not depend on their order)
@@ -451,13 +494,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int g = 0; g < 8; ++g) {
           const float4 b = *reinterpret_cast<const float4*>(sbias + cbase + c0 + g * 4);
           x[g * 4] += b.x; x[g * 4 + 1] += b.y; x[g * 4 + 2] += b.z; x[g * 4 + 3] += b.w;
-        }
-        if (a.epi_fn == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] *= row_scale;
-        } else if (a.epi_fn == 2) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = expf(x[j]) * row_scale;
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
@@ -766,7 +802,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w.size() == 768),
              SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
   // alignment slack, staging, bias, barriers
-  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
