@@ -390,7 +390,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (a.has_res == 2) tma_load_3d(st + 2048, &tmR_lo, wres, ch * 32, x0, y0);
     };
     uint32_t rphase = 0u;
-    uint32_t pseq = 0u;                           // plane stores issued by this warp (single-plane outputs: tile half = pseq & 1)
     if (a.has_res && lane == 0) issue_res(0, h);  // the residual of this warp's first chunk
     for (int it = 0; it < a.iters; ++it) {
       if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
@@ -470,10 +469,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // fused ConvSta: each warp of a pair sums its own chunks; the pair's two partial sums meet in global memory
       // (atomicAdd on a zeroed map: two addends, so the result does not depend on their order)
       float sta0 = h ? 0.f : a.sta_b[0], sta1 = h ? 0.f : a.sta_b[1], sta2 = h ? 0.f : a.sta_b[2];
-      // Without a residual the staging tile is pipelined at PLANE granularity: the hi plane of a chunk is sent as soon
-      // as it is staged, while the lo plane is still being computed, and each half of the tile is only waited for when
-      // it is written again (one bulk group may stay in flight).  Single-plane outputs alternate between the halves.
-      const bool pp = !a.has_res && a.out_mode != 2;
       for (int ch = h; ch < nstore; ch += 2) {
         const int c0 = ch * 32;
         // accumulator column of channel c0: diag-cat keeps [main 64 | correction 64] per 64-channel chunk
@@ -482,7 +477,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t v[32];
         float x[32];
         tmem_ld32(taddr + tcol, v);
-        if (!a.has_res && !pp) {                  // this warp's previous store must have finished reading the
+        if (!a.has_res) {                         // this warp's previous store must have finished reading the
           if (lane == 0) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
           __syncwarp();
         }
@@ -535,29 +530,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __align__(16) __half hi[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) hi[j] = __float2half_rn(x[j]);
-          // single-plane outputs: the two 2 KB halves of the tile take turns
-          uint8_t* st_hi = (pp && a.out_mode == 0 && (pseq & 1u)) ? st + 2048 : st;
-          if (pp) {                               // the store issued from this half two groups ago has read it
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(st_hi + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
-          if (pp) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { tma_store_3d(&tmO_hi, st_hi, cbase + c0, x0, y0); bulk_commit(); }
-            ++pseq;
-          }
+            *reinterpret_cast<uint4*>(st + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
           if (a.out_mode == 1) {
             __align__(16) __half lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) lo[j] = __float2half_rn(x[j] - __half2float(hi[j]));
-            if (pp) {                             // (the latest group is this chunk's hi plane; the previous lo store is done)
-              if (lane == 0) bulk_wait_read<1>();
-              __syncwarp();
-            }
 #pragma unroll
             for (int g = 0; g < 4; ++g)
               *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
@@ -577,11 +556,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
         }
-        if (pp && a.out_mode == 0) continue;      // (already sent)
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          if (!pp) tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
+          tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
           if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           bulk_commit();
           if (a.has_res) {                        // refill the tile with the residual of this warp's next chunk
