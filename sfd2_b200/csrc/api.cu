@@ -327,7 +327,6 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_FUSE_STA")) g_fuse_sta = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_DIAGCAT")) g_tc_diagcat = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_SPLIT1X1")) g_tc_split1x1 = atoi(e) != 0;
-  if (const char* e = getenv("SFD2_TC_1X1NS")) g_tc_1x1ns = atoi(e) != 0;
   const char* env_streams = getenv("SFD2_STREAMS");
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;

@@ -52,12 +52,6 @@ struct TcConvArgs {
                    // main + correction accumulators of BOTH TMEM buffers fit (N=256: 2 x (128 + 128) x 2 = 512 columns)
                    // and the epilogue of one pass overlaps the MMAs of the next; the small halo A tile is re-fetched
   int tap_rows;    // rows per tap in the packed weights (= the layer's padded Cout)
-  int stg_bytes;   // staging bytes per epilogue warp: one 4 KB tile, or three (stg2)
-  int stg2;        // 1x1 layers as two channel passes of 128: the weight stage shrinks from 64 to 32 KB and the freed
-                   // shared memory gives every epilogue warp three staging tiles - without a residual the output tile is
-                   // double-buffered; with one, the residual lands in its own two tiles and is requested TWO own chunks
-                   // ahead, right after the previous one has been read, instead of after the output store has drained
-                   // (ncu: the epilogue warps of these layers spent most samples waiting for the residual and the drain)
   int ncat;        // per-tap ring, exact mode, N <= 64 with a correction accumulator: see the MMA issuer
   int cat;         // grouped layers, exact mode ("diag-cat"): the weight slab of a (tap, 64-channel chunk) is the
                    // N-concatenation [w_hi | w_lo] (128 rows), so ONE N=128 MMA per K step yields a_hi*w_hi (columns
@@ -105,7 +99,7 @@ struct TcStaW { float w[256 * 3]; };
 constexpr int TC_HALO_W = 10, TC_HALO_H = 18;
 constexpr int TC_HALO_BYTES = TC_HALO_W * TC_HALO_H * 128;           // 23040
 constexpr int TC_HALO_SLOT = 23 * 1024;                                // per plane, 1024-aligned
-constexpr int TC_STG_TILE = 4096;               // one (32 px x 128 B) staging tile
+constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * 4096;   // one (32 px x 128 B) staging tile per epilogue warp
 constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-column over-read)
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
 constexpr int TC_EXCH_BYTES = 2 * TC_EPI_WARPS * 32 * 4;   // head epilogues: partial-sum exchange between paired warps
@@ -121,17 +115,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + (size_t)a.ring_bytes;                        // 1024-aligned
-  const int stg_total = TC_EPI_WARPS * a.stg_bytes;
-  float* sbias = reinterpret_cast<float*>(staging + stg_total);
-  uint64_t* full = reinterpret_cast<uint64_t*>(staging + stg_total + TC_BIAS_BYTES);
+  float* sbias = reinterpret_cast<float*>(staging + TC_STAGING_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
-  uint64_t* resbar = tempty + 2;                                         // [8 epilogue warps][2 residual tiles]
-  uint64_t* fullA = resbar + 2 * TC_EPI_WARPS;                           // halo mode: A-tile ring
+  uint64_t* resbar = tempty + 2;                                         // [8 epilogue warps]
+  uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
-  float* exch = reinterpret_cast<float*>(staging + stg_total + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
+  float* exch = reinterpret_cast<float*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -143,7 +136,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
     for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
-    for (int i = 0; i < 2 * TC_EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
+    for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -376,8 +369,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
-    uint8_t* st = staging + ew * a.stg_bytes;
-    uint64_t* wres = resbar + 2 * ew;
+    uint8_t* st = staging + ew * 4096;
+    uint64_t* wres = resbar + ew;
     int buf = 0;
     uint32_t bphase = 0;
     const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
@@ -397,27 +390,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (a.has_res == 2) tma_load_3d(st + 2048, &tmR_lo, wres, ch * 32, x0, y0);
     };
     uint32_t rphase = 0u;
-    // stg2: own chunks are numbered n = 0, 1, 2, ... over (tile, channel pass, chunk); residual n lives in tile 1 + (n & 1)
-    const int opp = (nstore > h) ? (nstore - h + 1) / 2 : 0;   // own chunks per channel pass
-    uint32_t oseq = 0u, rseq = 0u;
-    auto issue_res2 = [&](uint32_t n) {           // lane 0 only
-      if (opp == 0) return;
-      const int per_tile = opp * a.nsplit;
-      const int it_n = (int)n / per_tile, rem = (int)n - it_n * per_tile;
-      const int nh_n = rem / opp, ch_n = h + 2 * (rem - nh_n * opp);
-      if (it_n >= a.iters || cl_first + it_n * (int)gridDim.x >= a.num_tiles) return;
-      int x0, y0;
-      tile_xy(it_n, x0, y0);
-      uint8_t* rb = st + TC_STG_TILE * (1 + (n & 1u));
-      uint64_t* bar = wres + (n & 1u);
-      mbar_expect_tx(bar, a.has_res == 2 ? 4096u : 2048u);
-      tma_load_3d(rb, &tmR_hi, bar, nh_n * a.n_mma + ch_n * 32, x0, y0);
-      if (a.has_res == 2) tma_load_3d(rb + 2048, &tmR_lo, bar, nh_n * a.n_mma + ch_n * 32, x0, y0);
-    };
-    if (a.has_res && lane == 0) {
-      if (a.stg2) { issue_res2(0u); issue_res2(1u); }
-      else issue_res(0, h);                       // the residual of this warp's first chunk
-    }
+    if (a.has_res && lane == 0) issue_res(0, h);  // the residual of this warp's first chunk
     for (int it = 0; it < a.iters; ++it) {
       if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
       int x0, y0;
@@ -504,12 +477,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint32_t v[32];
         float x[32];
         tmem_ld32(taddr + tcol, v);
-        // output tile: double-buffered when three tiles are available and none is needed for a residual
-        uint8_t* ot = (a.stg2 && !a.has_res && (oseq & 1u)) ? st + TC_STG_TILE : st;
-        if (!a.has_res || a.stg2) {               // the store that last used this tile must have finished reading it
-          if (lane == 0) {                        // (legacy residual path: issue_res waited already)
-            if (a.stg2 && !a.has_res) bulk_wait_read<1>(); else bulk_wait_read<0>();
-          }
+        if (!a.has_res) {                         // this warp's previous store must have finished reading the
+          if (lane == 0) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
           __syncwarp();
         }
         tmem_ld_wait();
@@ -528,12 +497,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
-          const uint8_t* rt = a.stg2 ? st + TC_STG_TILE * (1 + (rseq & 1u)) : st;
-          if (a.stg2) mbar_wait(wres + (rseq & 1u), (rseq >> 1) & 1u);
-          else { mbar_wait(wres, rphase); rphase ^= 1u; }
+          mbar_wait(wres, rphase);
+          rphase ^= 1u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const uint4 h = *reinterpret_cast<const uint4*>(rt + r * 64 + ((g ^ sw64) << 4));
+            const uint4 h = *reinterpret_cast<const uint4*>(st + r * 64 + ((g ^ sw64) << 4));
             const __half* hh = reinterpret_cast<const __half*>(&h);
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(hh[j]);
@@ -541,17 +509,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (a.has_res == 2) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              const uint4 l = *reinterpret_cast<const uint4*>(rt + 2048 + r * 64 + ((g ^ sw64) << 4));
+              const uint4 l = *reinterpret_cast<const uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4));
               const __half* ll = reinterpret_cast<const __half*>(&l);
 #pragma unroll
               for (int j = 0; j < 8; ++j) x[g * 8 + j] += __half2float(ll[j]);
             }
           }
           __syncwarp();                           // everyone has read the residual before it is overwritten
-          if (a.stg2) {                           // its tile is free again: request the residual two own chunks ahead
-            if (lane == 0) issue_res2(rseq + 2u);
-            ++rseq;
-          }
         }
         if (a.relu) {
 #pragma unroll
@@ -560,7 +524,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (a.out_mode == 2) {                    // fp32 rows of 128 B, SWIZZLE_128B
 #pragma unroll
           for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(ot + r * 128 + ((g ^ (r & 7)) << 4)) =
+            *reinterpret_cast<float4*>(st + r * 128 + ((g ^ (r & 7)) << 4)) =
                 make_float4(x[g * 4], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
         } else {
           __align__(16) __half hi[32];
@@ -568,14 +532,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int j = 0; j < 32; ++j) hi[j] = __float2half_rn(x[j]);
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<uint4*>(ot + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
+            *reinterpret_cast<uint4*>(st + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
           if (a.out_mode == 1) {
             __align__(16) __half lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) lo[j] = __float2half_rn(x[j] - __half2float(hi[j]));
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-              *reinterpret_cast<uint4*>(ot + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
+              *reinterpret_cast<uint4*>(st + 2048 + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(lo)[g];
           }
           if (a.sta_out) {
             // the three ConvSta dot products on x (fp32; hi + lo carries 22 of its 24 bits, and the 3-class argmax
@@ -594,12 +558,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
-        ++oseq;
         if (lane == 0) {
-          tma_store_3d(&tmO_hi, ot, cbase + c0, x0, y0);
-          if (a.out_mode == 1) tma_store_3d(&tmO_lo, ot + 2048, cbase + c0, x0, y0);
+          tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
+          if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           bulk_commit();
-          if (a.has_res && !a.stg2) {             // refill the tile with the residual of this warp's next chunk
+          if (a.has_res) {                        // refill the tile with the residual of this warp's next chunk
             bulk_wait_read<0>();
             if (ch + 2 < nstore) issue_res(it, ch + 2); else issue_res(it + 1, h);
           }
@@ -776,7 +739,6 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 }
 
 int g_tc_nsplit = 1;      // SFD2_TC_NSPLIT=0: keep wide layers in one channel pass (single-buffered accumulators)
-int g_tc_1x1ns = 1;       // SFD2_TC_1X1NS=0: ResBlock 1x1 layers as one 256-channel pass with one staging tile per warp
 int g_tc_split1x1 = 0;    // SFD2_TC_SPLIT1X1=1: 1x1 layers with split A / B rings (measured: c1 63 -> 68 us)
 int g_tc_diagcat = 1;     // SFD2_TC_DIAGCAT=0: grouped layers in exact mode as three N=64 MMAs per K step (no [w_hi | w_lo] slabs)
 int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for the stride-1 3x3 layers
@@ -790,10 +752,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const bool diag = (L.groups == 32);
   TcConvArgs a{};
   a.Ho = out.H; a.Wo = out.W;
-  // 1x1 256 -> 256 layers (ResBlock c1 / c3) without a fused ConvSta: two channel passes + three staging tiles per warp
-  const bool stg2 = g_tc_1x1ns && L.k == 1 && L.stride == 1 && !diag && L.cout == 256 && L.cout_tc == 256 && !out_f32_map &&
-                    !(sta && sta_out);
-  const bool split1 = (g_tc_split1x1 || stg2) && L.k == 1 && L.stride == 1 && !diag;
+  const bool split1 = g_tc_split1x1 && L.k == 1 && L.stride == 1 && !diag;
   a.halo = ((g_tc_halo && L.k == 3 && L.stride == 1) || split1) ? 1 : 0;
   a.hw = split1 ? 8 : TC_HALO_W;
   a.hoff = split1 ? 0 : 1;
@@ -817,13 +776,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     a.n_mma = L.cout_tc / 2;
     a.acc_cols = a.n_mma;
   }
-  if (stg2) {
-    a.nsplit = 2;
-    a.n_mma = L.cout_tc / 2;
-    a.acc_cols = a.n_mma;
-  }
-  a.stg2 = stg2 ? 1 : 0;
-  a.stg_bytes = stg2 ? 3 * TC_STG_TILE : TC_STG_TILE;
   // (block-diagonal grouped layers add mostly exact zeros, so their single accumulator is already accurate)
   a.corr = (split == 3 && L.k == 3 && !diag) ? 1 : 0;
   a.buf_stride = a.acc_cols * (1 + a.corr);
@@ -850,7 +802,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w.size() == 768),
              SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
   // alignment slack, staging, bias, barriers
-  const int smem_fixed = 1024 + TC_EPI_WARPS * a.stg_bytes + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
+  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
@@ -859,7 +811,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   if (a.halo) {
     a.a_slot_bytes = (split == 3 ? 2 : 1) * a.a_plane_off;
     a.a_slots = 2;
-    if (split1 && !stg2)   // a whole tile of A in flight if two weight slabs still fit beside it
+    if (split1)   // a whole tile of A in flight if two weight slabs still fit beside it
       while (a.a_slots < 4 && a.a_slots < a.kchunks && (a.a_slots + 1) * a.a_slot_bytes + 2 * a.b_bytes <= smem_max - smem_fixed) ++a.a_slots;
     int bs = (smem_max - smem_fixed - a.a_slots * a.a_slot_bytes) / a.b_bytes;
     const int max_bs = getenv("SFD2_TC_BSTAGES") ? atoi(getenv("SFD2_TC_BSTAGES")) : TC_MAX_STAGES;

@@ -5,5 +5,5 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
 tail -3 gpurun_out/${tag}_pytest.log
-timeout 900 python tools/ab_bench.py "warm:mixed:SFD2_TC_1X1NS=1" "base:mixed:SFD2_TC_1X1NS=1" "off:mixed:SFD2_TC_1X1NS=0" "base:exact:SFD2_TC_1X1NS=1" "base:fast:SFD2_TC_1X1NS=1" "off:fast:SFD2_TC_1X1NS=0" > gpurun_out/${tag}_ab.log 2>&1
+timeout 900 python tools/ab_bench.py "warm:mixed:" "base:mixed:" "base:exact:" "base:fast:" > gpurun_out/${tag}_ab.log 2>&1
 cat gpurun_out/${tag}_ab.log
