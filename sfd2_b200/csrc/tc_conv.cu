@@ -2,8 +2,9 @@
 //
 //   out[pixel][co] = sum_{tap, ci} act[pixel @ tap][ci] * w[tap][co][ci]   (+ bias, ReLU, residual)
 //
-// * M tile  = 128 output pixels = 8 rows x 16 columns of the output map (one TMEM lane each);
-// * N       = all output channels of the layer (64 / 80 / 128 / 256), one fp32 accumulator of
+// * M tile  = 128 output pixels = 8 rows x 16 columns of the output map (one TMEM lane each); 16 rows x 8 columns
+//             for the stride-1 3x3 layers, whose nine taps read ONE halo box per chunk (TcConvArgs::halo);
+// * N       = all output channels of the layer (64 / 80 / 128 / 192 / 256), one fp32 accumulator of
 //             N columns in TMEM, double-buffered so the epilogue of tile i overlaps the MMAs of i+1;
 // * K loop  = (tap, 64-channel chunk).  For each step TMA brings
 //               A: the box {64 ch, 16 px, 8 rows} of the NHWC activation at the tap's offset - it
@@ -12,10 +13,12 @@
 //                  Stride-2 layers view the (even-padded) activation as [H/2][2][W/2][2][C] and
 //                  pick the tap's parity plane with a 5-D box, so no im2col buffer ever exists;
 //               B: the tap's [N][64] weight slab (K-major, pre-packed per layer).
-// * precision: split==1 -> one fp16 MMA per step; split==3 -> a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into
-//   the same fp32 accumulator (activations and weights carried as fp16 hi/lo planes, ~22 bits).
+// * precision: split==1 -> one fp16 MMA per step; split==3 -> a_hi*w_hi + a_hi*w_lo + a_lo*w_hi
+//   (activations and weights carried as fp16 hi/lo planes, ~22 bits); the two correction products of the 3x3
+//   layers accumulate in their own TMEM columns (TcConvArgs::corr) and are added in the epilogue.
 // * grouped 3x3 (groups=32, 8 ch/group): "diag" mode - for each 64-channel chunk the weight slab is
-//   the 64x64 block-diagonal piece, one N=64 MMA per chunk into its own 64 accumulator columns.
+//   the 64x64 block-diagonal piece, one N=64 MMA per chunk into its own 64 accumulator columns; in exact
+//   mode the slab is [w_hi | w_lo] and a_hi meets both halves in one N=128 MMA (TcConvArgs::cat).
 //
 // * weight multicast: CTAs run as clusters of 2 neighbouring tiles; each CTA fetches HALF of every
 //   weight slab and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM traffic of
@@ -56,9 +59,9 @@ struct TcConvArgs {
   int cat;         // grouped layers, exact mode ("diag-cat"): the weight slab of a (tap, 64-channel chunk) is the
                    // N-concatenation [w_hi | w_lo] (128 rows), so ONE N=128 MMA per K step yields a_hi*w_hi (columns
                    // 0..63 of the chunk's 128 accumulator columns) and a_hi*w_lo (columns 64..127); a_lo*w_hi is an
-                   // N=64 MMA on the slab's first 64 rows into columns 64..127.  N=64 MMAs are bound by the 4 KB
-                   // A-operand read (32 cycles for 16 cycles of math), so two A reads per K step instead of three cut
-                   // the layer's tensor time by a third.  The 256 output channels run as two channel passes of two
+                   // N=64 MMA on the slab's first 64 rows into columns 64..127.  An SMEM-operand MMA at M=128 costs
+                   // ~64-73 cycles for every N <= 128 (measured), so two MMAs per K step instead of three cut the
+                   // layer's tensor time by a third.  The 256 output channels run as two channel passes of two
                    // chunks (2 x 128 columns per buffer, double-buffered); chunks are independent, nothing is re-read.
   int corr;        // 1: the hi*lo / lo*hi passes accumulate in their own TMEM region (added in the epilogue)
   int nbuf;        // accumulator buffers (2 = epilogue overlaps the next tile's MMAs)
