@@ -38,6 +38,7 @@ extern "C" {
 
 #define SFD2_ABI_VERSION 1
 #define SFD2_DESC_DIM 128
+#define SFD2_MATCH_PLAIN_CODES 0x100
 
 typedef struct sfd2_ctx sfd2_ctx;
 
@@ -83,8 +84,10 @@ typedef struct {
   float distance_threshold; /* :30 ; <= 0 means None                                     */
   float ratio_threshold;    /* :29 ; <= 0 means None                                     */
   int32_t precision;        /* sfd2_precision (FP32 = CUDA cores, TC_* = tcgen05)        */
-  int32_t ratio_mode;       /* 0: hloc find_nn formula (nearest_neighbor.py:10-11);
-                               1: it_loc mutual_nn_ratio_matcher formula (it_loc/matcher.py:172-174) */
+  int32_t ratio_mode;       /* bits 0..7: 0 = hloc find_nn formula (nearest_neighbor.py:10-11),
+                               1 = it_loc mutual_nn_ratio_matcher formula (it_loc/matcher.py:172-174);
+                               bit 8 (SFD2_MATCH_PLAIN_CODES): report every unmatched row as -1
+                               (no -2 for "rejected only by the mutual check") */
 } sfd2_match_params;
 
 SFD2_API int sfd2_abi_version(void);

@@ -540,7 +540,8 @@ static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int 
     if (rc) return rc;
   }
   return launch_match_finish(c->row_key, c->col_key, n0, n1, p->do_mutual_check, p->distance_threshold,
-                             p->ratio_threshold, p->ratio_mode == 1 ? 2 : 1, c->row2, c->col2, matches0, sim0, st);
+                             p->ratio_threshold, ((p->ratio_mode & 0xFF) == 1 ? 2 : 1) | (p->ratio_mode & SFD2_MATCH_PLAIN_CODES),
+                             c->row2, c->col2, matches0, sim0, st);
 }
 
 SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,

@@ -228,6 +228,8 @@ __global__ void match_finish_kernel(const unsigned long long* __restrict__ row_k
   const int j = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
   const float s = unord_f32((unsigned)(k >> 32));
   bool ok = true;
+  const bool plain = (ratio_mode & SFD2_MATCH_PLAIN_CODES) != 0;   // every unmatched row reads -1
+  ratio_mode &= 0xFF;
   if (ratio_th > 0.f) ok = ratio_ok(s, row2[i], ratio_th, ratio_mode);
   if (ok && dist_th > 0.f) ok = (2.f * (1.f - s)) <= dist_th * dist_th;      // nearest_neighbor.py:8,12-13
   const bool row_ok = ok;   // find_nn's own mask for this row (decides whether hloc keeps its score)
@@ -238,7 +240,7 @@ __global__ void match_finish_kernel(const unsigned long long* __restrict__ row_k
     if (ok && ratio_th > 0.f) ok = ratio_ok(unord_f32((unsigned)(kc >> 32)), col2[j], ratio_th, ratio_mode);
     if (ok && dist_th > 0.f) ok = (2.f * (1.f - unord_f32((unsigned)(kc >> 32)))) <= dist_th * dist_th;
   }
-  matches0[i] = ok ? j : (row_ok ? -2 : -1);   // -1: rejected by the row's own tests, -2: by the mutual check
+  matches0[i] = ok ? j : ((row_ok && !plain) ? -2 : -1);   // -1: rejected by the row's own tests, -2: by the mutual check
   sim0[i] = s;
 }
 

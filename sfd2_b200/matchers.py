@@ -49,12 +49,11 @@ def match_dev(d0: torch.Tensor, d1: torch.Tensor, mutual=True, dist_th=None, rat
     s0 = torch.empty((n0,), dtype=torch.float32, device=dev)
     if n0 == 0:
         return m0, s0
-    p = _mparams(mutual, dist_th, ratio_th, precision, ratio_mode)
+    # raw=False: the finish kernel itself reports every unmatched row as -1 (SFD2_MATCH_PLAIN_CODES), no clamp launch
+    p = _mparams(mutual, dist_th, ratio_th, precision, int(ratio_mode) | (0 if raw else 0x100))
     st = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(_lib.lib().sfd2_match_dev(_ctx(dev.index or 0).handle, d0.data_ptr(), n0, d1.data_ptr(), n1, d,
                                          C.byref(p), m0.data_ptr(), s0.data_ptr(), st), "sfd2_match_dev")
-    if not raw:
-        m0.clamp_(min=-1)
     return m0, s0
 
 
