@@ -129,7 +129,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
   float* exch = reinterpret_cast<float*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The warp index goes through a shuffle so that the compiler KNOWS it is warp-uniform: the producer and MMA-issuer
+  // loops below are run by the whole warp (ring indices, phases, descriptors stay in uniform registers) and only the
+  // TMA / MMA / commit instructions themselves sit behind elect.sync.  With the loops inside a single elected lane
+  // every descriptor went through vector registers + R2UR and the issue loop took ~300 cycles per tap - as long as
+  // the four single-pass MMAs it issues (ncu source view: 80 dependent instructions per tap).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi);
     prefetch_tmap(&tmB_hi);
@@ -157,8 +162,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    const bool leader = elect_one();
-    if (leader && a.halo) {
+    if (a.halo) {
       const int planes = (a.split == 3) ? 2 : 1;
       uint8_t* bring = smem + (size_t)a.a_slots * a.a_slot_bytes;
       int sa = 0, sb = 0;
@@ -171,9 +175,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
-          mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
-          tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
-          if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+          if (elect_one()) {
+            mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
+            tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+            if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+          }
+          __syncwarp();
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
           for (int tap = 0; tap < a.taps; ++tap) {
             const int brow = a.cat ? (tap * 4 + kc) * 128 : (a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
@@ -181,20 +188,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int pl = 0; pl < (a.cat ? 1 : planes); ++pl) {
               mbar_wait(&empty[sb], phb ^ 1);
               uint8_t* bs = bring + (size_t)sb * a.b_bytes;
-              mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
               const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
-              if (a.mc > 1) {
-                const int ro = (int)crank * (a.n_mma / 2);
-                tma_load_2d_mc(bs + ro * 128, tb, &full[sb], bcol, brow + ro, cmask);
-              } else {
-                tma_load_2d(bs, tb, &full[sb], bcol, brow);
+              if (elect_one()) {
+                mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
+                if (a.mc > 1) {
+                  const int ro = (int)crank * (a.n_mma / 2);
+                  tma_load_2d_mc(bs + ro * 128, tb, &full[sb], bcol, brow + ro, cmask);
+                } else {
+                  tma_load_2d(bs, tb, &full[sb], bcol, brow);
+                }
               }
+              __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
           }
         }
       }
-    } else if (leader && !a.halo) {
+    } else {
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < a.iters; ++it) {
@@ -207,8 +217,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
             uint8_t* sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
-            mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
             const int c0 = kc * 64;
+            if (elect_one()) {
+            mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
             if (a.stride == 1) {
               const int cx = x0 + kx - 1, cy = y0 + ky - 1;
               tma_load_3d(sa, &tmA_hi, &full[stage], c0, cx, cy);
@@ -230,6 +241,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               tma_load_2d(sb, &tmB_hi, &full[stage], bcol, brow);
               if (a.split == 3) tma_load_2d(sb + a.b_bytes, &tmB_lo, &full[stage], bcol, brow);
             }
+            }
+            __syncwarp();
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -237,8 +250,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const bool leader = elect_one();
-    if (leader && a.halo) {
+    // (whole warp runs the loops; tcgen05.mma / commit come from the one lane elect.sync picks - always the same)
+    if (a.halo) {
       const uint32_t idesc = make_idesc_f16(128, a.cat ? 64 : a.n_mma);
       const uint32_t idesc_cat = make_idesc_f16(128, 128);
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
@@ -266,13 +279,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               mbar_wait(&full[sb], phb);
               tc_fence_after();
               const uint64_t dbc = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(dbc, k), idesc_cat, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(dbc, k), idesc_cat, (first && k == 0) ? 0u : 1u);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(dbc, k), idesc, 1u);
-              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(dbc, k), idesc, 1u);
+                if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+              }
+              __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
               continue;
             }
@@ -280,35 +296,43 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             mbar_wait(&full[sb], phb);
             tc_fence_after();
             uint64_t db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (first && k == 0) ? 0u : 1u);
-            if (a.split == 3) {
+            if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, (a.corr && first && k == 0) ? 0u : 1u);
+                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (first && k == 0) ? 0u : 1u);
+              if (a.split == 3) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, (a.corr && first && k == 0) ? 0u : 1u);
+              }
+              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
             }
-            if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+            __syncwarp();
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             if (a.split == 3) {                 // weight slab, lo plane: a_hi * w_lo
               mbar_wait(&full[sb], phb);
               tc_fence_after();
               db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(ccol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
-              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(ccol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
+                if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+              }
+              __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
           }
-          umma_commit(&emptyA[sa]);             // halo tile free once all nine taps have read it
+          if (elect_one()) umma_commit(&emptyA[sa]);   // halo tile free once all nine taps have read it
+          __syncwarp();
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
         }
-        umma_commit(&tfull[buf]);
+        if (elect_one()) umma_commit(&tfull[buf]);
+        __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
         }
       }
-    } else if (leader && !a.halo) {
+    } else {
       const uint32_t idesc = make_idesc_f16(128, a.n_mma);
       const uint32_t idesc_ncat = make_idesc_f16(128, 2 * a.n_mma);
       int stage = 0;
@@ -328,6 +352,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + a.b_bytes);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? (kb % a.kchunks) * 64 : 0));
           const bool first = a.diag ? (kb < a.kchunks) : (kb == 0);
+          if (elect_one()) {
           if (a.ncat) {
             // narrow layers (N <= 64): an SMEM-operand MMA at M = 128 costs ~64 cycles whatever N <= 128 is (measured:
             // 67 cycles at N = 64), so a_hi x w_hi and a_hi x w_lo go out as ONE MMA over the adjacent [w_hi | w_lo]
@@ -355,9 +380,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           // smem slot free once these MMAs have read it (in both CTAs when the slab is multicast)
           if (a.mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
+          }
+          __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[buf]);               // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull[buf]);   // accumulator complete -> epilogue
+        __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
     }
