@@ -48,13 +48,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// whole-warp wait with ONE polling lane (the lane elect.sync always picks); the rest of the warp parks at the
-// warp barrier.  32 lanes spinning on try_wait cost measurable power on a power-capped part.
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if (elect_one()) mbar_wait(bar, parity);
-  __syncwarp();
-}
-
 // ---- TMA tiled loads (global -> shared, completion on an mbarrier) -------------------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");

@@ -173,7 +173,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
         for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
-          mbar_wait_warp(&emptyA[sa], pha ^ 1);
+          mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
           if (elect_one()) {
             mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
@@ -186,7 +186,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int brow = a.cat ? (tap * 4 + kc) * 128 : (a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
             const int bcol = a.diag ? 0 : kc * 64;
             for (int pl = 0; pl < (a.cat ? 1 : planes); ++pl) {
-              mbar_wait_warp(&empty[sb], phb ^ 1);
+              mbar_wait(&empty[sb], phb ^ 1);
               uint8_t* bs = bring + (size_t)sb * a.b_bytes;
               const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
               if (elect_one()) {
@@ -214,7 +214,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < a.kchunks; ++kc) {
-            mbar_wait_warp(&empty[stage], phase ^ 1);
+            mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
             uint8_t* sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
             const int c0 = kc * 64;
@@ -260,10 +260,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int it = 0; it < a.iters; ++it) {
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
         for (int nh = 0; nh < a.nsplit; ++nh) {
-        mbar_wait_warp(&tempty[buf], bphase ^ 1);
+        mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
-          mbar_wait_warp(&fullA[sa], pha);
+          mbar_wait(&fullA[sa], pha);
           tc_fence_after();
           const uint32_t abase = smem_u32(smem + (size_t)sa * a.a_slot_bytes);
           const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.cat ? (kc & 1) * 128 : (a.diag ? kc * 64 : 0)));
@@ -276,7 +276,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (a.cat) {
               // one [w_hi | w_lo] slab: a_hi x both (N = 128: main | correction), then a_lo x w_hi (N = 64) into the
               // correction columns - which the N = 128 MMA of this tap has already initialised when tap == 0
-              mbar_wait_warp(&full[sb], phb);
+              mbar_wait(&full[sb], phb);
               tc_fence_after();
               const uint64_t dbc = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
               if (elect_one()) {
@@ -293,7 +293,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               continue;
             }
             // weight slab, hi plane: main product, then (exact mode) a_lo * w_hi into the correction accumulator
-            mbar_wait_warp(&full[sb], phb);
+            mbar_wait(&full[sb], phb);
             tc_fence_after();
             uint64_t db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
             if (elect_one()) {
@@ -310,7 +310,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             if (a.split == 3) {                 // weight slab, lo plane: a_hi * w_lo
-              mbar_wait_warp(&full[sb], phb);
+              mbar_wait(&full[sb], phb);
               tc_fence_after();
               db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
               if (elect_one()) {
@@ -341,10 +341,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
-        mbar_wait_warp(&tempty[buf], bphase ^ 1);
+        mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait_warp(&full[stage], phase);
+          mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
           const uint32_t sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
@@ -428,7 +428,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       tile_xy(it, x0, y0);
       for (int nh = 0; nh < a.nsplit; ++nh) {
       const int cbase = nh * a.n_mma;             // first output channel of this pass (0 unless nsplit > 1)
-      mbar_wait_warp(&tfull[buf], bphase);
+      mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
       if (a.epi_fn) {
@@ -528,7 +528,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
-          mbar_wait_warp(wres, rphase);
+          mbar_wait(wres, rphase);
           rphase ^= 1u;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {

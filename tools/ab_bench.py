@@ -17,9 +17,6 @@ sys.path.insert(0, REPO)
 
 def main():
     import torch
-    if os.environ.get("AB_LIB"):          # time another build of the library (e.g. the previous commit's) on the same box
-        from sfd2_b200 import _lib
-        _lib.LIB_PATH = os.path.abspath(os.environ["AB_LIB"])
     from sfd2_b200 import Extractor
     from sfd2_b200.synth import synth_image_u8
     H, W, B = 1200, 1600, 8

@@ -1,10 +1,9 @@
 #!/bin/bash
-# same-box A/B of two builds of the library: tools/_ab/libsfd2_b200_old.so (previous commit) against the in-tree one
+# A/B run of the library toggles (see tools/ab_bench.py); results in gpurun_out/<tag>_ab.log
 tag=${1:-ab}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; tail -2 gpurun_out/${tag}_pytest.log
-for rep in 1; do
-  AB_LIB=tools/_ab/libsfd2_b200_old.so timeout 300 python tools/ab_bench.py "old:mixed:" "old:exact:" "old:fast:" >> gpurun_out/${tag}_ab.log 2>&1
-  timeout 300 python tools/ab_bench.py "new:mixed:" "new:exact:" "new:fast:" >> gpurun_out/${tag}_ab.log 2>&1
-done
-grep -A1 "^##" gpurun_out/${tag}_ab.log
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
+tail -3 gpurun_out/${tag}_pytest.log
+timeout 400 python tools/ab_bench.py "warm:mixed:" "base:mixed:" "base:exact:" "base:fast:" > gpurun_out/${tag}_ab.log 2>&1
+cat gpurun_out/${tag}_ab.log
