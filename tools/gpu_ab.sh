@@ -1,9 +1,8 @@
 #!/bin/bash
-# A/B run of the library toggles (see tools/ab_bench.py); results in gpurun_out/<tag>_ab.log
+# same-box A/B of two builds of the library: tools/_ab/libsfd2_b200_old.so (previous commit) against the in-tree one
 tag=${1:-ab}
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1
-echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
-tail -3 gpurun_out/${tag}_pytest.log
-timeout 400 python tools/ab_bench.py "warm:mixed:" "base:mixed:" "base:exact:" "base:fast:" > gpurun_out/${tag}_ab.log 2>&1
-cat gpurun_out/${tag}_ab.log
+timeout 150 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2>&1; tail -2 gpurun_out/${tag}_pytest.log
+AB_LIB=tools/_ab/libsfd2_b200_old.so timeout 100 python tools/ab_bench.py "old:mixed:" "old:exact:" >> gpurun_out/${tag}_ab.log 2>&1
+timeout 100 python tools/ab_bench.py "new:mixed:" "new:exact:" "new:fast:" >> gpurun_out/${tag}_ab.log 2>&1
+grep -A1 "^##" gpurun_out/${tag}_ab.log
