@@ -168,6 +168,9 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* ctx, const float* x_host, int h, int w, i
 
 /* Hardware probe used while designing the conv kernel's operand staging (tools/umma_probe.py). */
 SFD2_API int sfd2_debug_umma_probe(int pitch, int ky, int kx, int use_base_offset, int pattern, float* out_host);
+/* Hardware probe: cycles per CTA for `iters` back-to-back SMEM-operand tcgen05.mma of shape M128 x n x K
+ * (kind 0: f16, K = 16; kind 1: f8f6f4 / E4M3, K = 32) on `grid` CTAs (tools/mma_rate_probe.py). */
+SFD2_API int sfd2_debug_mma_rate(int n, int kind, int iters, int grid, unsigned long long* cycles_host);
 
 #ifdef __cplusplus
 }

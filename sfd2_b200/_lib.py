@@ -52,6 +52,7 @@ _PROTOS = {
     "sfd2_nms_select_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(ExtractParams),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sfd2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sfd2_debug_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -114,3 +114,69 @@ extern "C" SFD2_API int sfd2_debug_umma_probe(int pitch, int ky, int kx, int use
   cudaFree(dX); cudaFree(dB); cudaFree(dO);
   return SFD2_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Second probe: issue rate of SMEM-operand tcgen05.mma at M = 128 as a function of N and of the operand kind
+// (tools/mma_rate_probe.py).  One thread per CTA issues `iters` back-to-back MMAs on zeroed operands (no loads, no
+// epilogue) and the CTA reports clock64() cycles from the first issue to the completion of the last one.
+namespace sfd2 {
+using namespace ptx;
+
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 1)
+mma_rate_probe_kernel(int n, int kind, int iters, unsigned long long* __restrict__ cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                 // 128 rows x 128 B
+  uint8_t* sB = smem + 16384;         // up to 256 rows x 128 B
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
+  for (int i = threadIdx.x; i < (16384 + 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(done, 1); fence_barrier_init(); }
+  if ((threadIdx.x >> 5) == 0) tmem_alloc(slot, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint64_t da = make_desc_sw128(smem_u32(sA)), db = make_desc_sw128(smem_u32(sB));
+    const uint32_t idesc = make_idesc_f16(128, n);      // format code 0 = F16 (kind::f16) / E4M3 (kind::f8f6f4)
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (kind == 0) umma_f16(tmem, desc_advance_k(da, i & 3), desc_advance_k(db, i & 3), idesc, 1u);
+      else umma_f8(tmem, desc_advance_k(da, i & 3), desc_advance_k(db, i & 3), idesc, 1u);
+    }
+    umma_commit(done);
+    mbar_wait(done, 0);
+    cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace sfd2
+
+// cycles_host[grid]: cycles each CTA needed for `iters` MMAs of shape M128 x N x (K16 fp16 | K32 fp8)
+extern "C" SFD2_API int sfd2_debug_mma_rate(int n, int kind, int iters, int grid, unsigned long long* cycles_host) {
+  SFD2_CHECK(n >= 16 && n <= 256 && n % 16 == 0 && (kind == 0 || kind == 1) && iters > 0 && grid > 0 && grid <= 1024,
+             SFD2_ERR_ARG, "sfd2_debug_mma_rate: bad argument");
+  unsigned long long* d = nullptr;
+  SFD2_CUDA(cudaMalloc(&d, (size_t)grid * 8));
+  const int smem = 16384 + 32768 + 256 + 1024;
+  SFD2_CUDA(cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_probe_kernel<<<grid, 128, smem>>>(n, kind, iters, d);
+  SFD2_CUDA(cudaGetLastError());
+  SFD2_CUDA(cudaDeviceSynchronize());
+  SFD2_CUDA(cudaMemcpy(cycles_host, d, (size_t)grid * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return SFD2_OK;
+}
