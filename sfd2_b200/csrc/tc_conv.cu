@@ -60,7 +60,7 @@ struct TcConvArgs {
                    // N-concatenation [w_hi | w_lo] (128 rows), so ONE N=128 MMA per K step yields a_hi*w_hi (columns
                    // 0..63 of the chunk's 128 accumulator columns) and a_hi*w_lo (columns 64..127); a_lo*w_hi is an
                    // N=64 MMA on the slab's first 64 rows into columns 64..127.  An SMEM-operand MMA at M=128 costs
-                   // ~64-73 cycles for every N <= 128 (measured), so two MMAs per K step instead of three cut the
+                   // >= 53 cycles whatever N is, 64 at N = 128 (tools/mma_rate_probe.py), so two MMAs per K step instead of three cut the
                    // layer's tensor time by a third.  The 256 output channels run as two channel passes of two
                    // chunks (2 x 128 columns per buffer, double-buffered); chunks are independent, nothing is re-read.
   int corr;        // 1: the hi*lo / lo*hi passes accumulate in their own TMEM region (added in the epilogue)
@@ -354,8 +354,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           const bool first = a.diag ? (kb < a.kchunks) : (kb == 0);
           if (elect_one()) {
           if (a.ncat) {
-            // narrow layers (N <= 64): an SMEM-operand MMA at M = 128 costs ~64 cycles whatever N <= 128 is (measured:
-            // 67 cycles at N = 64), so a_hi x w_hi and a_hi x w_lo go out as ONE MMA over the adjacent [w_hi | w_lo]
+            // narrow layers (N <= 64): an SMEM-operand MMA at M = 128 costs >= 53 cycles whatever N is and 64 at N = 128
+            // (tools/mma_rate_probe.py), so a_hi x w_hi and a_hi x w_lo go out as ONE MMA over the adjacent [w_hi | w_lo]
             // slabs of the stage - it fills the main columns and, right behind them, the correction columns
 #pragma unroll
             for (int k = 0; k < 4; ++k)
