@@ -36,9 +36,11 @@ extern "C" {
 #define SFD2_API
 #endif
 
-#define SFD2_ABI_VERSION 1
+#define SFD2_ABI_VERSION 2
 #define SFD2_DESC_DIM 128
 #define SFD2_MATCH_PLAIN_CODES 0x100
+#define SFD2_MATCH_HLOC_SCORES 0x200
+#define SFD2_MATCH_I64 0x400
 
 typedef struct sfd2_ctx sfd2_ctx;
 
@@ -87,8 +89,30 @@ typedef struct {
   int32_t ratio_mode;       /* bits 0..7: 0 = hloc find_nn formula (nearest_neighbor.py:10-11),
                                1 = it_loc mutual_nn_ratio_matcher formula (it_loc/matcher.py:172-174);
                                bit 8 (SFD2_MATCH_PLAIN_CODES): report every unmatched row as -1
-                               (no -2 for "rejected only by the mutual check") */
+                               (no -2 for "rejected only by the mutual check");
+                               bit 9 (SFD2_MATCH_HLOC_SCORES, tcgen05 modes): sim0 = hloc's matching_scores0, i.e.
+                               (sim + 1) / 2 where the row passed its own ratio / distance test, else 0 (:14-15);
+                               bit 10 (SFD2_MATCH_I64, tcgen05 modes): matches0 is an int64 buffer (hloc's dtype) */
+  int32_t layout;           /* sfd2_desc_layout of d0 / d1 in sfd2_match_dev / sfd2_match_host */
 } sfd2_match_params;
+
+/* memory layout of a descriptor set */
+typedef enum {
+  SFD2_DESC_ROWS = 0, /* float32 [n, 128] row-major  (it_loc/matcher.py:94-95, the extractor's output)        */
+  SFD2_DESC_COLS = 1  /* float32 [128, n]            (hloc: data['descriptors0'][0], nearest_neighbor.py:39)  */
+} sfd2_desc_layout;
+
+/* One descriptor set of a grouped match call (all pointers are DEVICE pointers). */
+typedef struct {
+  const float* data;    /* descriptors in `layout`                                                                 */
+  int32_t n;            /* number of descriptors; the CAPACITY of the set when `count` is given                    */
+  int32_t layout;       /* sfd2_desc_layout                                                                        */
+  const int32_t* count; /* optional: the set's valid row count lives in device memory (e.g. sfd2_extract_dev's     */
+                        /* counts[i]) - an extract -> match pipeline then never synchronises with the host         */
+  const int32_t* ids;   /* optional int32 [n]: rows with ids[r] == -1 take no part (the localizer matches only db   */
+                        /* keypoints that have a 3-D point: desc_db[db_3D_ids != -1], it_loc/localize_cv2.py:540-555); */
+                        /* matches are reported as ORIGINAL row indices (the remap of :557-559 happens on the device) */
+} sfd2_desc_set;
 
 SFD2_API int sfd2_abi_version(void);
 SFD2_API const char* sfd2_last_error(void);
@@ -114,6 +138,11 @@ SFD2_API int sfd2_extract_dev(sfd2_ctx* ctx, const void* img_dev, int img_dtype,
 SFD2_API int sfd2_extract_host(sfd2_ctx* ctx, const void* img_host, int img_dtype, int n, int h, int w,
                       const sfd2_extract_params* p, float* kpts_host, float* scores_host,
                       float* desc_host, int32_t* counts_host);
+/* The *_dev extract call is asynchronous, so it cannot report that NMS produced more candidates than the workspace
+ * holds (the results are then a truncated, order-dependent subset).  This query synchronises `stream`, returns
+ * SFD2_ERR_OVERFLOW if any extract since the last query overflowed, SFD2_OK otherwise, and clears the flag.
+ * sfd2_extract_host calls it itself.  (The reference has no such limit: nets/extractor.py:158 uses nonzero().) */
+SFD2_API int sfd2_extract_status(sfd2_ctx* ctx, void* stream);
 
 /* Replaces NearestNeighbor._forward (hloc/matchers/nearest_neighbor.py:38-57) and
  * Matcher.mutual_nn_matcher (it_loc/matcher.py:122-130).
@@ -125,6 +154,13 @@ SFD2_API int sfd2_match_dev(sfd2_ctx* ctx, const float* d0_dev, int n0, const fl
                    const sfd2_match_params* p, int32_t* matches0_dev, float* sim0_dev, void* stream);
 SFD2_API int sfd2_match_host(sfd2_ctx* ctx, const float* d0_host, int n0, const float* d1_host, int n1, int d,
                     const sfd2_match_params* p, int32_t* matches0_host, float* sim0_host);
+/* Many pairs in ONE grouped launch: pair k matches sets[pair_a[k]] (rows of the result) against sets[pair_b[k]].
+ * Replaces the per-pair loops hloc/match_features.py:90-121 and it_loc/localize_cv2.py:511-560,705-731.
+ *   matches0 int32, sim0 float32: pair k's rows start at sum_{q<k} sets[pair_a[q]].n (capacity rows; rows beyond a
+ *   device-side count read -1 / 0).  Codes as in sfd2_match_dev.  pair_a / pair_b / sets are HOST arrays. */
+SFD2_API int sfd2_match_pairs_dev(sfd2_ctx* ctx, const sfd2_desc_set* sets, int nsets, const int32_t* pair_a,
+                                  const int32_t* pair_b, int npairs, const sfd2_match_params* p,
+                                  int32_t* matches0_dev, float* sim0_dev, void* stream);
 /* Many independent pairs in one call (hloc/match_features.py:90 pair loop;
  * it_loc/localize_cv2.py:705 one query against <= 50 db images).  Pair i uses rows
  * [off0[i], off0[i+1]) of d0 and [off1[i], off1[i+1]) of d1; outputs are indexed
@@ -166,11 +202,9 @@ SFD2_API int sfd2_debug_conv(sfd2_ctx* ctx, const float* x_host, int h, int w, i
                     const float* b_host, int cout, int ksize, int stride, int groups, int relu,
                     int precision, float* y_host);
 
-/* Hardware probe used while designing the conv kernel's operand staging (tools/umma_probe.py). */
-SFD2_API int sfd2_debug_umma_probe(int pitch, int ky, int kx, int use_base_offset, int pattern, float* out_host);
-/* Hardware probe: cycles per CTA for `iters` back-to-back SMEM-operand tcgen05.mma of shape M128 x n x K
- * (kind 0: f16, K = 16; kind 1: f8f6f4 / E4M3, K = 32) on `grid` CTAs (tools/mma_rate_probe.py). */
-SFD2_API int sfd2_debug_mma_rate(int n, int kind, int iters, int grid, unsigned long long* cycles_host);
+/* (The two hardware probes used while designing the conv kernel - tools/umma_probe.py, tools/mma_rate_probe.py -
+ * are NOT part of this ABI: they are compiled in only by `SFD2_WITH_PROBES=1 python -m sfd2_b200.build --force` and
+ * declared in sfd2_b200/csrc/probes.h.) */
 
 #ifdef __cplusplus
 }

@@ -320,6 +320,22 @@ def match_itloc_nnr(descriptors0: np.ndarray, descriptors1: np.ndarray, ratio: f
     return {"matches0": all_matches, "matching_scores0": scores.squeeze(-1).numpy()}
 
 
+def feature_matching(desc_q: np.ndarray, desc_db: np.ndarray, db_3D_ids=None):
+    """it_loc/localize_cv2.py:511-560 without labels, matcher = Matcher(confs['NNM']) (it_loc/matcher.py:85-130):
+    only db keypoints with a 3-D point take part (desc_db[db_3D_ids != -1]); matches are mapped back to the
+    original db rows (:557-559); <= 3 valid db keypoints -> no matches (:537-538)."""
+    if db_3D_ids is None:
+        return match_itloc(desc_q, desc_db)["matches0"]
+    masks = (np.asarray(db_3D_ids) != -1)
+    if np.sum(masks) <= 3:
+        return np.ones((desc_q.shape[0],), dtype=int) * -1
+    valid_ids = np.nonzero(masks)[0]
+    matches = match_itloc(desc_q, desc_db[masks])["matches0"].copy()
+    ok = matches >= 0
+    matches[ok] = valid_ids[matches[ok]]
+    return matches
+
+
 def mutual_nn_exact(d0: np.ndarray, d1: np.ndarray):
     """Tie-aware float64 restatement of A.8 used to classify disagreements:
     returns sim-free nn12, nn21 (lowest index on ties) and the top-1/top-2 gap per row."""

@@ -7,7 +7,9 @@ LIB_PATH = os.path.join(_HERE, "libsfd2_b200.so")
 
 PREC = {"fp32": 0, "exact": 1, "fast": 2, "mixed": 3}
 IMG_F32_NCHW, IMG_U8_NHWC = 0, 1
+DESC_ROWS, DESC_COLS = 0, 1
 DESC_DIM = 128
+ABI_VERSION = 2
 
 
 class ExtractParams(C.Structure):
@@ -18,11 +20,31 @@ class ExtractParams(C.Structure):
 
 class MatchParams(C.Structure):
     _fields_ = [("do_mutual_check", C.c_int32), ("distance_threshold", C.c_float),
-                ("ratio_threshold", C.c_float), ("precision", C.c_int32), ("ratio_mode", C.c_int32)]
+                ("ratio_threshold", C.c_float), ("precision", C.c_int32), ("ratio_mode", C.c_int32),
+                ("layout", C.c_int32)]
+
+
+class DescSet(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("layout", C.c_int32), ("count", C.c_void_p),
+                ("ids", C.c_void_p)]
 
 
 class Sfd2Error(RuntimeError):
     pass
+
+
+def device_index(device=None) -> int:
+    """CUDA device index of `device` (None / 'cuda' / torch.device without an index = the CURRENT device,
+    not GPU 0: under torchrun every rank has set its own)."""
+    import torch
+    if device is None:
+        return torch.cuda.current_device()
+    if isinstance(device, int):
+        return device
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise Sfd2Error(f"sfd2_b200 runs on CUDA devices only (got {d})")
+    return torch.cuda.current_device() if d.index is None else d.index
 
 
 _lib = None
@@ -37,10 +59,13 @@ _PROTOS = {
                                    C.c_void_p]),
     "sfd2_extract_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(ExtractParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sfd2_extract_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sfd2_match_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_match_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.POINTER(MatchParams), C.c_void_p, C.c_void_p]),
+    "sfd2_match_pairs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_match_batched_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_int, C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_match_one_to_many_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
@@ -51,8 +76,6 @@ _PROTOS = {
     "sfd2_profile_read": (C.c_longlong, [C.c_void_p, C.c_char_p, C.c_longlong]),
     "sfd2_nms_select_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(ExtractParams),
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "sfd2_debug_umma_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "sfd2_debug_mma_rate": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "sfd2_debug_conv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
@@ -70,7 +93,7 @@ def lib():
         for name, (res, args) in _PROTOS.items():
             fn = getattr(h, name)     # AttributeError if the .so does not export what the header declares
             fn.restype, fn.argtypes = res, args
-        if h.sfd2_abi_version() != 1:
+        if h.sfd2_abi_version() != ABI_VERSION:
             raise Sfd2Error("libsfd2_b200.so ABI version mismatch")
         _lib = h
     return _lib

@@ -13,8 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsfd2_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_match.cu", "post.cu", "match.cu", "umma_probe.cu"]
-HEADERS = ["common.cuh", "ptx.cuh", os.path.join("..", "..", "include", "sfd2_b200.h")]
+SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_match.cu", "post.cu", "match.cu"]
+# hardware probes (tools/umma_probe.py, tools/mma_rate_probe.py): measurement scaffolding, only on request
+if os.environ.get("SFD2_WITH_PROBES") == "1":
+    SOURCES.append("umma_probe.cu")
+HEADERS = ["common.cuh", "ptx.cuh", "probes.h", os.path.join("..", "..", "include", "sfd2_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

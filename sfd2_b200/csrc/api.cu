@@ -8,6 +8,7 @@
 #include <map>
 
 #include "common.cuh"
+#include "tc_match.cuh"
 
 namespace sfd2 {
 
@@ -39,11 +40,16 @@ struct BlobLayer {
 
 enum ActId { A1A, A1B, A2A, A2B, A3A, A3B, T1, T2, BA, BB, PA, DA, NUM_ACTS };
 
-// per-image extract workspace (activations, TMA views, head buffers, candidate list), sized for wsH x wsW
+// per-image extract workspace (activations, TMA views, head buffers, candidate list).  Buffers are grow-only:
+// every buffer keeps its own byte capacity, a new image size only re-allocates the buffers it outgrows and
+// re-encodes the tensor maps (host-side, no device sync), so a stream of mixed portrait / landscape / multi-scale
+// sizes settles after the largest one has been seen instead of freeing and re-allocating ~40 buffers per call.
 struct Ws {
-  int wsH = 0, wsW = 0;
-  bool have_f32 = false, have_tc = false;
+  int wsH = 0, wsW = 0;          // shape the dims / tensor maps below are encoded for
+  bool maps_tc = false;          // tensor maps valid for (wsH, wsW)
+  bool zero_f32 = false, zero_tc = false;   // padded planes must be re-zeroed on the next use (shape changed)
   Act acts[NUM_ACTS];
+  size_t cap_f32[NUM_ACTS] = {}, cap_hi[NUM_ACTS] = {}, cap_lo[NUM_ACTS] = {};
   CUtensorMap maps[NUM_ACTS][8];
   CUtensorMap st_maps[NUM_ACTS][4];
   CUtensorMap map_1a[4];                    // conv1a output rows: [hi, lo] box {64 ch, 256 px, 1 row}, [hi, lo] box {64, 128, 1}
@@ -52,6 +58,8 @@ struct Ws {
   float4* nimg = nullptr;  // normalised image, NHWC4 fp32
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
   unsigned long long *cand = nullptr, *scratch = nullptr;
+  size_t cap_nimg = 0, cap_logits = 0, cap_semi = 0, cap_descmap = 0, cap_sta = 0, cap_heat = 0, cap_nmsdbg = 0,
+         cap_cand = 0, cap_scratch = 0;
   int cap = 0;
   int *counter = nullptr, *status = nullptr;
 };
@@ -73,11 +81,21 @@ struct sfd2_ctx {
   // host-API staging
   void* img_dev = nullptr; size_t img_cap = 0;
   float *kp_dev = nullptr, *sc_dev = nullptr, *de_dev = nullptr; int32_t* cnt_dev = nullptr; size_t out_cap = 0;
-  // matcher workspace
+  // matcher workspace, CUDA-core fp32 mode
   unsigned long long *row_key = nullptr, *col_key = nullptr; size_t key_cap = 0;
   unsigned *row2 = nullptr, *col2 = nullptr;   // second-best similarities (ratio tests)
-  int* seg_dev = nullptr; size_t seg_cap = 0;  // segment table of the one-to-many call
-  __half* mhalf = nullptr; size_t mhalf_cap = 0;
+  // matcher workspace, grouped tcgen05 path (grow-only; tensor maps cover the whole plane allocation)
+  struct MatchWs {
+    __half *hi = nullptr, *lo = nullptr; size_t cap_hi = 0, cap_lo = 0;
+    CUtensorMap tm_hi, tm_lo; bool maps_ok = false;
+    unsigned long long* keys = nullptr; size_t cap_keys = 0;
+    unsigned* sec = nullptr; size_t cap_sec = 0;
+    int *remap = nullptr, *efflen = nullptr, *done = nullptr; size_t cap_remap = 0, cap_efflen = 0, cap_done = 0;
+    uint8_t* tab = nullptr; size_t cap_tab = 0;
+    static constexpr int kRing = 8;
+    struct Slot { void* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; } ring[kRing];
+    unsigned next = 0;
+  } mws;
   float *m_d0 = nullptr, *m_d1 = nullptr; size_t m_d0_cap = 0, m_d1_cap = 0;
   int32_t* m_out = nullptr; float* m_sim = nullptr; size_t m_out_cap = 0;
   long long launches = 0;
@@ -119,19 +137,35 @@ static void free_workspace(Ws& w) {
   for (int i = 0; i < NUM_ACTS; ++i) {
     cudaFree(w.acts[i].f32); cudaFree(w.acts[i].hi); cudaFree(w.acts[i].lo);
     w.acts[i] = Act();
+    w.cap_f32[i] = w.cap_hi[i] = w.cap_lo[i] = 0;
   }
   cudaFree(w.nimg); w.nimg = nullptr;
   cudaFree(w.logits); cudaFree(w.semi); cudaFree(w.descmap); cudaFree(w.sta); cudaFree(w.heat); cudaFree(w.nmsdbg);
   cudaFree(w.cand); cudaFree(w.scratch); cudaFree(w.counter); cudaFree(w.status);
   w.logits = w.semi = w.descmap = w.sta = w.heat = w.nmsdbg = nullptr;
   w.cand = w.scratch = nullptr; w.counter = w.status = nullptr;
-  w.wsH = w.wsW = 0; w.have_f32 = w.have_tc = false;
+  w.cap_nimg = w.cap_logits = w.cap_semi = w.cap_descmap = w.cap_sta = w.cap_heat = w.cap_nmsdbg = w.cap_cand = w.cap_scratch = 0;
+  w.wsH = w.wsW = 0; w.maps_tc = false; w.zero_f32 = w.zero_tc = false;
+}
+
+// grow-only device buffer: re-allocates only when `bytes` exceeds the capacity (contents are then undefined)
+template <typename T>
+static int reserve(T*& p, size_t& cap, size_t bytes, bool* grew = nullptr) {
+  if (grew) *grew = false;
+  if (bytes <= cap && p) return SFD2_OK;
+  if (p) { cudaFree(p); p = nullptr; cap = 0; }
+  SFD2_CUDA(cudaMalloc(&p, bytes));
+  cap = bytes;
+  if (grew) *grew = true;
+  return SFD2_OK;
 }
 
 static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
+  int rc;
+  const bool want_tc = (prec != SFD2_PREC_FP32);
   if (w.wsH != H || w.wsW != W) {
-    free_workspace(w);
     w.wsH = H; w.wsW = W;
+    w.maps_tc = false;
     w.H2 = conv_out(H, 2); w.W2 = conv_out(W, 2);
     w.H4 = conv_out(w.H2, 2); w.W4 = conv_out(w.W2, 2);
     w.H8 = conv_out(w.H4, 2); w.W8 = conv_out(w.W4, 2);
@@ -143,42 +177,49 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       a.H = dims[i][0]; a.W = dims[i][1]; a.C = dims[i][2];
       a.Hp = round_up(a.H, 2); a.Wp = round_up(a.W, 2);
     }
+    // planes that exist already hold another shape's data where this shape's zero padding must be
+    w.zero_f32 = w.zero_tc = true;
     const size_t n8 = (size_t)w.H8 * w.W8, n4 = (size_t)w.H4 * w.W4;
-    SFD2_CUDA(cudaMalloc(&w.nimg, (size_t)H * W * sizeof(float4)));
-    SFD2_CUDA(cudaMalloc(&w.logits, n8 * 80 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&w.semi, n8 * 64 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&w.descmap, n4 * 128 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&w.sta, n4 * 3 * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&w.heat, (size_t)H * W * sizeof(float)));
-    SFD2_CUDA(cudaMalloc(&w.nmsdbg, (size_t)H * W * sizeof(float)));
+    if ((rc = reserve(w.nimg, w.cap_nimg, (size_t)H * W * sizeof(float4)))) return rc;
+    if ((rc = reserve(w.logits, w.cap_logits, n8 * 80 * sizeof(float)))) return rc;
+    if ((rc = reserve(w.semi, w.cap_semi, n8 * 64 * sizeof(float)))) return rc;
+    if ((rc = reserve(w.descmap, w.cap_descmap, n4 * 128 * sizeof(float)))) return rc;
+    if ((rc = reserve(w.sta, w.cap_sta, n4 * 3 * sizeof(float)))) return rc;
+    if ((rc = reserve(w.heat, w.cap_heat, (size_t)H * W * sizeof(float)))) return rc;
+    if ((rc = reserve(w.nmsdbg, w.cap_nmsdbg, (size_t)H * W * sizeof(float)))) return rc;
     // NMS survivors are >= 5 px apart except on exact plateaus: H*W/16 leaves 1.5x headroom.
     w.cap = (int)(((size_t)H * W) / 16) + 4096;
     int cap2 = 1;
     while (cap2 < w.cap) cap2 <<= 1;
-    SFD2_CUDA(cudaMalloc(&w.cand, (size_t)w.cap * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMalloc(&w.scratch, (size_t)cap2 * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMemset(w.scratch, 0, (size_t)cap2 * sizeof(unsigned long long)));   // select_kernel's rank / arrival counters
-    SFD2_CUDA(cudaMalloc(&w.counter, sizeof(int)));
-    SFD2_CUDA(cudaMalloc(&w.status, sizeof(int)));
-    SFD2_CUDA(cudaMemset(w.status, 0, sizeof(int)));
-  }
-  const bool want_tc = (prec != SFD2_PREC_FP32);
-  if (!want_tc && !w.have_f32) {
-    for (int i = 0; i < NUM_ACTS; ++i) {
-      Act& a = w.acts[i];
-      SFD2_CUDA(cudaMalloc(&a.f32, a.elems() * sizeof(float)));
-      SFD2_CUDA(cudaMemset(a.f32, 0, a.elems() * sizeof(float)));
+    if ((rc = reserve(w.cand, w.cap_cand, (size_t)w.cap * sizeof(unsigned long long)))) return rc;
+    bool grew = false;
+    if ((rc = reserve(w.scratch, w.cap_scratch, (size_t)cap2 * sizeof(unsigned long long), &grew))) return rc;
+    // select_kernel's rank / arrival counters: zero once, the kernel leaves them zero
+    if (grew) SFD2_CUDA(cudaMemset(w.scratch, 0, w.cap_scratch));
+    if (!w.counter) SFD2_CUDA(cudaMalloc(&w.counter, sizeof(int)));
+    if (!w.status) {
+      SFD2_CUDA(cudaMalloc(&w.status, sizeof(int)));
+      SFD2_CUDA(cudaMemset(w.status, 0, sizeof(int)));
     }
-    w.have_f32 = true;
   }
-  if (want_tc && !w.have_tc) {
+  if (!want_tc) {
     for (int i = 0; i < NUM_ACTS; ++i) {
       Act& a = w.acts[i];
-      SFD2_CUDA(cudaMalloc(&a.hi, a.elems() * sizeof(__half)));
-      SFD2_CUDA(cudaMalloc(&a.lo, a.elems() * sizeof(__half)));
-      SFD2_CUDA(cudaMemset(a.hi, 0, a.elems() * sizeof(__half)));
-      SFD2_CUDA(cudaMemset(a.lo, 0, a.elems() * sizeof(__half)));
-      int rc = tc_make_act_maps(a, a.hi, &w.maps[i][0], &w.maps[i][2], &w.maps[i][4], &w.maps[i][6]);
+      if ((rc = reserve(a.f32, w.cap_f32[i], a.elems() * sizeof(float)))) return rc;
+    }
+  } else {
+    for (int i = 0; i < NUM_ACTS; ++i) {
+      Act& a = w.acts[i];
+      bool g0 = false, g1 = false;
+      if ((rc = reserve(a.hi, w.cap_hi[i], a.elems() * sizeof(__half), &g0))) return rc;
+      if ((rc = reserve(a.lo, w.cap_lo[i], a.elems() * sizeof(__half), &g1))) return rc;
+      if (g0 || g1) w.maps_tc = false;
+    }
+  }
+  if (want_tc && !w.maps_tc) {
+    for (int i = 0; i < NUM_ACTS; ++i) {
+      Act& a = w.acts[i];
+      rc = tc_make_act_maps(a, a.hi, &w.maps[i][0], &w.maps[i][2], &w.maps[i][4], &w.maps[i][6]);
       if (rc) return rc;
       rc = tc_make_act_maps(a, a.lo, &w.maps[i][1], &w.maps[i][3], &w.maps[i][5], &w.maps[i][7]);
       if (rc) return rc;
@@ -190,7 +231,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       if (rc) return rc;
       a.tm_st = w.st_maps[i];
     }
-    int rc = 0;
+    rc = 0;
     for (int pl = 0; pl < 4 && !rc; ++pl) {
       const Act& a = w.acts[A1A];
       const uint64_t dims[3] = {64, (uint64_t)a.W, (uint64_t)a.H};
@@ -204,8 +245,28 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
       if (!rc) rc = tc_make_store_map(&w.map_semi[b], w.semi, 64, w.W8, w.H8, w.W8, 1, b ? 8 : 16);
     }
     if (rc) return rc;
-    w.have_tc = true;
+    w.maps_tc = true;
   }
+  return SFD2_OK;
+}
+
+// The even-padded row / column of an activation (Hp > H or Wp > W) is read by stride-2 consumers as the conv's zero
+// padding and is never written by a producer (TMA stores clip at W x H): zero the padded planes once per shape, on
+// the stream that is about to use the workspace.
+static int zero_padding(Ws& w, bool tc, cudaStream_t st) {
+  bool& flag = tc ? w.zero_tc : w.zero_f32;
+  if (!flag) return SFD2_OK;
+  for (int i = 0; i < NUM_ACTS; ++i) {
+    Act& a = w.acts[i];
+    if (a.Hp == a.H && a.Wp == a.W) continue;
+    if (tc) {
+      SFD2_CUDA(cudaMemsetAsync(a.hi, 0, a.elems() * sizeof(__half), st));
+      SFD2_CUDA(cudaMemsetAsync(a.lo, 0, a.elems() * sizeof(__half), st));
+    } else {
+      SFD2_CUDA(cudaMemsetAsync(a.f32, 0, a.elems() * sizeof(float), st));
+    }
+  }
+  flag = false;
   return SFD2_OK;
 }
 
@@ -235,7 +296,8 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   // MIXED: the descriptor head only has to meet the 1e-3 tolerance, so it runs single-pass (hi planes only)
   const int split_d = (prec == SFD2_PREC_TC_MIXED) ? 1 : split;
   Act* A = w.acts;
-  int rc;
+  int rc = zero_padding(w, tc, st);
+  if (rc) return rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
   RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
@@ -371,7 +433,12 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
   for (Ws& w : c->ws) free_workspace(w);
   for (Layer& L : c->layers) free_layer(L);
   cudaFree(c->img_dev); cudaFree(c->kp_dev); cudaFree(c->sc_dev); cudaFree(c->de_dev); cudaFree(c->cnt_dev);
-  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2); cudaFree(c->seg_dev); cudaFree(c->mhalf); cudaFree(c->m_d0); cudaFree(c->m_d1);
+  cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2); cudaFree(c->m_d0); cudaFree(c->m_d1);
+  {
+    sfd2_ctx::MatchWs& m = c->mws;
+    cudaFree(m.hi); cudaFree(m.lo); cudaFree(m.keys); cudaFree(m.sec); cudaFree(m.remap); cudaFree(m.efflen); cudaFree(m.done); cudaFree(m.tab);
+    for (auto& sl : m.ring) { if (sl.host) cudaFreeHost(sl.host); if (sl.ev) cudaEventDestroy(sl.ev); }
+  }
   cudaFree(c->m_out); cudaFree(c->m_sim);
   for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -417,22 +484,25 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
   }
   const size_t img_stride = (size_t)h * w * 3 * (img_dtype == SFD2_IMG_F32_NCHW ? 4 : 1);
   const long long before = g_launches;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && !rc; ++i) {
     const int k = (ns > 1) ? (i % ns) : 0;
-    if (ready) SFD2_CUDA(cudaStreamWaitEvent(ns > 1 ? c->aux[k] : st, ready[i], 0));
+    cudaStream_t si = ns > 1 ? c->aux[k] : st;
+    if (ready && cudaStreamWaitEvent(si, ready[i], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent(image %d) failed", i); rc = SFD2_ERR_CUDA; break; }
     rc = extract_one(c, c->ws[k], static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
                      kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
-                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, ns > 1 ? c->aux[k] : st);
-    if (rc) return rc;
+                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, si);
   }
+  // join the internal streams to the caller's stream also when an image failed: whatever was launched must
+  // be ordered before the caller's next work (and before the workspaces are reused)
   if (ns > 1)
     for (int k = 0; k < ns; ++k) {
-      SFD2_CUDA(cudaEventRecord(c->ev_join[k], c->aux[k]));
-      SFD2_CUDA(cudaStreamWaitEvent(st, c->ev_join[k], 0));
+      const bool ok = cudaEventRecord(c->ev_join[k], c->aux[k]) == cudaSuccess &&
+                      cudaStreamWaitEvent(st, c->ev_join[k], 0) == cudaSuccess;
+      if (!ok && !rc) { set_error("joining internal stream %d failed", k); rc = SFD2_ERR_CUDA; }
     }
   c->launches += g_launches - before;
   c->last_prec = p->precision;
-  return SFD2_OK;
+  return rc;
 }
 
 SFD2_API int sfd2_extract_dev(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
@@ -463,8 +533,6 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
     c->out_cap = rows;
   }
   cudaStream_t st = c->stream;
-  SFD2_CUDA(cudaMemsetAsync(c->kp_dev, 0, rows * 2 * sizeof(float), st));
-  SFD2_CUDA(cudaMemsetAsync(c->sc_dev, 0, rows * sizeof(float), st));
   if (n == 1) {
     SFD2_CUDA(cudaMemcpyAsync(c->img_dev, img, img_bytes, cudaMemcpyHostToDevice, st));
     rc = extract_batch(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st, nullptr);
@@ -491,20 +559,31 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
   SFD2_CUDA(cudaMemcpyAsync(scores, c->sc_dev, rows * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(desc, c->de_dev, rows * SFD2_DESC_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
   SFD2_CUDA(cudaMemcpyAsync(counts, c->cnt_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return sfd2_extract_status(c, st);
+}
+
+// Candidate-overflow flag of the extract calls issued so far (select_kernel raises it; it is sticky per workspace
+// until queried).  Synchronises `stream`, clears the flags.
+SFD2_API int sfd2_extract_status(sfd2_ctx* c, void* stream) {
+  SFD2_CHECK(c != nullptr, SFD2_ERR_ARG, "sfd2_extract_status: NULL ctx");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   int status[sfd2_ctx::kMaxStreams] = {};
   for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k)
-    if (c->ws[k].status) SFD2_CUDA(cudaMemcpyAsync(&status[k], c->ws[k].status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (c->ws[k].status) {
+      SFD2_CUDA(cudaMemcpyAsync(&status[k], c->ws[k].status, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SFD2_CUDA(cudaMemsetAsync(c->ws[k].status, 0, sizeof(int), st));
+    }
   SFD2_CUDA(cudaStreamSynchronize(st));
   if (status[0] | status[1] | status[2] | status[3]) {
-    for (int k = 0; k < sfd2_ctx::kMaxStreams; ++k)
-      if (c->ws[k].status) cudaMemset(c->ws[k].status, 0, sizeof(int));
     set_error("NMS produced more candidates than the workspace holds (cap %d); results truncated", c->ws[0].cap);
     return SFD2_ERR_OVERFLOW;
   }
   return SFD2_OK;
 }
 
-static int ensure_match_ws(sfd2_ctx* c, int n0, int n1) {
+// ---- matcher -----------------------------------------------------------------------------------------------
+static int ensure_match_ws_simt(sfd2_ctx* c, int n0, int n1) {
   const size_t need = (size_t)(n0 > n1 ? n0 : n1) + 128;
   if (need > c->key_cap) {
     cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2);
@@ -515,27 +594,19 @@ static int ensure_match_ws(sfd2_ctx* c, int n0, int n1) {
     SFD2_CUDA(cudaMalloc(&c->col2, need * sizeof(unsigned)));
     c->key_cap = need;
   }
-  const size_t hneed = 2 * ((size_t)round_up(n0 > 0 ? n0 : 1, 128) + round_up(n1 > 0 ? n1 : 1, 128)) * 128;
-  if (hneed > c->mhalf_cap) {
-    cudaFree(c->mhalf); c->mhalf = nullptr; c->mhalf_cap = 0;
-    SFD2_CUDA(cudaMalloc(&c->mhalf, hneed * sizeof(__half)));
-    c->mhalf_cap = hneed;
-  }
   return SFD2_OK;
 }
 
-static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
-                     int32_t* matches0, float* sim0, cudaStream_t st) {
-  int rc;
-  prof_begin(c, p->precision == SFD2_PREC_FP32 ? "match_simt" : "match_tc", st);
-  if (p->precision == SFD2_PREC_FP32)
-    rc = launch_match_simt(d0, n0, d1, n1, d, c->row_key, c->col_key, st);
-  else
-    rc = launch_match_tc(d0, n0, d1, n1, d, p->precision != SFD2_PREC_TC_FAST ? 3 : 1, c->mhalf, c->row_key,
-                         c->col_key, c->num_sms, st);
+// CUDA-core fp32 reference mode (SFD2_PREC_FP32): one pair, host-known sizes, [n, 128] rows
+static int match_one_simt(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
+                          int32_t* matches0, float* sim0, cudaStream_t st) {
+  int rc = ensure_match_ws_simt(c, n0, n1);
+  if (rc) return rc;
+  prof_begin(c, "match_simt", st);
+  rc = launch_match_simt(d0, n0, d1, n1, d, c->row_key, c->col_key, st);
   prof_end(c, st);
   if (rc) return rc;
-  if (p->ratio_threshold > 0.f) {   // second-best pass (CUDA-core fp32 in every precision mode)
+  if (p->ratio_threshold > 0.f) {   // second-best pass on CUDA cores (fp32 mode only; the tcgen05 modes keep top-2 in the epilogue)
     rc = launch_match_second(d0, n0, d1, n1, d, c->row_key, c->col_key, c->row2, c->col2, st);
     if (rc) return rc;
   }
@@ -544,95 +615,197 @@ static int match_one(sfd2_ctx* c, const float* d0, int n0, const float* d1, int 
                              c->row2, c->col2, matches0, sim0, st);
 }
 
+// the grouped tcgen05 matcher: tables -> device, prep (split / compaction / resets), one GEMM + arg-max + finish launch
+static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, const int32_t* pa, const int32_t* pb, int npairs,
+                          const sfd2_match_params* p, int32_t* matches0, float* sim0, cudaStream_t st) {
+  sfd2_ctx::MatchWs& m = c->mws;
+  std::vector<MOperD> opers(nsets);
+  long long prow = 0;
+  bool any_ids = false;
+  for (int i = 0; i < nsets; ++i) {
+    const sfd2_desc_set& s = sets[i];
+    SFD2_CHECK(s.n >= 0 && (s.n == 0 || s.data), SFD2_ERR_ARG, "match: set %d has n = %d, data = %p", i, s.n, (const void*)s.data);
+    SFD2_CHECK(s.layout == SFD2_DESC_ROWS || s.layout == SFD2_DESC_COLS, SFD2_ERR_ARG, "match: set %d: bad layout %d", i, s.layout);
+    MOperD& o = opers[i];
+    o.src = s.data;
+    o.layout = s.layout;
+    o.rs = s.layout == SFD2_DESC_ROWS ? SFD2_DESC_DIM : 1;
+    o.cs = s.layout == SFD2_DESC_ROWS ? 1 : s.n;
+    o.cap = s.n; o.prow0 = (int)prow; o.pad_ = 0;
+    o.count = s.count; o.ids = s.ids;
+    any_ids |= s.ids != nullptr;
+    prow += round_up(s.n > 0 ? s.n : 1, 128);
+    SFD2_CHECK(prow < (1ll << 30), SFD2_ERR_ARG, "match: too many descriptor rows in one call");
+  }
+  const int passes = p->ratio_threshold > 0.f ? 2 : 1;
+  std::vector<MProbD> probs(npairs);
+  long long koff = 0, ooff = 0, tiles = 0;
+  for (int k = 0; k < npairs; ++k) {
+    SFD2_CHECK(pa[k] >= 0 && pa[k] < nsets && pb[k] >= 0 && pb[k] < nsets, SFD2_ERR_ARG, "match: pair %d refers to a set out of range", k);
+    MProbD& q = probs[k];
+    q.a = pa[k]; q.b = pb[k];
+    const int na = sets[q.a].n, nb = sets[q.b].n;
+    q.tm = cdiv(na, 128); q.tn = cdiv(nb, 128);
+    q.tile0 = (int)tiles;
+    q.ntiles = q.tm * q.tn * passes;
+    tiles += q.ntiles;
+    q.key_a = koff; koff += round_up(na > 0 ? na : 1, 128);
+    q.key_b = koff; koff += round_up(nb > 0 ? nb : 1, 128);
+    q.out_off = ooff; ooff += na;
+    SFD2_CHECK(tiles < (1ll << 30), SFD2_ERR_ARG, "match: too many tiles in one call");
+    if (q.ntiles == 0 && na > 0) {      // empty db: no CTA will ever finish this pair - every row is unmatched
+      const size_t isz = (p->ratio_mode & SFD2_MATCH_I64) ? 8 : 4;
+      SFD2_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(matches0) + q.out_off * isz, 0xFF, (size_t)na * isz, st));
+      SFD2_CUDA(cudaMemsetAsync(sim0 + q.out_off, 0, (size_t)na * sizeof(float), st));
+    }
+  }
+  if (tiles == 0) return SFD2_OK;
+  // workspace (grow-only)
+  int rc;
+  bool grew_hi = false, grew_lo = false;
+  if ((rc = reserve(m.hi, m.cap_hi, (size_t)prow * 128 * sizeof(__half), &grew_hi))) return rc;
+  if ((rc = reserve(m.lo, m.cap_lo, (size_t)prow * 128 * sizeof(__half), &grew_lo))) return rc;
+  if (grew_hi || grew_lo || !m.maps_ok) {
+    // the maps cover the whole allocation, so they only change when the planes are re-allocated
+    if ((rc = tm_make_plane_map(&m.tm_hi, m.hi, m.cap_hi / 256))) return rc;
+    if ((rc = tm_make_plane_map(&m.tm_lo, m.lo, m.cap_lo / 256))) return rc;
+    m.maps_ok = true;
+  }
+  if ((rc = reserve(m.keys, m.cap_keys, (size_t)koff * sizeof(unsigned long long)))) return rc;
+  if (passes == 2 && (rc = reserve(m.sec, m.cap_sec, (size_t)koff * sizeof(unsigned)))) return rc;
+  if (any_ids && (rc = reserve(m.remap, m.cap_remap, (size_t)prow * sizeof(int)))) return rc;
+  if ((rc = reserve(m.efflen, m.cap_efflen, (size_t)nsets * sizeof(int)))) return rc;
+  if ((rc = reserve(m.done, m.cap_done, (size_t)npairs * sizeof(int)))) return rc;
+  const size_t tab_bytes = opers.size() * sizeof(MOperD) + probs.size() * sizeof(MProbD);
+  if ((rc = reserve(m.tab, m.cap_tab, tab_bytes))) return rc;
+  // tables: pinned staging ring -> device (stream-ordered behind the previous call's kernels)
+  sfd2_ctx::MatchWs::Slot& slot = m.ring[m.next++ % sfd2_ctx::MatchWs::kRing];
+  if (!slot.ev) SFD2_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+  else SFD2_CUDA(cudaEventSynchronize(slot.ev));      // the copy that last used this slot has completed
+  if (tab_bytes > slot.cap) {
+    if (slot.host) cudaFreeHost(slot.host);
+    slot.host = nullptr; slot.cap = 0;
+    SFD2_CUDA(cudaMallocHost(&slot.host, tab_bytes * 2));
+    slot.cap = tab_bytes * 2;
+  }
+  memcpy(slot.host, opers.data(), opers.size() * sizeof(MOperD));
+  memcpy(static_cast<uint8_t*>(slot.host) + opers.size() * sizeof(MOperD), probs.data(), probs.size() * sizeof(MProbD));
+  SFD2_CUDA(cudaMemcpyAsync(m.tab, slot.host, tab_bytes, cudaMemcpyHostToDevice, st));
+  SFD2_CUDA(cudaEventRecord(slot.ev, st));
+  const MOperD* opers_dev = reinterpret_cast<const MOperD*>(m.tab);
+  const MProbD* probs_dev = reinterpret_cast<const MProbD*>(m.tab + opers.size() * sizeof(MOperD));
+  prof_begin(c, "match_prep", st);
+  rc = launch_match_prep(opers_dev, nsets, (int)prow, any_ids, m.hi, m.lo, m.remap, m.efflen, m.keys, passes == 2 ? m.sec : nullptr,
+                         koff, m.done, npairs, c->num_sms, st);
+  prof_end(c, st);
+  if (rc) return rc;
+  TcMatchArgs a{};
+  a.opers = opers_dev; a.probs = probs_dev;
+  a.nprob = npairs; a.total_tiles = (int)tiles;
+  a.passes = passes;
+  a.cols = (passes == 1 && p->do_mutual_check) ? 1 : 0;
+  a.split = p->precision != SFD2_PREC_TC_FAST ? 3 : 1;
+  a.mutual = p->do_mutual_check ? 1 : 0;
+  a.ratio_mode = ((p->ratio_mode & 0xFF) == 1 ? 2 : 1) | (p->ratio_mode & (SFD2_MATCH_PLAIN_CODES | SFD2_MATCH_HLOC_SCORES | SFD2_MATCH_I64));
+  a.dist_th = p->distance_threshold; a.ratio_th = p->ratio_threshold;
+  a.keys = m.keys; a.sec = passes == 2 ? m.sec : nullptr;
+  a.efflen = m.efflen; a.remap = m.remap; a.done = m.done;
+  a.matches0 = matches0; a.sim0 = sim0;
+  prof_begin(c, "match_tc", st);
+  rc = launch_match_tc(m.tm_hi, m.tm_lo, a, c->num_sms, st);
+  prof_end(c, st);
+  return rc;
+}
+
+static int check_match_params(const sfd2_match_params* p) {
+  SFD2_CHECK(p != nullptr, SFD2_ERR_ARG, "match params is NULL");
+  SFD2_CHECK(p->precision >= 0 && p->precision <= 3, SFD2_ERR_ARG, "bad precision %d", p->precision);
+  SFD2_CHECK(p->layout == SFD2_DESC_ROWS || p->layout == SFD2_DESC_COLS, SFD2_ERR_ARG, "bad descriptor layout %d", p->layout);
+  return SFD2_OK;
+}
+
+SFD2_API int sfd2_match_pairs_dev(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, const int32_t* pa, const int32_t* pb,
+                                  int npairs, const sfd2_match_params* p, int32_t* matches0, float* sim0, void* stream) {
+  SFD2_CHECK(c && sets && pa && pb && nsets >= 1 && npairs >= 0, SFD2_ERR_ARG, "sfd2_match_pairs_dev: bad argument");
+  int rc = check_match_params(p);
+  if (rc) return rc;
+  if (npairs == 0) return SFD2_OK;
+  SFD2_CHECK(matches0 && sim0, SFD2_ERR_ARG, "sfd2_match_pairs_dev: NULL output");
+  SFD2_CUDA(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long before = g_launches;
+  if (p->precision == SFD2_PREC_FP32) {   // CUDA-core reference mode: plain loop over host-sized row-major sets
+    SFD2_CHECK(!(p->ratio_mode & (SFD2_MATCH_HLOC_SCORES | SFD2_MATCH_I64)), SFD2_ERR_ARG,
+               "the fp32 CUDA-core mode writes int32 matches and raw similarities only");
+    long long off = 0;
+    for (int k = 0; k < npairs && !rc; ++k) {
+      SFD2_CHECK(pa[k] >= 0 && pa[k] < nsets && pb[k] >= 0 && pb[k] < nsets, SFD2_ERR_ARG, "match: pair %d refers to a set out of range", k);
+      const sfd2_desc_set &a = sets[pa[k]], &b = sets[pb[k]];
+      SFD2_CHECK(!a.count && !b.count && !a.ids && !b.ids && a.layout == SFD2_DESC_ROWS && b.layout == SFD2_DESC_ROWS, SFD2_ERR_ARG,
+                 "the fp32 CUDA-core mode takes host-sized [n,128] sets only (no device counts / ids / [128,n] layout)");
+      if (a.n > 0) rc = match_one_simt(c, a.data, a.n, b.data, b.n, SFD2_DESC_DIM, p, matches0 + off, sim0 + off, st);
+      off += a.n;
+    }
+  } else {
+    rc = match_pairs_tc(c, sets, nsets, pa, pb, npairs, p, matches0, sim0, st);
+  }
+  c->launches += g_launches - before;
+  return rc;
+}
+
 SFD2_API int sfd2_match_dev(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
                    int32_t* matches0, float* sim0, void* stream) {
   SFD2_CHECK(c && p && (n0 == 0 || (d0 && matches0 && sim0)) && (n1 == 0 || d1), SFD2_ERR_ARG, "sfd2_match_dev: NULL argument");
   SFD2_CHECK(n0 >= 0 && n1 >= 0 && d >= 1, SFD2_ERR_ARG, "sfd2_match_dev: bad shape %d x %d x %d", n0, n1, d);
-  SFD2_CHECK(p->precision >= 0 && p->precision <= 3, SFD2_ERR_ARG, "bad precision %d", p->precision);
-  SFD2_CUDA(cudaSetDevice(c->device));
-  int rc = ensure_match_ws(c, n0, n1);
+  int rc = check_match_params(p);
   if (rc) return rc;
-  const long long before = g_launches;
-  rc = match_one(c, d0, n0, d1, n1, d, p, matches0, sim0, static_cast<cudaStream_t>(stream));
-  c->launches += g_launches - before;
-  return rc;
+  if (n0 == 0) return SFD2_OK;
+  if (p->precision == SFD2_PREC_FP32) {
+    SFD2_CHECK(p->layout == SFD2_DESC_ROWS && !(p->ratio_mode & (SFD2_MATCH_HLOC_SCORES | SFD2_MATCH_I64)), SFD2_ERR_ARG,
+               "the fp32 CUDA-core mode takes [n,128] rows and writes int32 matches / raw similarities only");
+    SFD2_CUDA(cudaSetDevice(c->device));
+    const long long before = g_launches;
+    rc = match_one_simt(c, d0, n0, d1, n1, d, p, matches0, sim0, static_cast<cudaStream_t>(stream));
+    c->launches += g_launches - before;
+    return rc;
+  }
+  SFD2_CHECK(d == SFD2_DESC_DIM, SFD2_ERR_ARG, "match: descriptor dim must be 128 (got %d)", d);
+  const sfd2_desc_set sets[2] = {{d0, n0, p->layout, nullptr, nullptr}, {d1, n1, p->layout, nullptr, nullptr}};
+  const int32_t a = 0, b = 1;
+  return sfd2_match_pairs_dev(c, sets, 2, &a, &b, 1, p, matches0, sim0, stream);
 }
 
 SFD2_API int sfd2_match_batched_dev(sfd2_ctx* c, const float* d0, const int32_t* off0, const float* d1, const int32_t* off1,
                            int npairs, int d, const sfd2_match_params* p, int32_t* matches0, float* sim0, void* stream) {
   SFD2_CHECK(c && p && off0 && off1 && npairs >= 0, SFD2_ERR_ARG, "sfd2_match_batched_dev: bad argument");
-  SFD2_CUDA(cudaSetDevice(c->device));
-  int mx0 = 0, mx1 = 0;
+  SFD2_CHECK(d == SFD2_DESC_DIM, SFD2_ERR_ARG, "match: descriptor dim must be 128 (got %d)", d);
+  std::vector<sfd2_desc_set> sets(2 * (size_t)npairs);
+  std::vector<int32_t> pa(npairs), pb(npairs);
   for (int i = 0; i < npairs; ++i) {
     SFD2_CHECK(off0[i + 1] >= off0[i] && off1[i + 1] >= off1[i], SFD2_ERR_ARG, "offsets must be non-decreasing");
-    mx0 = std::max(mx0, off0[i + 1] - off0[i]);
-    mx1 = std::max(mx1, off1[i + 1] - off1[i]);
+    sets[2 * i] = sfd2_desc_set{d0 + (size_t)off0[i] * d, off0[i + 1] - off0[i], SFD2_DESC_ROWS, nullptr, nullptr};
+    sets[2 * i + 1] = sfd2_desc_set{d1 + (size_t)off1[i] * d, off1[i + 1] - off1[i], SFD2_DESC_ROWS, nullptr, nullptr};
+    pa[i] = 2 * i; pb[i] = 2 * i + 1;
   }
-  int rc = ensure_match_ws(c, mx0, mx1);
-  if (rc) return rc;
-  const long long before = g_launches;
-  for (int i = 0; i < npairs && !rc; ++i)
-    rc = match_one(c, d0 + (size_t)off0[i] * d, off0[i + 1] - off0[i], d1 + (size_t)off1[i] * d, off1[i + 1] - off1[i],
-                   d, p, matches0 + off0[i], sim0 + off0[i], static_cast<cudaStream_t>(stream));
-  c->launches += g_launches - before;
-  return rc;
+  if (npairs == 0) return SFD2_OK;
+  // outputs are indexed like d0: pair i's rows start at off0[i] - off0[0] = the packed offset when off0[0] == 0
+  return sfd2_match_pairs_dev(c, sets.data(), 2 * npairs, pa.data(), pb.data(), npairs, p, matches0 + off0[0], sim0 + off0[0], stream);
 }
 
 SFD2_API int sfd2_match_one_to_many_dev(sfd2_ctx* c, const float* q, int nq, const float* db, const int32_t* db_off,
                                         int ndb, int d, const sfd2_match_params* p, int32_t* matches0, float* sim0,
                                         void* stream) {
   SFD2_CHECK(c && p && q && db && db_off && matches0 && sim0, SFD2_ERR_ARG, "sfd2_match_one_to_many_dev: NULL argument");
-  SFD2_CHECK(nq >= 1 && ndb >= 1 && d == 128, SFD2_ERR_ARG, "sfd2_match_one_to_many_dev: bad shape (d must be 128)");
-  SFD2_CHECK(p->ratio_threshold <= 0.f, SFD2_ERR_ARG, "ratio tests are not available in the grouped call: use sfd2_match_batched_dev");
-  SFD2_CUDA(cudaSetDevice(c->device));
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (p->precision == SFD2_PREC_FP32) {   // CUDA-core mode: plain loop
-    int rc = SFD2_OK;
-    for (int i = 0; i < ndb && !rc; ++i)
-      rc = sfd2_match_dev(c, q, nq, db + (size_t)db_off[i] * d, db_off[i + 1] - db_off[i], d, p, matches0 + (size_t)i * nq,
-                          sim0 + (size_t)i * nq, stream);
-    return rc;
-  }
-  std::vector<int> seg(3 * (ndb + 1));
-  int P1 = 0;
+  SFD2_CHECK(nq >= 1 && ndb >= 1 && d == SFD2_DESC_DIM, SFD2_ERR_ARG, "sfd2_match_one_to_many_dev: bad shape (d must be 128)");
+  std::vector<sfd2_desc_set> sets(1 + (size_t)ndb);
+  std::vector<int32_t> pa(ndb, 0), pb(ndb);
+  sets[0] = sfd2_desc_set{q, nq, SFD2_DESC_ROWS, nullptr, nullptr};
   for (int i = 0; i < ndb; ++i) {
     SFD2_CHECK(db_off[i + 1] >= db_off[i], SFD2_ERR_ARG, "offsets must be non-decreasing");
-    seg[i] = db_off[i];
-    seg[(ndb + 1) + i] = P1;
-    seg[2 * (ndb + 1) + i] = db_off[i + 1] - db_off[i];
-    P1 += round_up(std::max(db_off[i + 1] - db_off[i], 1), 128);
+    sets[1 + i] = sfd2_desc_set{db + (size_t)db_off[i] * d, db_off[i + 1] - db_off[i], SFD2_DESC_ROWS, nullptr, nullptr};
+    pb[i] = 1 + i;
   }
-  seg[ndb] = db_off[ndb];
-  seg[(ndb + 1) + ndb] = P1;
-  // workspace: keys [max(nq*ndb, P1)], split planes [(nq_pad + P1) * 2 * 128] halves, segment table
-  const size_t need_keys = std::max((size_t)nq * ndb, (size_t)P1) + 128;
-  if (need_keys > c->key_cap) {
-    cudaFree(c->row_key); cudaFree(c->col_key); cudaFree(c->row2); cudaFree(c->col2);
-    c->row_key = c->col_key = nullptr; c->row2 = c->col2 = nullptr; c->key_cap = 0;
-    SFD2_CUDA(cudaMalloc(&c->row_key, need_keys * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMalloc(&c->col_key, need_keys * sizeof(unsigned long long)));
-    SFD2_CUDA(cudaMalloc(&c->row2, need_keys * sizeof(unsigned)));
-    SFD2_CUDA(cudaMalloc(&c->col2, need_keys * sizeof(unsigned)));
-    c->key_cap = need_keys;
-  }
-  const size_t hneed = 2 * ((size_t)round_up(nq, 128) + P1) * 128;
-  if (hneed > c->mhalf_cap) {
-    cudaFree(c->mhalf); c->mhalf = nullptr; c->mhalf_cap = 0;
-    SFD2_CUDA(cudaMalloc(&c->mhalf, hneed * sizeof(__half)));
-    c->mhalf_cap = hneed;
-  }
-  if (seg.size() > c->seg_cap) {
-    cudaFree(c->seg_dev); c->seg_dev = nullptr; c->seg_cap = 0;
-    SFD2_CUDA(cudaMalloc(&c->seg_dev, seg.size() * sizeof(int)));
-    c->seg_cap = seg.size();
-  }
-  SFD2_CUDA(cudaMemcpyAsync(c->seg_dev, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  const long long before = g_launches;
-  const int rc = launch_match_one_to_many(q, nq, db, c->seg_dev, ndb, P1, p->precision != SFD2_PREC_TC_FAST ? 3 : 1,
-                                          p->do_mutual_check, p->distance_threshold, c->mhalf, c->row_key, c->col_key,
-                                          matches0, sim0, c->num_sms, st);
-  c->launches += g_launches - before;
-  return rc;
+  return sfd2_match_pairs_dev(c, sets.data(), 1 + ndb, pa.data(), pb.data(), ndb, p, matches0, sim0, stream);
 }
 
 SFD2_API int sfd2_match_host(sfd2_ctx* c, const float* d0, int n0, const float* d1, int n1, int d, const sfd2_match_params* p,
@@ -707,21 +880,24 @@ SFD2_API int sfd2_nms_select_dev(sfd2_ctx* c, const float* heat, int h, int w, c
   while (cap2 < cap) cap2 <<= 1;
   unsigned long long *cand = nullptr, *scratch = nullptr;
   int *counter = nullptr, *status = nullptr;
-  SFD2_CUDA(cudaMalloc(&cand, (size_t)cap * 8));
-  SFD2_CUDA(cudaMalloc(&scratch, (size_t)cap2 * 8));
-  SFD2_CUDA(cudaMalloc(&counter, 4));
-  SFD2_CUDA(cudaMalloc(&status, 4));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  SFD2_CUDA(cudaMemsetAsync(status, 0, 4, st));
-  SFD2_CUDA(cudaMemsetAsync(scratch, 0, (size_t)cap2 * 8, st));
+  int hstatus = 0, rc = SFD2_OK;
   const long long before = g_launches;
-  int rc = launch_nms(heat, h, w, p->conf_th, p->border, p->border_w > 0 ? p->border_w : w, p->border_h > 0 ? p->border_h : h,
-                      nms_out, cand, cap, counter, st);
-  if (!rc) rc = launch_select(cand, cap, counter, w, p->topk, kpts, scores, count, status, scratch, st);
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && !rc) { set_error("sfd2_nms_select_dev: %s -> %s", what, cudaGetErrorString(e)); rc = SFD2_ERR_CUDA; }
+    return e == cudaSuccess;
+  };
+  if (ck(cudaMalloc(&cand, (size_t)cap * 8), "cudaMalloc(cand)") && ck(cudaMalloc(&scratch, (size_t)cap2 * 8), "cudaMalloc(scratch)") &&
+      ck(cudaMalloc(&counter, 4), "cudaMalloc(counter)") && ck(cudaMalloc(&status, 4), "cudaMalloc(status)") &&
+      ck(cudaMemsetAsync(status, 0, 4, st), "memset(status)") && ck(cudaMemsetAsync(scratch, 0, (size_t)cap2 * 8, st), "memset(scratch)")) {
+    rc = launch_nms(heat, h, w, p->conf_th, p->border, p->border_w > 0 ? p->border_w : w, p->border_h > 0 ? p->border_h : h,
+                    nms_out, cand, cap, counter, st);
+    if (!rc) rc = launch_select(cand, cap, counter, w, p->topk, kpts, scores, count, status, scratch, st);
+    ck(cudaMemcpyAsync(&hstatus, status, 4, cudaMemcpyDeviceToHost, st), "copy(status)");
+  }
+  // the private buffers must outlive the kernels: synchronise (also on the error paths) before freeing them
+  ck(cudaStreamSynchronize(st), "cudaStreamSynchronize");
   c->launches += g_launches - before;
-  int hstatus = 0;
-  cudaMemcpyAsync(&hstatus, status, 4, cudaMemcpyDeviceToHost, st);
-  cudaStreamSynchronize(st);
   cudaFree(cand); cudaFree(scratch); cudaFree(counter); cudaFree(status);
   if (!rc && hstatus) { set_error("candidate overflow (cap %d)", cap); rc = SFD2_ERR_OVERFLOW; }
   return rc;

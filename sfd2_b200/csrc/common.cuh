@@ -106,11 +106,6 @@ int launch_sample(const float* desc_map, int H4, int W4, int H, int W, const flo
 // match.cu
 int launch_match_simt(const float* d0, int n0, const float* d1, int n1, int d, unsigned long long* row_key,
                       unsigned long long* col_key, cudaStream_t st);
-int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int split, __half* ws_half,
-                    unsigned long long* row_key, unsigned long long* col_key, int num_sms, cudaStream_t st);
-int launch_match_one_to_many(const float* q, int nq, const float* db, const int* seg_dev, int nseg, int P1, int split,
-                             int mutual, float dist_th, __half* ws_half, unsigned long long* row_key,
-                             unsigned long long* col_key, int32_t* matches0, float* sim0, int num_sms, cudaStream_t st);
 int launch_match_second(const float* d0, int n0, const float* d1, int n1, int d, const unsigned long long* row_key,
                         const unsigned long long* col_key, unsigned* row2, unsigned* col2, cudaStream_t st);
 int launch_match_finish(const unsigned long long* row_key, const unsigned long long* col_key, int n0, int n1,

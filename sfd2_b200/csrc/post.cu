@@ -264,6 +264,11 @@ select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* _
     n = cap;
   }
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *count_out = (topk > 0 && topk < n) ? topk : n;
+  // rows beyond the count read zero (sample_kernel does the same for the descriptors): callers need no memset
+  if (blockIdx.y == 0)
+    for (int r = ((topk > 0 && topk < n) ? topk : n) + blockIdx.x * SEL_THREADS + threadIdx.x; r < topk; r += gridDim.x * SEL_THREADS) {
+      kpts[2 * r] = 0.f; kpts[2 * r + 1] = 0.f; scores[r] = 0.f;
+    }
   const int nchunks = (n + SEL_CHUNK - 1) / SEL_CHUNK;
   const int active_y = min(nchunks, (int)gridDim.y);
   if (blockIdx.x * SEL_THREADS >= n || (int)blockIdx.y >= active_y) return;

@@ -1,20 +1,31 @@
-// Mutual-NN matcher on tcgen05: sim = D0 * D1^T as a K-major x K-major GEMM (K = 128) whose
-// epilogue reduces every 128 x 128 accumulator tile straight into the per-row / per-column
-// arg-max keys of match.cu - the similarity matrix never exists in HBM.
+// Mutual-NN matcher on tcgen05 (hloc/matchers/nearest_neighbor.py:6-57, it_loc/matcher.py:122-194).
 //
-// Operands are the fp16 hi/lo split of the fp32 descriptors (unit-norm rows, so hi+lo carries
-// ~22 bits): split==3 issues d0_hi*d1_hi + d0_hi*d1_lo + d0_lo*d1_hi into one fp32 accumulator,
-// which reproduces the fp32 reference arg-max on real SFD2 descriptors;
-// split==1 is the single-pass fp16 variant.
+// sim = D0 * D1^T is ONE K-major x K-major GEMM (K = 128) per pair; the epilogue reduces every 128 x 128 accumulator
+// tile straight into 64-bit arg-max keys, so the similarity matrix never exists in HBM:
+//   * rows    (TMEM lane = row): thread-local running (best, index [, second best]) along the CTA's strip of tiles,
+//             merged into keys[] with one atomicMax per row per strip;
+//   * columns (TMEM column = column): a THRESHOLD FILTER - every thread compares its 64 values with the column's current
+//             best (keys[] as of the tile's start, staged in shared memory): 1 compare + 1 vote per column.  Only columns
+//             where some row of the warp reaches the threshold take the slow path: warp arg-max (redux.sync + ballot,
+//             lowest row wins ties) and ONE atomicMax.  After a column has seen a few hundred rows that is a handful of
+//             columns per tile.  (Round 1 ran the transposed product D1 * D0^T as a second GEMM to make the column
+//             reduction thread-local: twice the tensor work, which capped the kernel at 1/6 of the pipe in exact mode.)
+//   * ratio tests need the SECOND best of every row and column (topk(2), nearest_neighbor.py:7): those configurations run
+//             both products with the thread-local (best, second) reduction on each - still tensor cores, no CUDA-core pass.
+//   * the mutual check / thresholds / index remap run in the tail of the CTA that completes a pair's last tile.
 //
-// Each CTA owns a CONTIGUOUS range of tiles in row-major order and keeps the A row-block (both K halves, hi and lo
-// planes: 64 KB) resident in shared memory while it walks along the columns; only the B tiles stream through the
-// stage ring.  The first version reloaded A for every tile and was bound by L2->SM bandwidth (128 KB per 1536 MMA
-// cycles per SM, ncu: tensor pipe 42 % active).
+// One launch serves MANY pairs: a table of descriptor sets (operands) and of (set a, set b) problems; tiles of all
+// problems form one list cut into contiguous per-CTA ranges.  Set sizes may live in DEVICE memory (the extractor's counts),
+// so an extract -> match pipeline never synchronises with the host.
+//
+// Operands are the fp16 hi/lo split of the fp32 descriptors (unit-norm rows: hi + lo carries ~22 bits), written by
+// match_prep_kernel from either layout ([n,128] rows or hloc's [128,n]); split==3 issues a_hi*b_hi + a_hi*b_lo + a_lo*b_hi
+// into one fp32 accumulator, which reproduces the fp32 reference arg-max on real SFD2 descriptors; split==1 is single-pass.
 #include <math_constants.h>
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tc_match.cuh"
 
 namespace sfd2 {
 
@@ -24,437 +35,574 @@ __device__ __forceinline__ unsigned m_ord_f32(float f) {
   const unsigned u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float m_unord_f32(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
 __device__ __forceinline__ unsigned long long m_key(float sim, int idx) {
   return ((unsigned long long)m_ord_f32(sim) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)idx);
 }
+__device__ __forceinline__ int m_key_idx(unsigned long long k) { return (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)); }
+__device__ __forceinline__ float m_key_sim(unsigned long long k) { return m_unord_f32((unsigned)(k >> 32)); }
 
-// fp32 rows [n][128] -> fp16 hi / lo rows [n_pad][128] (rows >= n are zero)
-__global__ void split_rows_kernel(const float* __restrict__ src, int n, int n_pad, __half* __restrict__ hi,
-                                  __half* __restrict__ lo) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
-  if (idx >= n_pad * 32) return;
-  const int r = idx >> 5;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < n) v = __ldg(reinterpret_cast<const float4*>(src) + idx);
-  const float x[4] = {v.x, v.y, v.z, v.w};
-  __align__(8) __half h[4];
-  __align__(8) __half l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2half_rn(x[j]);
-    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ prep
+// ids -> order-preserving compaction table (desc_db[db_3D_ids != -1], it_loc/localize_cv2.py:540-555): one block per
+// operand with ids; remap[prow0 + k] = k-th row whose id != -1, efflen = number of such rows.
+__global__ void __launch_bounds__(1024)
+match_scan_ids_kernel(const MOperD* __restrict__ opers, int noper, int* __restrict__ efflen, int* __restrict__ remap) {
+  __shared__ int warp_sums[32];
+  __shared__ int base;
+  for (int o = blockIdx.x; o < noper; o += gridDim.x) {
+    const MOperD op = opers[o];
+    if (!op.ids) continue;
+    int n = op.cap;
+    if (op.count) n = min(n, max(0, *op.count));
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < n; r0 += blockDim.x) {
+      const int r = r0 + threadIdx.x;
+      const int valid = (r < n && op.ids[r] != -1) ? 1 : 0;
+      const unsigned b = __ballot_sync(0xffffffffu, valid);
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      if (lane == 0) warp_sums[w] = __popc(b);
+      __syncthreads();
+      int woff = 0;
+      for (int k = 0; k < w; ++k) woff += warp_sums[k];
+      const int pos = base + woff + __popc(b & ((1u << lane) - 1u));
+      if (valid) remap[op.prow0 + pos] = r;
+      __syncthreads();
+      if (threadIdx.x == blockDim.x - 1) base = pos + valid;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) efflen[o] = base;
+    __syncthreads();
   }
-  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
-  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
 }
 
-// both operands of a pair in one launch, plus the reset of the arg-max keys (saves two launches and two memsets)
-__global__ void split_rows2_kernel(const float* __restrict__ src0, int n0, int n0p, __half* __restrict__ hi0,
-                                   __half* __restrict__ lo0, const float* __restrict__ src1, int n1, int n1p,
-                                   __half* __restrict__ hi1, __half* __restrict__ lo1,
-                                   unsigned long long* __restrict__ key0, unsigned long long* __restrict__ key1) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
-  if (idx >= (n0p + n1p) * 32) return;
-  const bool second = idx >= n0p * 32;
-  if (second) idx -= n0p * 32;
-  const float* src = second ? src1 : src0;
-  const int n = second ? n1 : n0;
-  __half* hi = second ? hi1 : hi0;
-  __half* lo = second ? lo1 : lo0;
-  unsigned long long* key = second ? key1 : key0;
-  const int r = idx >> 5;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < n) {
-    v = __ldg(reinterpret_cast<const float4*>(src) + idx);
-    if ((idx & 31) == 0) key[r] = 0ull;
-  }
-  const float x[4] = {v.x, v.y, v.z, v.w};
-  __align__(8) __half h[4];
-  __align__(8) __half l[4];
+// fp32 descriptors -> fp16 hi / lo plane rows [prow][128] (rows >= the set's effective length are zero up to the next
+// multiple of 128), key / second-best / done-counter reset, effective lengths.  Block = 256 threads = 32 plane rows.
+__global__ void __launch_bounds__(256)
+match_prep_kernel(const MOperD* __restrict__ opers, int noper, int total_prows, __half* __restrict__ hi,
+                  __half* __restrict__ lo, const int* __restrict__ remap, int* __restrict__ efflen,
+                  unsigned long long* __restrict__ keys, unsigned* __restrict__ sec, long long nkeys,
+                  int* __restrict__ done, int nprob) {
+  __shared__ float tile[128][33];
+  pdl_launch_dependents();   // the matcher kernel may start its prologue; it waits (griddepcontrol.wait) before reading
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+  for (long long i = gtid; i < nkeys; i += gsz) { keys[i] = 0ull; if (sec) sec[i] = 0u; }
+  for (int i = gtid; i < nprob; i += gsz) done[i] = 0;
+  for (int g = blockIdx.x; g < total_prows / 32; g += gridDim.x) {
+    const int R0 = g * 32;
+    int a = 0, b = noper - 1;
+    while (a < b) { const int mid = (a + b + 1) >> 1; if (opers[mid].prow0 <= R0) a = mid; else b = mid - 1; }
+    const MOperD op = opers[a];
+    int n = op.cap;
+    if (op.ids) n = efflen[a];                            // written by match_scan_ids_kernel (earlier launch)
+    else if (op.count) n = min(n, max(0, *op.count));
+    if (!op.ids && R0 == op.prow0 && threadIdx.x == 0) efflen[a] = n;
+    const int l0 = R0 - op.prow0;                         // first local row of this group
+    if (l0 >= ((n + 127) & ~127)) continue;               // beyond the last tile any kernel will touch
+    if (op.layout == 0) {
+      // [n][128] rows: thread -> (row = tid / 32, 4 consecutive k), 8 rows per sweep
+      for (int rr = threadIdx.x >> 5; rr < 32; rr += 8) {
+        const int l = l0 + rr, kq = threadIdx.x & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (l < n) {
+          const int sr = op.ids ? remap[op.prow0 + l] : l;
+          v = __ldg(reinterpret_cast<const float4*>(op.src + (size_t)sr * op.rs) + kq);
+        }
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        __align__(8) __half h[4];
+        __align__(8) __half q[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2half_rn(x[j]);
-    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
+        for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); q[j] = __float2half_rn(x[j] - __half2float(h[j])); }
+        const size_t o = ((size_t)(R0 + rr) * 128 + kq * 4) / 4;
+        reinterpret_cast<uint2*>(hi)[o] = *reinterpret_cast<uint2*>(h);
+        reinterpret_cast<uint2*>(lo)[o] = *reinterpret_cast<uint2*>(q);
+      }
+    } else {
+      // hloc layout [128][n] (element (row r, k) at src[k * cs + r * rs], rs == 1): coalesced along r, transposed in smem
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+      const int l = l0 + lane;
+      const bool ok = l < n;
+      const int sr = ok ? (op.ids ? remap[op.prow0 + l] : l) : 0;
+      for (int k = w; k < 128; k += 8) tile[k][lane] = ok ? __ldg(op.src + (size_t)k * op.cs + (size_t)sr * op.rs) : 0.f;
+      __syncthreads();
+      const int rr = threadIdx.x >> 3, k0 = (threadIdx.x & 7) * 16;
+      __align__(16) __half h[16];
+      __align__(16) __half q[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x = tile[k0 + j][rr];
+        h[j] = __float2half_rn(x);
+        q[j] = __float2half_rn(x - __half2float(h[j]));
+      }
+      uint4* oh = reinterpret_cast<uint4*>(hi + (size_t)(R0 + rr) * 128 + k0);
+      uint4* ol = reinterpret_cast<uint4*>(lo + (size_t)(R0 + rr) * 128 + k0);
+      oh[0] = reinterpret_cast<const uint4*>(h)[0]; oh[1] = reinterpret_cast<const uint4*>(h)[1];
+      ol[0] = reinterpret_cast<const uint4*>(q)[0]; ol[1] = reinterpret_cast<const uint4*>(q)[1];
+      __syncthreads();
+    }
   }
-  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
-  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
 }
 
+// ------------------------------------------------------------------------------------------------ main kernel
 constexpr int TM_TILE = 128;
-constexpr int TM_OP_BYTES = 128 * 128;  // 128 rows x 64 fp16
-constexpr int TM_THREADS = 192;
-constexpr int TM_MAX_STAGES = 6;
+constexpr int TM_OP_BYTES = 128 * 128;   // 128 rows x 64 fp16 (one K half of one plane)
+constexpr int TM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int TM_EPI_THREADS = 256;
+constexpr int TM_ACC_BUFS = 4;           // 4 x 128 fp32 columns = the whole TMEM: the MMAs run up to three tiles ahead
+constexpr int TM_MAX_STAGES = 8;
 
-// One launch runs BOTH products: pass 0 = D0 * D1^T reduces its rows into p[0].row_key (the row arg-max), pass 1 =
-// D1 * D0^T reduces ITS rows (= the columns of the first product) into p[1].row_key (the column arg-max).  The GEMM is
-// ~3 us of tensor work either way; what costs is the epilogue, and a row reduction is thread-local (one TMEM lane = one
-// row) while a column reduction needs a shared-memory transpose plus 128 atomics per warp per tile - doing the cheap
-// reduction twice is ~2x faster than doing both at once.  The tiles of the two passes form one list that is cut into
-// contiguous per-CTA ranges, so there is one launch, one ramp and one tail.
-struct TcMatchPass {
-  int n0, n1, tiles_m, tiles_n;   // rows / columns of this pass's product and its tile grid
-  unsigned long long* row_key;
-};
-struct TcMatchArgs {
-  TcMatchPass p[2];
-  int split, stages, stage_bytes;
-  // one-to-many (pass 0 only): the B operand is a concatenation of nseg row segments, each padded to a multiple of
-  // 128 rows (seg_poff = padded starts, seg_len = valid rows); row keys are then kept per (segment, row): key index
-  // seg * n0 + i, column index local to the segment
-  int nseg;
-  const int* seg_poff;
-  const int* seg_len;
+struct TileInfo {
+  int p, pass, mt, nt;
+  int a_len, b_len;            // effective rows of the A / B operand of this pass
+  int a_prow, b_prow;          // first plane row of the A / B operand
+  long long ka, kb;            // key offsets of the A rows / B rows
+  int rb;                      // row-block identity within the launch (changes <=> the resident A operand changes)
+  bool skip;
 };
 
-__device__ __forceinline__ void tm_decode(const TcMatchArgs& a, int tile, int& pass, int& mt, int& nt) {
-  const int t0 = a.p[0].tiles_m * a.p[0].tiles_n;
-  pass = tile >= t0 ? 1 : 0;
-  const int t = pass ? tile - t0 : tile;
-  const int tn = a.p[pass].tiles_n;
-  mt = t / tn;
-  nt = t - mt * tn;
+// Linear tile -> (problem, pass, mt, nt).  Problems are laid out by their CAPACITY tile counts (host-known);
+// tiles beyond the effective extents (device-side counts) are skipped identically by all three warp roles.
+__device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, int& p_cache, TileInfo& t) {
+  int p = p_cache;
+  if (p < 0 || tile < a.probs[p].tile0 || tile >= a.probs[p].tile0 + a.probs[p].ntiles) {
+    int lo = 0, hi = a.nprob - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.probs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    p = lo;
+    p_cache = p;
+  }
+  const MProbD pr = a.probs[p];
+  int r = tile - pr.tile0;
+  const int t0 = pr.tm * pr.tn;
+  t.p = p;
+  t.pass = (r >= t0) ? 1 : 0;
+  if (t.pass) r -= t0;
+  const int tn = t.pass ? pr.tm : pr.tn;
+  t.mt = r / tn;
+  t.nt = r - t.mt * tn;
+  const int oa = t.pass ? pr.b : pr.a, ob = t.pass ? pr.a : pr.b;
+  t.a_len = a.efflen[oa]; t.b_len = a.efflen[ob];
+  t.a_prow = a.opers[oa].prow0; t.b_prow = a.opers[ob].prow0;
+  t.ka = t.pass ? pr.key_b : pr.key_a;
+  t.kb = t.pass ? pr.key_a : pr.key_b;
+  t.rb = pr.tile0 + (t.pass ? t0 : 0) + t.mt * tn;     // linear index of the strip's first tile: unique per (p, pass, mt)
+  t.skip = (t.mt * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
+}
+
+// Lowe ratio test on (best, second-best) similarity.  mode 1 = hloc find_nn (nearest_neighbor.py:8-11):
+// 2(1-s0) <= r^2 * 2(1-s1); mode 2 = it_loc (matcher.py:172-174): sqrt(2-2 s0) / (sqrt(2-2 s1) + 1e-8) <= r.
+// A missing second neighbour (only one candidate) passes.
+__device__ __forceinline__ bool tm_ratio_ok(float s0, unsigned second_ord, float r, int mode) {
+  if (second_ord == 0u) return true;
+  const float s1 = m_unord_f32(second_ord);
+  if (mode == 2) return sqrtf(2.f - 2.f * s0) / (sqrtf(2.f - 2.f * s1) + 1e-8f) <= r;
+  return 2.f * (1.f - s0) <= (r * r) * (2.f * (1.f - s1));
+}
+
+// Tail of a problem (run by the 256 epilogue threads of the CTA that completed its last tile): decode keys, ratio /
+// distance tests, mutual check, index remap -> matches0 / sim0.  Same decisions as match_finish_kernel (match.cu).
+__device__ void tm_finish(const TcMatchArgs& a, int p, int et) {
+  const MProbD pr = a.probs[p];
+  const int n0 = a.efflen[pr.a];
+  const int cap0 = a.opers[pr.a].cap;
+  const int* remap_b = a.opers[pr.b].ids ? a.remap + a.opers[pr.b].prow0 : nullptr;
+  // feature_matching (it_loc/localize_cv2.py:537-538): a db image with <= 3 keypoints that have a 3-D point yields no matches
+  const bool too_few = remap_b && a.efflen[pr.b] <= 3;
+  const volatile unsigned long long* rk = a.keys + pr.key_a;
+  const volatile unsigned long long* ck = a.keys + pr.key_b;
+  const volatile unsigned* rs = a.sec ? a.sec + pr.key_a : nullptr;
+  const volatile unsigned* cs = a.sec ? a.sec + pr.key_b : nullptr;
+  const bool plain = (a.ratio_mode & SFD2_MATCH_PLAIN_CODES) != 0;
+  const bool hloc_scores = (a.ratio_mode & SFD2_MATCH_HLOC_SCORES) != 0;
+  const bool i64 = (a.ratio_mode & SFD2_MATCH_I64) != 0;
+  const int rmode = a.ratio_mode & 0xFF;
+  for (int i = et; i < cap0; i += TM_EPI_THREADS) {
+    int m = -1;
+    float s = 0.f;
+    bool keep_score = false;
+    const unsigned long long k = (i < n0 && !too_few) ? rk[i] : 0ull;
+    if (k != 0ull) {
+      const int j = m_key_idx(k);
+      s = m_key_sim(k);
+      bool ok = true;
+      if (a.ratio_th > 0.f) ok = tm_ratio_ok(s, rs[i], a.ratio_th, rmode);
+      if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - s)) <= a.dist_th * a.dist_th;     // nearest_neighbor.py:8,12-13
+      const bool row_ok = ok;   // find_nn's own mask for this row (decides whether hloc keeps its score)
+      keep_score = row_ok;
+      if (ok && a.mutual) {
+        const unsigned long long kc = ck[j];
+        ok = (kc != 0ull) && (m_key_idx(kc) == i);                                      // mutual_check, :19-24
+        if (ok && a.ratio_th > 0.f) ok = tm_ratio_ok(m_key_sim(kc), cs[j], a.ratio_th, rmode);
+        if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - m_key_sim(kc))) <= a.dist_th * a.dist_th;
+      }
+      // -1: rejected by the row's own tests, -2: only by the mutual check; matches report ORIGINAL db rows (remap)
+      m = ok ? (remap_b ? remap_b[j] : j) : ((row_ok && !plain) ? -2 : -1);
+    }
+    // hloc's find_nn (nearest_neighbor.py:14-15): (sim + 1) / 2 where the row passed its own tests, else 0
+    if (hloc_scores) s = keep_score ? (s + 1.f) * 0.5f : 0.f;
+    if (i64) reinterpret_cast<long long*>(a.matches0)[pr.out_off + i] = (long long)m;
+    else a.matches0[pr.out_off + i] = m;
+    a.sim0[pr.out_off + i] = s;
+  }
 }
 
 __global__ void __launch_bounds__(TM_THREADS, 1)
-tc_match_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const __grid_constant__ TcMatchArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nops = (a.split == 3) ? 2 : 1;
-  uint8_t* aslot = smem;                                       // resident A: [kb][plane] x 16 KB
-  uint8_t* bring = smem + 2 * nops * TM_OP_BYTES;              // B ring: stage = [plane] x 16 KB of one K half
-  uint64_t* full = reinterpret_cast<uint64_t*>(bring + (size_t)a.stages * a.stage_bytes);
+  const int a_slot_bytes = 2 * nops * TM_OP_BYTES;                 // resident A: [kb][plane] x 16 KB, two slots
+  uint8_t* aslot = smem;
+  uint8_t* bring = smem + 2 * a_slot_bytes;                        // B ring: stage = one plane of one K half (16 KB)
+  uint8_t* tail = bring + (size_t)a.stages * TM_OP_BYTES;
+  unsigned long long* thr_key = reinterpret_cast<unsigned long long*>(tail);        // [2][128] column keys at tile start
+  float* thr_sim = reinterpret_cast<float*>(tail + 2048);                           // [2][128] their similarities
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail + 3072);
   uint64_t* empty = full + TM_MAX_STAGES;
   uint64_t* tfull = empty + TM_MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* afull = tempty + 2;
-  uint64_t* aempty = afull + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
+  uint64_t* tempty = tfull + TM_ACC_BUFS;
+  uint64_t* afull = tempty + TM_ACC_BUFS;
+  uint64_t* aempty = afull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
+  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA_hi);
-    prefetch_tmap(&tmB_hi);
-  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
-    mbar_init(afull, 1); mbar_init(aempty, 1);
+    for (int i = 0; i < TM_ACC_BUFS; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 256);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int num_tiles = a.p[0].tiles_m * a.p[0].tiles_n + a.p[1].tiles_m * a.p[1].tiles_n;
-  const int per_cta = (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per_cta = (a.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_begin = (int)blockIdx.x * per_cta;
-  const int tile_end = min(tile_begin + per_cta, num_tiles);
+  const int tile_end = min(tile_begin + per_cta, a.total_tiles);
+  pdl_wait();   // everything below reads what match_prep_kernel wrote (planes, effective lengths, zeroed keys)
 
   if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer (one elected lane)
     if (elect_one()) {
-      int stage = 0, prev_rb = -1;
-      uint32_t phase = 0, aphase = 0;
+      int stage = 0, prev_rb = -1, as = 0, pc = -1;
+      uint32_t phase = 0, aph = 0u;             // bit s of aph = phase of A slot s
+      TileInfo t;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int pass, mt, nt;
-        tm_decode(a, tile, pass, mt, nt);
-        const int rb = pass ? a.p[0].tiles_m + mt : mt;       // row-block id over both passes
-        const int r0 = mt * TM_TILE, c0 = nt * TM_TILE;
-        const CUtensorMap* ah = pass ? &tmB_hi : &tmA_hi;
-        const CUtensorMap* al = pass ? &tmB_lo : &tmA_lo;
-        const CUtensorMap* bh = pass ? &tmA_hi : &tmB_hi;
-        const CUtensorMap* bl = pass ? &tmA_lo : &tmB_lo;
-        if (rb != prev_rb) {                    // new row-block: (re)load the resident A operand
-          mbar_wait(aempty, aphase ^ 1);
-          mbar_expect_tx(afull, (uint32_t)(2 * nops * TM_OP_BYTES));
+        tm_locate(a, tile, pc, t);
+        if (t.skip) continue;
+        if (t.rb != prev_rb) {                    // new strip: load its A operand into the other slot
+          if (prev_rb >= 0) as ^= 1;
+          mbar_wait(&aempty[as], ((aph >> as) & 1u) ^ 1u);
+          aph ^= 1u << as;
+          uint8_t* dst = aslot + (size_t)as * a_slot_bytes;
+          mbar_expect_tx(&afull[as], (uint32_t)a_slot_bytes);
           for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(aslot + (kb * nops) * TM_OP_BYTES, ah, afull, kb * 64, r0);
-            if (a.split == 3) tma_load_2d(aslot + (kb * nops + 1) * TM_OP_BYTES, al, afull, kb * 64, r0);
+            tma_load_2d(dst + (kb * nops) * TM_OP_BYTES, &tm_hi, &afull[as], kb * 64, t.a_prow + t.mt * TM_TILE);
+            if (nops == 2) tma_load_2d(dst + (kb * nops + 1) * TM_OP_BYTES, &tm_lo, &afull[as], kb * 64, t.a_prow + t.mt * TM_TILE);
           }
-          aphase ^= 1;
-          prev_rb = rb;
+          prev_rb = t.rb;
         }
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          uint8_t* sb = bring + (size_t)stage * a.stage_bytes;
-          mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
-          tma_load_2d(sb, bh, &full[stage], kb * 64, c0);
-          if (a.split == 3) tma_load_2d(sb + TM_OP_BYTES, bl, &full[stage], kb * 64, c0);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
-        }
+        for (int kb = 0; kb < 2; ++kb)
+          for (int pl = 0; pl < nops; ++pl) {     // one stage = one plane of one K half of the B tile (16 KB)
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sb = bring + (size_t)stage * TM_OP_BYTES;
+            mbar_expect_tx(&full[stage], (uint32_t)TM_OP_BYTES);
+            tma_load_2d(sb, pl ? &tm_lo : &tm_hi, &full[stage], kb * 64, t.b_prow + t.nt * TM_TILE);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
       }
     }
   } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer (one elected lane)
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      int stage = 0, buf = 0, prev_rb = -1;
-      uint32_t phase = 0, bphase = 0, aphase = 0;
+      int stage = 0, buf = 0, prev_rb = -1, as = 0, pc = -1, pc2 = -1;
+      uint32_t phase = 0, bphase = 0, aph = 0u;
+      TileInfo t, t2;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int pass, mt, nt;
-        tm_decode(a, tile, pass, mt, nt);
-        const int rb = pass ? a.p[0].tiles_m + mt : mt;
-        if (rb != prev_rb) {
-          mbar_wait(afull, aphase);
-          aphase ^= 1;
-          prev_rb = rb;
+        tm_locate(a, tile, pc, t);
+        if (t.skip) continue;
+        if (t.rb != prev_rb) {
+          if (prev_rb >= 0) as ^= 1;
+          mbar_wait(&afull[as], (aph >> as) & 1u);
+          aph ^= 1u << as;
+          prev_rb = t.rb;
         }
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < 2; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(aslot + (kb * nops) * TM_OP_BYTES);
-          const uint32_t sb = smem_u32(bring + (size_t)stage * a.stage_bytes);
-          const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
-          const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + TM_OP_BYTES);
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
-#pragma unroll 1
-          for (int pass_k = 0; pass_k < a.split; ++pass_k) {
-            const uint64_t da = (pass_k == 2) ? da_lo : da_hi;
-            const uint64_t db = (pass_k == 1) ? db_lo : db_hi;
+        const uint32_t abase = smem_u32(aslot + (size_t)as * a_slot_bytes);
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
+        for (int kb = 0; kb < 2; ++kb)
+          for (int pl = 0; pl < nops; ++pl) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = abase + (uint32_t)((kb * nops) * TM_OP_BYTES);
+            const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
+            const uint64_t db = make_desc_sw128(smem_u32(bring + (size_t)stage * TM_OP_BYTES));
+            if (pl == 0) {                          // b_hi: a_hi * b_hi, then (exact mode) a_lo * b_hi
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16(dcol, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (kb == 0 && pass_k == 0 && k == 0) ? 0u : 1u);
+              for (int k = 0; k < 4; ++k)
+                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+              if (nops == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, 1u);
+              }
+            } else {                                // b_lo: a_hi * b_lo
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&empty[stage]);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
-        }
         umma_commit(&tfull[buf]);
-        // last tile of this row-block (or of the CTA): the resident A may be replaced once these MMAs are done
-        bool last_of_rb = (tile + 1 == tile_end);
-        if (!last_of_rb) {
-          int p2, m2, n2;
-          tm_decode(a, tile + 1, p2, m2, n2);
-          last_of_rb = (p2 ? a.p[0].tiles_m + m2 : m2) != rb;
+        // last non-skipped tile of this strip within the CTA's range: its A slot may be refilled once these MMAs are done
+        bool last_of_rb = true;
+        for (int nx = tile + 1; nx < tile_end; ++nx) {
+          tm_locate(a, nx, pc2, t2);
+          if (t2.skip) continue;
+          last_of_rb = (t2.rb != t.rb);
+          break;
         }
-        if (last_of_rb) umma_commit(aempty);
-        if (++buf == 2) { buf = 0; bphase ^= 1; }
+        if (last_of_rb) umma_commit(&aempty[as]);
+        if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
       }
     }
   } else {
-    const int q = warp & 3;
-    int buf = 0;
+    // ---------------------------------------------------------------- epilogue (warps 2..9)
+    // warp (q, h): TMEM lanes 32q.. (q = warp % 4, the hardware's lane-quarter rule), columns [64h, 64h + 64) of each tile
+    const int et = (int)threadIdx.x - 64;
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const bool top2 = a.passes == 2;
+    int buf = 0, pc = -1, par = 0;
     uint32_t bphase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-      int pass, mt, nt;
-      tm_decode(a, tile, pass, mt, nt);
-      const int r0 = mt * TM_TILE;
-      int c0 = nt * TM_TILE;
-      const int i = r0 + q * 32 + lane;
-      const int rows = a.p[pass].n0;
-      int n1 = a.p[pass].n1, seg = 0;
-      if (pass == 0 && a.nseg > 0) {            // which segment does this column block belong to?
-        int lo = 0, hi = a.nseg - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(a.seg_poff + mid) <= c0) lo = mid; else hi = mid - 1; }
-        seg = lo;
-        c0 -= __ldg(a.seg_poff + seg);          // column index local to the segment
-        n1 = __ldg(a.seg_len + seg);
+    int cur_rb = -1, cur_p = -1, p_tiles = 0;
+    long long cur_ka = 0;
+    int cur_i = 0;
+    bool cur_valid = false;
+    float rbest = -CUDART_INF_F, rsec = -CUDART_INF_F;
+    int rbest_j = -1;
+    TileInfo t;
+
+    auto flush_rows = [&]() {          // merge this thread's strip result into the row keys
+      if (cur_rb >= 0 && cur_valid && rbest_j >= 0) {
+        const unsigned long long key = m_key(rbest, rbest_j);
+        const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i, key);
+        if (top2) {
+          // every partial best except the final winner loses exactly one atomicMax: it is a second-best candidate
+          float cand = rsec;
+          if (old != 0ull) cand = fmaxf(cand, fminf(m_key_sim(old), rbest));
+          if (cand > -CUDART_INF_F) atomicMax(a.sec + cur_ka + cur_i, m_ord_f32(cand));
+        }
       }
+      rbest = -CUDART_INF_F; rsec = -CUDART_INF_F; rbest_j = -1;
+    };
+    auto leave_problem = [&]() {       // count this CTA's tiles of problem cur_p; the CTA completing the problem finishes it
+      if (cur_p < 0) return;
+      __threadfence();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (et == 0) {
+        const int old = atomicAdd(a.done + cur_p, p_tiles);
+        *last_flag = (old + p_tiles == a.probs[cur_p].ntiles) ? 1 : 0;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (*last_flag) {
+        __threadfence();
+        tm_finish(a, cur_p, et);
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");    // last_flag is rewritten by the next problem
+      p_tiles = 0;
+    };
+
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      tm_locate(a, tile, pc, t);
+      if (t.p != cur_p) {
+        flush_rows();
+        cur_rb = -1;
+        leave_problem();
+        cur_p = t.p;
+      }
+      ++p_tiles;
+      if (t.skip) continue;
+      if (t.rb != cur_rb) {
+        flush_rows();
+        cur_rb = t.rb;
+        cur_ka = t.ka;
+        cur_i = t.mt * TM_TILE + q * 32 + lane;
+        cur_valid = cur_i < t.a_len;
+      }
+      const bool want_cols = a.cols && t.pass == 0;
+      const int c0 = t.nt * TM_TILE;
+      unsigned long long kc = 0ull;
+      if (want_cols && et < 128) kc = __ldcg(a.keys + t.kb + c0 + et);      // in flight while the MMAs finish
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128);
-      // the whole 128-column row of this lane in one go: four loads in flight, one wait (the epilogue, not the
-      // MMAs, bounds this kernel, and each tcgen05.ld -> wait round trip used to be paid four times per tile)
-      uint32_t v[4][32];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) tmem_ld32(taddr + ch * 32, v[ch]);
+      if (want_cols) {
+        if (et < 128) {
+          thr_key[par * 128 + et] = kc;
+          thr_sim[par * 128 + et] = kc ? m_key_sim(kc) : -CUDART_INF_F;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * 64);
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr, v0);
+      tmem_ld32(taddr + 32, v1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);   // the accumulator is in registers: the MMAs of tile + 2 may start
-      float rbest = -CUDART_INF_F;              // plain float compares in the loops; keys are built once per tile
-      int rbest_j = -1;
+      if (lane == 0) mbar_arrive(&tempty[buf]);   // this warp's share of the accumulator is in registers
+      float f[64];
+      const int cols_valid = t.b_len - c0 - h * 64;           // valid columns among this warp's 64
+      if (cols_valid >= 64 && cur_valid) {
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        const int jbase = c0 + ch * 32;
-        // row arg-max over this chunk's 32 columns (thread-local: one TMEM lane = one row).  A running
-        // "if (s > best)" chain is 128 dependent compare/select steps per tile and made the epilogue slower than
-        // the MMAs (ncu: IPC 0.9, tensor pipe 42 %); instead: tree max of the values, then tree min of the
-        // indices that attain it - lowest column wins among equal values, every step is independent.
-        const int cols_valid = min(32, n1 - jbase);
-        float f[32];
-        if (cols_valid >= 32) {
+        for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[ch][j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = (j < cols_valid) ? __uint_as_float(v[ch][j]) : -CUDART_INF_F;
+        for (int j = 0; j < 32; ++j) {
+          f[j] = (cur_valid && j < cols_valid) ? __uint_as_float(v0[j]) : -CUDART_INF_F;
+          f[32 + j] = (cur_valid && 32 + j < cols_valid) ? __uint_as_float(v1[j]) : -CUDART_INF_F;
         }
-        float m16[16], m8[8], m4[4];
+      }
+      // ---- rows: tree max of the values, then (only when it beats the running best) tree min of the indices attaining it
+      {
+        float m32[32], m16[16], m8[8], m4[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) m16[j] = fmaxf(f[2 * j], f[2 * j + 1]);
+        for (int j = 0; j < 32; ++j) m32[j] = fmaxf(f[2 * j], f[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) m16[j] = fmaxf(m32[2 * j], m32[2 * j + 1]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) m8[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
         const float cmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        if (cols_valid > 0 && cmax > rbest) {     // strict: an equal value in a later chunk keeps the earlier column
-          int i16[16], i8[8], i4[4];
+        if (top2) {
+          // second best of this tile = max over everything except ONE instance of the maximum
+          int amin = 64;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) i16[j] = min((f[2 * j] == cmax) ? 2 * j : 64, (f[2 * j + 1] == cmax) ? 2 * j + 1 : 64);
+          for (int j = 63; j >= 0; --j) amin = (f[j] == cmax) ? j : amin;
+          float s2 = -CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) s2 = fmaxf(s2, (j == amin) ? -CUDART_INF_F : f[j]);
+          if (cmax > rbest) {           // strict: an equal value in a later tile keeps the earlier column
+            rsec = fmaxf(rbest, fmaxf(rsec, s2));
+            rbest = cmax;
+            rbest_j = c0 + h * 64 + amin;
+          } else {
+            rsec = fmaxf(rsec, cmax);
+          }
+        } else if (cmax > rbest) {
+          int i32[32], i16[16], i8[8], i4[4];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) i32[j] = min((f[2 * j] == cmax) ? 2 * j : 64, (f[2 * j + 1] == cmax) ? 2 * j + 1 : 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) i16[j] = min(i32[2 * j], i32[2 * j + 1]);
 #pragma unroll
           for (int j = 0; j < 8; ++j) i8[j] = min(i16[2 * j], i16[2 * j + 1]);
 #pragma unroll
           for (int j = 0; j < 4; ++j) i4[j] = min(i8[2 * j], i8[2 * j + 1]);
           rbest = cmax;
-          rbest_j = jbase + min(min(i4[0], i4[1]), min(i4[2], i4[3]));
+          rbest_j = c0 + h * 64 + min(min(i4[0], i4[1]), min(i4[2], i4[3]));
         }
       }
-      if (i < rows && rbest_j >= 0) atomicMax(a.p[pass].row_key + (size_t)seg * rows + i, m_key(rbest, rbest_j));
-      if (++buf == 2) { buf = 0; bphase ^= 1; }
+      // ---- columns: threshold filter against the column's best so far; rare slow path = warp arg-max + one atomicMax
+      if (want_cols) {
+        const float* ts = thr_sim + par * 128 + h * 64;
+        const unsigned long long* tk = thr_key + par * 128 + h * 64;
+        unsigned long long* gk = a.keys + t.kb + c0 + h * 64;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; ++j4) {
+          const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
+          const float thv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = j4 * 4 + jj;
+            const bool pj = f[j] >= thv[jj] && f[j] > -CUDART_INF_F;
+            if (__any_sync(0xffffffffu, pj)) {
+              const unsigned s = pj ? m_ord_f32(f[j]) : 0u;
+              const unsigned mx = __reduce_max_sync(0xffffffffu, s);
+              const unsigned w = __ballot_sync(0xffffffffu, pj && s == mx);
+              if (lane == __ffs(w) - 1) {                        // lowest row of the warp among equal maxima
+                const unsigned long long key = ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cur_i);
+                if (key > tk[j]) atomicMax(gk + j, key);
+              }
+            }
+          }
+        }
+        par ^= 1;
+      }
+      if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
     }
+    flush_rows();
+    leave_problem();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 256);
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-static size_t tm_smem_bytes(int split, int stages) {
-  return (size_t)2 * (split == 3 ? 2 : 1) * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES * (split == 3 ? 2 : 1) + 1024 + 256;
+// ------------------------------------------------------------------------------------------------ host side
+constexpr size_t TM_TAIL_BYTES = 3072 + 512;      // thresholds + barriers
+
+size_t tm_smem_bytes(int split, int stages) {
+  const int nops = split == 3 ? 2 : 1;
+  return 1024 + (size_t)2 * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
 }
 
-// ws_half must hold 2 * (n0_pad + n1_pad) * 128 halves (n*_pad = n* rounded up to 128)
-int launch_match_tc(const float* d0, int n0, const float* d1, int n1, int d, int split, __half* ws_half,
-                    unsigned long long* row_key, unsigned long long* col_key, int num_sms, cudaStream_t st) {
-  SFD2_CHECK(d == 128, SFD2_ERR_ARG, "match_tc: descriptor dim must be 128 (got %d)", d);
-  if (n0 <= 0 || n1 <= 0) {   // degenerate: every row is unmatched
-    SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)(n0 > 0 ? n0 : 1), st));
-    SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)(n1 > 0 ? n1 : 1), st));
-    return SFD2_OK;
-  }
-  const int n0p = round_up(n0, TM_TILE), n1p = round_up(n1, TM_TILE);
-  __half* a_hi = ws_half;
-  __half* a_lo = a_hi + (size_t)n0p * 128;
-  __half* b_hi = a_lo + (size_t)n0p * 128;
-  __half* b_lo = b_hi + (size_t)n1p * 128;
-  split_rows2_kernel<<<cdiv((n0p + n1p) * 32, 256), 256, 0, st>>>(d0, n0, n0p, a_hi, a_lo, d1, n1, n1p, b_hi, b_lo, row_key, col_key);
-  ++g_launches;
-  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
-  const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
+int tm_stages(int split) {
+  const int nops = split == 3 ? 2 : 1;
+  const size_t fixed = 1024 + (size_t)2 * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
+  int s = (int)((227 * 1024 - fixed) / (size_t)TM_OP_BYTES);
+  return s > TM_MAX_STAGES ? TM_MAX_STAGES : s;
+}
+
+int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows) {
+  const uint64_t dims[2] = {128, (uint64_t)rows};
   const uint64_t strides[1] = {256};
-  {
-    const uint64_t dims[2] = {128, (uint64_t)n0p};
-    int rc = make_tmap_f16(&tA_hi, a_hi, 2, dims, strides, box);
-    if (rc) return rc;
-    rc = make_tmap_f16(&tA_lo, a_lo, 2, dims, strides, box);
-    if (rc) return rc;
+  const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
+  return make_tmap_f16(tm, base, 2, dims, strides, box);
+}
+
+int launch_match_prep(const MOperD* opers_dev, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
+                      int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
+                      int num_sms, cudaStream_t st) {
+  if (any_ids) {
+    match_scan_ids_kernel<<<noper < 4 * num_sms ? noper : 4 * num_sms, 1024, 0, st>>>(opers_dev, noper, efflen, remap);
+    ++g_launches;
   }
-  {
-    const uint64_t dims[2] = {128, (uint64_t)n1p};
-    int rc = make_tmap_f16(&tB_hi, b_hi, 2, dims, strides, box);
-    if (rc) return rc;
-    rc = make_tmap_f16(&tB_lo, b_lo, 2, dims, strides, box);
-    if (rc) return rc;
-  }
-  TcMatchArgs a{};
-  a.p[0] = TcMatchPass{n0, n1, n0p / TM_TILE, n1p / TM_TILE, row_key};
-  a.p[1] = TcMatchPass{n1, n0, n1p / TM_TILE, n0p / TM_TILE, col_key};
-  a.split = split;
-  a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
-  a.stages = 4;
-  const size_t smem = tm_smem_bytes(split, a.stages);
-  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = 2 * a.p[0].tiles_m * a.p[0].tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
+  int blocks = total_prows / 32;
+  if (blocks > 8 * num_sms) blocks = 8 * num_sms;
+  if (blocks < 1) blocks = 1;
+  match_prep_kernel<<<blocks, 256, 0, st>>>(opers_dev, noper, total_prows, hi, lo, remap, efflen, keys, sec, nkeys, done, nprob);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
 }
 
-// rows of `nseg` segments (unpadded starts `off`, padded starts `poff`) -> fp16 hi / lo rows in the padded layout
-__global__ void split_rows_seg_kernel(const float* __restrict__ src, const int* __restrict__ off,
-                                      const int* __restrict__ poff, int nseg, int total_padded,
-                                      __half* __restrict__ hi, __half* __restrict__ lo) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 elements
-  if (idx >= total_padded * 32) return;
-  const int r = idx >> 5;
-  int a = 0, b = nseg - 1;
-  while (a < b) { const int mid = (a + b + 1) >> 1; if (__ldg(poff + mid) <= r) a = mid; else b = mid - 1; }
-  const int local = r - __ldg(poff + a), len = __ldg(off + a + 1) - __ldg(off + a);
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (local < len) v = __ldg(reinterpret_cast<const float4*>(src) + (size_t)(__ldg(off + a) + local) * 32 + (idx & 31));
-  const float x[4] = {v.x, v.y, v.z, v.w};
-  __align__(8) __half h[4];
-  __align__(8) __half l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    h[j] = __float2half_rn(x[j]);
-    l[j] = __float2half_rn(x[j] - __half2float(h[j]));
-  }
-  reinterpret_cast<uint2*>(hi)[idx] = *reinterpret_cast<uint2*>(h);
-  reinterpret_cast<uint2*>(lo)[idx] = *reinterpret_cast<uint2*>(l);
-}
-
-// matches0[p*nq + i] = local column of segment p (or -1 / -2), sim0[p*nq + i] = best similarity
-__global__ void match_finish_seg_kernel(const unsigned long long* __restrict__ row_key,
-                                        const unsigned long long* __restrict__ col_key_padded,
-                                        const int* __restrict__ poff, int nq, int nseg, int mutual, float dist_th,
-                                        int32_t* __restrict__ matches0, float* __restrict__ sim0) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nq * nseg) return;
-  const int p = t / nq, i = t - p * nq;
-  const unsigned long long k = row_key[t];
-  if (k == 0ull) { matches0[t] = -1; sim0[t] = 0.f; return; }
-  const int j = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
-  const unsigned o = (unsigned)(k >> 32);
-  const float s = __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
-  bool ok = true;
-  if (dist_th > 0.f) ok = (2.f * (1.f - s)) <= dist_th * dist_th;
-  const bool row_ok = ok;
-  if (ok && mutual) {
-    const unsigned long long kc = col_key_padded[__ldg(poff + p) + j];
-    ok = (kc != 0ull) && ((int)(0xFFFFFFFFu - (unsigned)(kc & 0xFFFFFFFFull)) == i);
-  }
-  matches0[t] = ok ? j : (row_ok ? -2 : -1);
-  sim0[t] = s;
-}
-
-// One query set against many db sets in one grouped launch (it_loc/localize_cv2.py:705: a query against the <= 50
-// retrieved db images).  seg_dev: device ints [off(nseg+1) | poff(nseg+1) | len(nseg)]; P1 = total padded db rows.
-int launch_match_one_to_many(const float* q, int nq, const float* db, const int* seg_dev, int nseg, int P1, int split,
-                             int mutual, float dist_th, __half* ws_half, unsigned long long* row_key,
-                             unsigned long long* col_key, int32_t* matches0, float* sim0, int num_sms, cudaStream_t st) {
-  const int* off = seg_dev;
-  const int* poff = seg_dev + (nseg + 1);
-  const int* len = seg_dev + 2 * (nseg + 1);
-  SFD2_CUDA(cudaMemsetAsync(row_key, 0, sizeof(unsigned long long) * (size_t)nq * nseg, st));
-  SFD2_CUDA(cudaMemsetAsync(col_key, 0, sizeof(unsigned long long) * (size_t)P1, st));
-  const int nqp = round_up(nq, TM_TILE);
-  __half* a_hi = ws_half;
-  __half* a_lo = a_hi + (size_t)nqp * 128;
-  __half* b_hi = a_lo + (size_t)nqp * 128;
-  __half* b_lo = b_hi + (size_t)P1 * 128;
-  split_rows_kernel<<<cdiv(nqp * 32, 256), 256, 0, st>>>(q, nq, nqp, a_hi, a_lo);
-  split_rows_seg_kernel<<<cdiv(P1 * 32, 256), 256, 0, st>>>(db, off, poff, nseg, P1, b_hi, b_lo);
-  g_launches += 2;
-  CUtensorMap tA_hi, tA_lo, tB_hi, tB_lo;
-  const uint32_t box[2] = {64u, (uint32_t)TM_TILE};
-  const uint64_t strides[1] = {256};
-  const uint64_t dq[2] = {128, (uint64_t)nqp}, dd[2] = {128, (uint64_t)P1};
-  int rc = make_tmap_f16(&tA_hi, a_hi, 2, dq, strides, box);
-  if (!rc) rc = make_tmap_f16(&tA_lo, a_lo, 2, dq, strides, box);
-  if (!rc) rc = make_tmap_f16(&tB_hi, b_hi, 2, dd, strides, box);
-  if (!rc) rc = make_tmap_f16(&tB_lo, b_lo, 2, dd, strides, box);
-  if (rc) return rc;
-  TcMatchArgs a{};
-  a.split = split;
-  a.stage_bytes = TM_OP_BYTES * (split == 3 ? 2 : 1);     // one K half of the B tile (hi [+ lo])
-  a.stages = 4;
-  // pass 0: rows = query, columns = padded db segments -> row_key[seg * nq + i];
-  // pass 1: rows = padded db rows, columns = query -> col_key[padded db row]
-  a.p[0] = TcMatchPass{nq, P1, nqp / TM_TILE, P1 / TM_TILE, row_key};
-  a.p[1] = TcMatchPass{P1, nq, P1 / TM_TILE, nqp / TM_TILE, col_key};
-  a.nseg = nseg; a.seg_poff = poff; a.seg_len = len;
-  const size_t smem = tm_smem_bytes(split, a.stages);
+int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st) {
+  a.stages = tm_stages(a.split);
+  const size_t smem = tm_smem_bytes(a.split, a.stages);
   SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = 2 * a.p[0].tiles_m * a.p[0].tiles_n;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  tc_match_kernel<<<grid, TM_THREADS, smem, st>>>(tA_hi, tA_lo, tB_hi, tB_lo, a);
-  ++g_launches;
-  match_finish_seg_kernel<<<cdiv(nq * nseg, 256), 256, 0, st>>>(row_key, col_key, poff, nq, nseg, mutual, dist_th, matches0, sim0);
+  if (a.total_tiles <= 0) return SFD2_OK;
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(TM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps match_prep_kernel's tail
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_match_kernel, tm_hi, tm_lo, a));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

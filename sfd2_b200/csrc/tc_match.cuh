@@ -1,0 +1,54 @@
+// Device-side tables of the grouped tcgen05 matcher (tc_match.cu) and its host launchers.
+#pragma once
+#include "common.cuh"
+
+namespace sfd2 {
+
+// One descriptor set = one GEMM operand.  Its fp16 hi / lo planes occupy rows [prow0, prow0 + round_up(cap, 128)).
+struct MOperD {
+  const float* src;       // device fp32 descriptors
+  long long rs, cs;       // element (row r, k) at src[r * rs + k * cs]
+  int layout;             // 0: [n][128] rows (cs == 1), 1: [128][n] (hloc, rs == 1)
+  int cap;                // rows (capacity when `count` is set)
+  int prow0;              // first plane row (multiple of 128)
+  int pad_;
+  const int* count;       // optional DEVICE row count (<= cap)
+  const int* ids;         // optional DEVICE int32 [cap]: rows with id == -1 are dropped (order-preserving compaction)
+};
+
+// One pair (set a, set b).  Tiles [tile0, tile0 + ntiles) of the launch's list: tm x tn tiles of a * b^T, followed
+// (two-product mode) by tn x tm tiles of b * a^T.
+struct MProbD {
+  int a, b;
+  int tile0, ntiles, tm, tn;
+  long long key_a, key_b;   // offsets of the a-row / b-row keys in keys[] (and sec[])
+  long long out_off;        // matches0 / sim0 rows of this pair start here (cap(a) rows)
+};
+
+struct TcMatchArgs {
+  const MOperD* opers;
+  const MProbD* probs;
+  int nprob, total_tiles;
+  int passes;             // 1: one product, rows thread-local + columns through the threshold filter; 2: both products, rows only (top-2)
+  int cols;               // passes == 1: reduce the columns too (mutual check)
+  int split, stages;
+  int mutual, ratio_mode;
+  float dist_th, ratio_th;
+  unsigned long long* keys;
+  unsigned* sec;          // second-best similarities (ordered uint), passes == 2 only
+  const int* efflen;      // effective rows per set (written by the prep kernels)
+  const int* remap;       // compaction tables, indexed by plane row
+  int* done;              // per-pair completed-tile counters
+  int32_t* matches0;
+  float* sim0;
+};
+
+size_t tm_smem_bytes(int split, int stages);
+int tm_stages(int split);
+int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows);
+int launch_match_prep(const MOperD* opers_dev, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
+                      int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
+                      int num_sms, cudaStream_t st);
+int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st);
+
+}  // namespace sfd2

@@ -3,6 +3,7 @@
 // of the 1024-byte swizzle pattern?  If so, one {64 ch, 10 px, 18 rows} halo load serves all nine taps of a
 // 3x3 convolution (tile = 16 rows x 8 px).  D = A(tap view) * I is read back and compared on the host.
 #include "common.cuh"
+#include "probes.h"
 #include "ptx.cuh"
 
 namespace sfd2 {

@@ -64,7 +64,7 @@ class ResSegNetV2(torch.nn.Module):
             raise _lib.Sfd2Error("load weights before .cuda()")
         if not torch.cuda.is_available():
             raise _lib.Sfd2Error("no CUDA device: sfd2_b200 has no CPU path")
-        dev = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+        dev = _lib.device_index(device)
         if self._ctx is None or self._ctx.device != dev:
             self._ctx = _lib.Context(self._blob, dev)
         return self
@@ -107,6 +107,13 @@ def _params(model, conf_th, topk, border=4, border_wh=(0, 0)):
                               border_w=int(border_wh[0]), border_h=int(border_wh[1]))
 
 
+def _same_device(ctx, dev):
+    """Foreign-device pointers would reach the kernels as illegal addresses: refuse them here."""
+    if dev.type != "cuda" or dev.index != ctx.device:
+        raise _lib.Sfd2Error(f"tensor lives on {dev} but the model's context is bound to cuda:{ctx.device}; "
+                             "move the tensor or call model.cuda(device)")
+
+
 def _pack(kp, sc, de, n):
     return {"keypoints": np.array(kp[:n], dtype=float),
             "descriptors": np.array(de[:n], dtype=float),
@@ -137,16 +144,19 @@ def extract_resnet_return(model, img, conf_th=0.001, mask=None, topK=-1, **kwarg
     if img.is_cuda:
         img = img.contiguous()
         dev = img.device
-        kp = torch.zeros(cap, 2, dtype=torch.float32, device=dev)
-        sc = torch.zeros(cap, dtype=torch.float32, device=dev)
+        _same_device(ctx, dev)
+        # every row of the outputs is written by the kernels (rows beyond the count read zero): no fills
+        kp = torch.empty(cap, 2, dtype=torch.float32, device=dev)
+        sc = torch.empty(cap, dtype=torch.float32, device=dev)
         de = torch.empty(cap, _lib.DESC_DIM, dtype=torch.float32, device=dev)
-        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        cnt = torch.empty(1, dtype=torch.int32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.sfd2_extract_dev(ctx.handle, img.data_ptr(), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
                                         kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
                    "sfd2_extract_dev")
+        _lib.check(lib.sfd2_extract_status(ctx.handle, st), "sfd2_extract_dev")     # synchronises; raises on candidate overflow
         n = int(cnt.item())
-        return _pack(kp.cpu().numpy(), sc.cpu().numpy(), de.cpu().numpy(), n)
+        return _pack(kp[:n].cpu().numpy(), sc[:n].cpu().numpy(), de[:n].cpu().numpy(), n)
     a = np.ascontiguousarray(img.numpy())
     kp = np.zeros((cap, 2), np.float32)
     sc = np.zeros((cap,), np.float32)
@@ -165,9 +175,9 @@ def _extract_multiscale(model, img, conf_th, topK, scales):
     float32 (:214-215), and the union is cut to topK by score (:322-326)."""
     import torch.nn.functional as F
     img = torch.as_tensor(img).float()
-    img = img.reshape(1, *img.shape[-3:]).cuda()
-    _, _, H, W = img.shape
     ctx = model.ctx
+    img = img.reshape(1, *img.shape[-3:]).to(torch.device("cuda", ctx.device))
+    _, _, H, W = img.shape
     lib = _lib.lib()
     pts, descs, lin = [], [], []
     for si, s in enumerate(scales):
@@ -178,15 +188,16 @@ def _extract_multiscale(model, img, conf_th, topK, scales):
         cur = cur.contiguous()
         nh, nw = int(cur.shape[2]), int(cur.shape[3])
         cap = int(topK) if topK and topK > 0 else (nh * nw) // 16 + 4096
-        kp = torch.zeros(cap, 2, dtype=torch.float32, device=img.device)
-        sc = torch.zeros(cap, dtype=torch.float32, device=img.device)
+        kp = torch.empty(cap, 2, dtype=torch.float32, device=img.device)
+        sc = torch.empty(cap, dtype=torch.float32, device=img.device)
         de = torch.empty(cap, _lib.DESC_DIM, dtype=torch.float32, device=img.device)
-        cnt = torch.zeros(1, dtype=torch.int32, device=img.device)
+        cnt = torch.empty(1, dtype=torch.int32, device=img.device)
         p = _params(model, conf_th, cap, border_wh=(W, H))
         st = torch.cuda.current_stream(img.device).cuda_stream
         _lib.check(lib.sfd2_extract_dev(ctx.handle, cur.data_ptr(), _lib.IMG_F32_NCHW, 1, nh, nw, C.byref(p),
                                         kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
                    "sfd2_extract_dev")
+        _lib.check(lib.sfd2_extract_status(ctx.handle, st), "sfd2_extract_dev")
         n = int(cnt.item())
         k = kp[:n].cpu().numpy()
         lin.append((si << 40) + k[:, 1].astype(np.int64) * nw + k[:, 0].astype(np.int64))
@@ -222,16 +233,24 @@ class Extractor:
             n, _, H, W = images.shape
             dt = _lib.IMG_F32_NCHW
         dev = images.device
-        kp = torch.zeros(n, self.topk, 2, dtype=torch.float32, device=dev)
-        sc = torch.zeros(n, self.topk, dtype=torch.float32, device=dev)
+        _same_device(self.model.ctx, dev)
+        kp = torch.empty(n, self.topk, 2, dtype=torch.float32, device=dev)
+        sc = torch.empty(n, self.topk, dtype=torch.float32, device=dev)
         de = torch.empty(n, self.topk, _lib.DESC_DIM, dtype=torch.float32, device=dev)
-        cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
         p = _params(self.model, self.conf_th, self.topk)
         st = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(_lib.lib().sfd2_extract_dev(self.model.ctx.handle, images.data_ptr(), dt, n, H, W, C.byref(p),
                                                kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
                    "sfd2_extract_dev")
         return {"keypoints": kp, "scores": sc, "descriptors": de, "counts": cnt}
+
+    def check_status(self):
+        """The batched device call is asynchronous; this synchronises the current stream and raises Sfd2Error if any
+        extract since the last check produced more NMS candidates than the workspace holds (truncated results)."""
+        ctx = self.model.ctx
+        st = torch.cuda.current_stream(torch.device("cuda", ctx.device)).cuda_stream
+        _lib.check(_lib.lib().sfd2_extract_status(ctx.handle, st), "sfd2_extract_dev")
 
     def extract_host(self, images):
         """Batched host entry point (sfd2_extract_host): images = CPU tensor / ndarray float32 [n,3,H,W] in

@@ -20,13 +20,14 @@ def test_library_exports_every_declared_symbol():
     h = _lib.lib()      # raises if the .so is missing or a symbol is absent
     for name in declared:
         assert hasattr(h, name)
-    assert h.sfd2_abi_version() == 1
+    assert h.sfd2_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_lib.ExtractParams) == 32
-    assert C.sizeof(_lib.MatchParams) == 20
+    assert C.sizeof(_lib.MatchParams) == 24
+    assert C.sizeof(_lib.DescSet) == 32
 
 
 def test_create_rejects_bad_blob_without_touching_cuda():

@@ -101,6 +101,21 @@ def test_large_random_heatmap_full_size():
 
 
 # ------------------------------------------------------------------ end-to-end extraction
+def _log_count(key, value):
+    """Measured parity counts go to gpurun_out/parity_counts.json (merged back from the GPU box) and to stdout."""
+    import json
+    print(f"[parity] {key} = {value}")
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, "parity_counts.json")
+        cur = json.load(open(path)) if os.path.exists(path) else {}
+        cur[key] = value
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 def _check_extract(out, g, exact_keypoints, score_rtol):
     """Keypoint parity.  `exact_keypoints`: the keypoint SET must equal the reference's, except
     candidates whose reference score is within `score_rtol` (the mode's measured arithmetic error)
@@ -155,8 +170,10 @@ def test_extract_matches_reference(golden, name, prec):
     g = golden(name)
     out = extract_resnet_return(model(prec), torch.from_numpy(_img(g)), topK=int(g["K"]), conf_th=0.001, scales=[1.0])
     missing = _check_extract(out, g, exact_keypoints=True, score_rtol={"fp32": 1e-5, "exact": 1e-4, "mixed": 1e-4}[prec])
-    if name in ("small_96x128", "odd_100x141", "c1_640x480"):
-        assert missing == 0      # the cut is not near-tied on these fixtures: identical keypoint sets
+    _log_count(f"extract_missing[{prec}-{name}]", missing)
+    # identical keypoint SETS on every fixture, C2 included (measured on B200: 0 missing in all three modes; the
+    # relative gap at C2's cut is 2.2e-4 against an arithmetic error of ~1e-5)
+    assert missing == 0, f"{missing} reference keypoints missing"
 
 
 @pytest.mark.parametrize("name", ["c1_640x480", "c2_1600x1200"])
@@ -254,9 +271,13 @@ def test_pair_matches_reference(golden, name, prec):
     if not np.array_equal(m0, ref):
         # disagreements are only allowed where the fp64 top-1/top-2 gap is below fp32 resolution
         nn12, nn21, gap, _ = orc.mutual_nn_exact(g["desc"], g["desc_b"])
+        _, _, cgap, _ = orc.mutual_nn_exact(g["desc_b"], g["desc"])
         bad = np.nonzero(m0 != ref)[0]
-        colgap_ok = all(gap[i] < 1e-6 or True for i in bad)
-        assert len(bad) <= 2 and colgap_ok, f"{len(bad)} rows differ"
+        assert len(bad) <= 2, f"{len(bad)} rows differ"
+        for i in bad:
+            # the row's own arg-max is near-tied, or the mutual check of a column it involves is
+            cols = {int(c) for c in (m0[i], ref[i], nn12[i]) if c >= 0}
+            assert gap[i] < 1e-6 or any(cgap[c] < 1e-6 for c in cols), (int(i), float(gap[i]), [float(cgap[c]) for c in cols])
     assert np.abs(out["matching_scores0"][0].cpu().numpy() - g["hloc_scores0"]).max() <= TOL
 
 
@@ -448,3 +469,154 @@ def test_large_image_modes_agree():
     i0, i1 = np.array(hit).T
     assert np.abs(b["scores"][i0] - a["scores"][i1]).max() <= TOL
     assert np.abs(b["descriptors"][i0] - a["descriptors"][i1]).max() <= TOL
+
+
+# ------------------------------------------------------------------ the batched paths the bench numbers come from
+def _c2_batch(golden, n=8):
+    g = golden("c2_1600x1200")
+    H, W = int(g["H"]), int(g["W"])
+    u8 = [synth_image_u8(int(g["seed"]) + i, H, W) for i in range(n)]
+    f32 = np.stack([(u.astype(np.float32) / np.float32(255)).transpose(2, 0, 1) for u in u8])
+    return g, u8, f32
+
+
+@pytest.mark.parametrize("prec", ["mixed", "exact"])
+def test_batched_paths_equal_single_image_calls(golden, prec):
+    """8 DISTINCT 1600x1200 images through (a) Extractor.extract_host (sfd2_extract_host, n = 8: copy stream, one event
+    per image, workspaces alternating on two internal streams) and (b) Extractor.__call__ (sfd2_extract_dev, n = 8)
+    must equal, image by image and bit for bit, the reference-signature call extract_resnet_return on that image
+    alone - and image 0 must equal the reference fixture.  Run twice so workspace reuse across calls is covered."""
+    from gpu_util import model, WEIGHTS
+    from sfd2_b200 import extract_resnet_return, Extractor
+    g, u8, f32 = _c2_batch(golden)
+    K = int(g["K"])
+    single = [extract_resnet_return(model(prec), torch.from_numpy(f32[i:i + 1]), topK=K, conf_th=0.001, scales=[1.0])
+              for i in range(len(f32))]
+    missing = _check_extract(single[0], g, exact_keypoints=True, score_rtol=1e-4)
+    assert missing == 0
+    ex = Extractor(WEIGHTS, use_stability=True, precision=prec, topk=K, conf_th=0.001)
+    host = torch.from_numpy(f32).pin_memory()
+    dev = torch.from_numpy(f32).cuda()
+    dev_u8 = torch.from_numpy(np.stack(u8)).cuda()
+    for rep in range(2):
+        h = ex.extract_host(host)
+        d = ex(dev)
+        ex.check_status()
+        d8 = ex(dev_u8)
+        ex.check_status()
+        for i, ref in enumerate(single):
+            n = len(ref["scores"])
+            for name, o in (("host", h), ("dev", {k: v.cpu().numpy() for k, v in d.items()}),
+                            ("dev_u8", {k: v.cpu().numpy() for k, v in d8.items()})):
+                assert int(o["counts"][i]) == n, (name, rep, i)
+                assert np.array_equal(o["keypoints"][i, :n].astype(np.float64), ref["keypoints"]), (name, rep, i)
+                assert np.array_equal(o["scores"][i, :n].astype(np.float64), ref["scores"]), (name, rep, i)
+                assert np.array_equal(o["descriptors"][i, :n].astype(np.float64), ref["descriptors"]), (name, rep, i)
+    # distinct images really gave distinct results
+    assert not np.array_equal(single[0]["keypoints"], single[1]["keypoints"])
+
+
+def test_pair_pipeline_matches_reference(golden):
+    """BASELINE configs[4] (C5): extract G(s), extract roll(G(s)), mutual-NN match - through the sweep the bench times
+    (sfd2_b200.sweep.pair_sweep: batched device extraction + one match per pair) against the reference fixture of the
+    same pair (hloc/match_features.py:90-121 on the reference's own features)."""
+    from gpu_util import WEIGHTS
+    from sfd2_b200.sweep import pair_sweep
+    from sfd2_b200.synth import shifted_twin
+    g = golden("c2_1600x1200")
+    H, W, K = int(g["H"]), int(g["W"]), int(g["K"])
+    a = synth_image_u8(int(g["seed"]), H, W)
+    pairs = [(a, shifted_twin(a)), (synth_image_u8(77, H, W), shifted_twin(synth_image_u8(77, H, W)))]
+    res = pair_sweep(pairs, WEIGHTS, precision="mixed", topk=K, conf_th=0.001, keep=True)
+    r0 = res["pairs"][0]
+    assert np.array_equal(r0["keypoints0"].astype(np.int16), g["kp_xy"])
+    assert np.array_equal(r0["keypoints1"].astype(np.int16), g["kp_xy_b"])
+    m0 = r0["matches0"]
+    bad = np.nonzero(m0 != g["hloc_matches0"])[0]
+    _log_count("pair_pipeline_rows_differing[mixed-c2]", int(len(bad)))
+    # our descriptors differ from the reference's by <= 1e-3 (single-pass head), so a near-tied arg-max may flip
+    nn12, nn21, gap, _ = orc.mutual_nn_exact(g["desc"], g["desc_b"])
+    _, _, cgap, _ = orc.mutual_nn_exact(g["desc_b"], g["desc"])
+    for i in bad:
+        cols = {int(c) for c in (m0[i], g["hloc_matches0"][i], nn12[i]) if c >= 0}
+        assert gap[i] < 4e-3 or any(cgap[c] < 4e-3 for c in cols), (int(i), float(gap[i]))
+    assert len(bad) <= 0.01 * len(m0)
+    assert np.abs((r0["sim0"] + 1) / 2 - g["hloc_scores0"]).max() <= TOL
+    assert res["pairs"][1]["matches0"].shape == (len(res["pairs"][1]["keypoints0"]),)
+    assert (res["pairs"][1]["matches0"] >= 0).sum() > 1000
+
+
+# ------------------------------------------------------------------ grouped matcher: device-side counts, layouts, ids
+def test_grouped_pairs_with_device_counts_equal_single_calls():
+    """sfd2_match_pairs_dev on fixed-capacity sets whose valid row counts live on the device (what the extract -> match
+    pipeline feeds it) must equal per-pair calls on the trimmed sets, for ragged counts incl. 0, 1 and the capacity."""
+    from sfd2_b200.matchers import match_dev, match_pairs_dev
+    K = 700
+    counts = [700, 513, 128, 1, 0, 257, 640, 699]
+    rng = np.random.RandomState(11)
+    base, _ = synth_descriptors(12, 900, 10)
+    D = np.zeros((len(counts), K, 128), np.float32)
+    for i, c in enumerate(counts):
+        d = base[rng.permutation(900)[:K]] + 0.25 * rng.randn(K, 128).astype(np.float32)
+        D[i] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    dd = torch.from_numpy(D).cuda()
+    cc = torch.tensor(counts, dtype=torch.int32, device="cuda")
+    idx0 = [0, 1, 2, 3, 4, 5, 6, 0, 7]
+    idx1 = [1, 2, 0, 0, 1, 6, 5, 4, 7]
+    for mutual in (True, False):
+        m, s_ = match_pairs_dev(dd, cc, idx0, idx1, mutual=mutual, precision="exact")
+        assert m.shape == (len(idx0), K)
+        for p, (a, b) in enumerate(zip(idx0, idx1)):
+            na, nb = counts[a], counts[b]
+            mi, si = match_dev(dd[a, :na], dd[b, :nb], mutual=mutual, precision="exact")
+            assert torch.equal(m[p, :na], mi), (mutual, p)
+            assert torch.equal(s_[p, :na], si), (mutual, p)
+            assert bool((m[p, na:] == -1).all()) and bool((s_[p, na:] == 0).all()), (mutual, p)
+            if na and nb:
+                ref = orc.match_hloc(D[a, :na].T[None], D[b, :nb].T[None], do_mutual_check=mutual)["matches0"][0].numpy()
+                assert (mi.cpu().numpy() == ref).mean() > 0.999, (mutual, p)
+
+
+def test_hloc_layout_is_read_in_place(golden):
+    """[1, D, N] (nearest_neighbor.py:39) goes to the kernels as is; results equal the row-major call bit for bit."""
+    from sfd2_b200.matchers import match_dev
+    g = golden("match_cases")
+    for tag in ["sq", "wide", "tall", "one", "col"]:
+        d0, d1 = g[f"{tag}_d0"], g[f"{tag}_d1"]
+        a, b = torch.from_numpy(d0).cuda(), torch.from_numpy(d1).cuda()
+        at, bt = torch.from_numpy(d0.T.copy()).cuda(), torch.from_numpy(d1.T.copy()).cuda()
+        for kw in ({}, {"ratio_th": 0.8, "dist_th": 0.7}, {"mutual": False}):
+            m_r, s_r = match_dev(a, b, precision="exact", **kw)
+            m_c, s_c = match_dev(at, bt, precision="exact", layout="cols", **kw)
+            assert torch.equal(m_r, m_c) and torch.equal(s_r, s_c), (tag, kw)
+
+
+def test_localizer_subset_and_remap_on_device():
+    """it_loc/localize_cv2.py:511-560: match a query against db images using only db keypoints with a 3-D point
+    (db_3D_ids != -1) and report ORIGINAL db rows - one grouped launch for the whole list of db images."""
+    from sfd2_b200.matchers import feature_matching
+    rng = np.random.RandomState(21)
+    q, _ = synth_descriptors(41, 1500, 10)
+    sizes = [900, 300, 2, 1201, 5, 128]
+    dbs, ids = [], []
+    for k, m in enumerate(sizes):
+        d = rng.randn(m, 128).astype(np.float32)
+        take = min(m, 400)
+        d[:take] = q[rng.permutation(1500)[:take]] + 0.2 * rng.randn(take, 128).astype(np.float32)
+        dbs.append(d / np.linalg.norm(d, axis=1, keepdims=True))
+        i3 = rng.randint(0, 10000, m)
+        i3[rng.rand(m) < (0.5 if k != 4 else 0.9)] = -1
+        ids.append(i3)
+    ids[2][:] = -1                                   # nothing valid
+    ids[5][:] = np.arange(128)                       # everything valid
+    out = feature_matching(q.astype(np.float64), dbs, db_3D_ids=ids)
+    for k in range(len(sizes)):
+        ref = orc.feature_matching(q, dbs[k], ids[k])
+        assert out[k].shape == ref.shape
+        assert (out[k] == ref).mean() > 0.999, (k, (out[k] != ref).sum())
+        ok = out[k] >= 0
+        assert (ids[k][out[k][ok]] != -1).all(), k     # only keypoints with a 3-D point are ever matched
+    single = feature_matching(q, dbs[0], db_3D_ids=ids[0])
+    assert np.array_equal(single, out[0])
+    plain = feature_matching(q, dbs[0])
+    assert (plain == orc.feature_matching(q, dbs[0])).mean() > 0.999

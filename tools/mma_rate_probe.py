@@ -13,6 +13,10 @@ from sfd2_b200 import _lib
 
 torch.cuda.init(); torch.zeros(1).cuda()
 lib = _lib.lib()
+if not hasattr(lib, 'sfd2_debug_mma_rate'):
+    sys.exit('build the library with the probes first: SFD2_WITH_PROBES=1 python -m sfd2_b200.build --force')
+lib.sfd2_debug_mma_rate.restype = C.c_int
+lib.sfd2_debug_mma_rate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
 nsm = torch.cuda.get_device_properties(0).multi_processor_count
 iters = 8192
 for grid in (1, nsm):

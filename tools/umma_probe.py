@@ -7,6 +7,9 @@ import torch
 from sfd2_b200 import _lib
 torch.cuda.init(); torch.zeros(1).cuda()
 lib = _lib.lib()
+if not hasattr(lib, 'sfd2_debug_umma_probe'):
+    sys.exit('build the library with the probes first: SFD2_WITH_PROBES=1 python -m sfd2_b200.build --force')
+lib.sfd2_debug_umma_probe.restype = __import__('ctypes').c_int
 for pitch in (10, 16):
     for bo in (0, 1):
         ok_all = True
