@@ -4,22 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision exact|mixed|fast|fp32]
     python bench.py --impl reference [...]        # the reference's CPU path (oracle port) on host cores
 
-Metric (BASELINE.json): images/s of extract @1600x1200, top-4096 keypoints
-(configs[1]); the 4096x4096 mutual-NN matcher (configs[2]) is reported beside it.
+Metric (BASELINE.json): images/s of extract @1600x1200, top-4096 keypoints (configs[1]).  The same JSON line
+carries the other BASELINE configs as full entries:
+  "match"  configs[2]  4096 x 4096 x 128 mutual-NN matcher: device-resident pairs/s, its own roofline, the end-to-end
+                       rate through the two reference plugins (hloc NearestNeighbor with [1,128,N] tensors built from
+                       host arrays, it_loc Matcher with float64 numpy) and the CPU rate;
+  "sweep"  configs[3]  1040 images (the Aachen v1.1 query count) sharded images[rank::world] (strong scaling);
+  "pairs"  configs[4]  pair pipeline = extract both 1600x1200 frames + match, pairs[rank::world]; 10 000 pairs at
+                       8 GPUs = 1250 per GPU (weak scaling), device-resident and host-in / host-out.
 
-A "step" is one pass of the extract path over a batch of B synthetic 1600x1200
-images.  `value` times the C-ABI device entry point with the batch already
-resident in HBM; `e2e` times the reference-facing call
-`extract_resnet_return(model, img_cpu, topK=4096, ...)` per image with pinned
-HOST buffers (H2D of the image and D2H of keypoints/scores/descriptors inside the
-timed region).  Inputs cycle through a pool larger than L2 and every step
-rewrites ~GBs of activations, so nothing is served from a warm L2.
+A "step" is one pass of the extract path over a batch of B synthetic 1600x1200 images.  `value` times the C-ABI
+device entry point with the batch already resident in HBM; `e2e` times the reference-facing plugin call
+`extract_resnet_return(model, img_cpu, topK=4096, ...)`, one synchronous call per image with HOST buffers (H2D of
+the image and D2H of keypoints/scores/descriptors inside the timed region); `e2e.batched` is the batched C-ABI host
+call (sfd2_extract_host, B pinned images per call).  Inputs cycle through a pool larger than L2 and every image
+rewrites >1 GB of activations, so nothing is served from a warm L2.
 
-One JSON line on stdout (rank 0).  Under torchrun each rank owns its own batch
-(weak scaling, no data-path collective); one NCCL all_gather collects
-(x, y, score) + counts for the benchmark table outside the timed region.
+One JSON line on stdout (rank 0).  Under torchrun each rank owns its own batch (no data-path collective); one NCCL
+all_gather (sfd2_b200.shard.gather_table) collects (x, y, score) + counts for the table outside the timed regions.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -38,6 +43,19 @@ GFLOP_PER_IMAGE = 831.114        # reference's dense count, SURVEY.md A.1 (415.5
 GFLOP_CONV1A, GFLOP_STA = 6.636, 0.184   # the two layers that do not run in tc_conv_kernel
 GFLOP_PER_PAIR = 4.295           # 2 * 4096 * 4096 * 128
 METRIC = "images/sec extract@1600x1200 top-4096"
+SWEEP_IMAGES = 1040              # Aachen v1.1 query count
+PAIRS_AT_8 = 10000               # C5: 10k pairs on 8 GPUs = 1250 per GPU
+
+# activation planes each tc_conv layer reads / writes at 1600x1200 (elements; x2 bytes per fp16 plane, hi+lo in the
+# exact layers): input, output, residual.  Used for roofline.traffic_model (algorithmic HBM bytes per launch).
+_P1, _P2, _P4, _P8 = 1200 * 1600, 600 * 800, 300 * 400, 150 * 200
+LAYER_ELEMS = {  # name: (in elems, out elems, residual elems, out is fp32)
+    "conv1b": (_P1 * 64, _P2 * 64, 0, 0), "conv2a": (_P2 * 64, _P2 * 128, 0, 0), "conv2b": (_P2 * 128, _P4 * 128, 0, 0),
+    "conv3a": (_P4 * 128, _P4 * 256, 0, 0), "conv3b": (_P4 * 256, _P4 * 256, 0, 0),
+    **{f"rb{i}c{j}": (_P4 * 256, _P4 * 256, _P4 * 256 if j == 3 else 0, 0) for i in range(3) for j in (1, 2, 3)},
+    "convPa0": (_P4 * 256, _P8 * 123, 0, 0), "convDa0": (_P4 * 256, _P4 * 186, 0, 0),
+    "headP": (_P8 * 123, _P8 * 64, 0, 1), "headD": (_P4 * 186, _P4 * 128, 0, 1),
+}
 
 
 def peaks():
@@ -47,6 +65,35 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops": d["bf16_tflops_sustained"],
                 "src": "measured"}
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops": 1400.0, "src": "fallback"}
+
+
+def traffic_entry(precision):
+    """Measured DRAM bytes per tc_conv launch from the committed ncu --set full capture of THIS code (refreshed by
+    tools/gpu_final.sh; the entry names the capture and the sha of the kernel source it was taken from) and the
+    algorithmic plane traffic per launch from the layer table (no L2 hits assumed: every plane read and written once)."""
+    planes = 2 if precision in ("exact", "mixed") else 1
+    tot = 0
+    for name, (i, o, r, f32) in LAYER_ELEMS.items():
+        pl = 1 if (precision == "mixed" and name == "headD") else planes      # mixed: descriptor head reads hi only
+        po = 1 if (precision == "mixed" and name == "convDa0") else planes
+        tot += i * 2 * pl + r * 2 * planes + (o * 4 if f32 else o * 2 * po)
+    model = tot / len(LAYER_ELEMS)
+    measured, src = None, None
+    tp = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        e = tj.get(precision)
+        if e:
+            measured = e.get("tc_conv_bytes_per_launch")
+            src = {k: e.get(k) for k in ("source", "launches", "kernel_sha", "metric")}
+            cur = file_sha(os.path.join(REPO, "sfd2_b200", "csrc", "tc_conv.cu"))
+            src["kernel_sha_now"] = cur
+            src["stale"] = bool(e.get("kernel_sha")) and e.get("kernel_sha") != cur
+    return measured, model, src
+
+
+def file_sha(path):
+    return hashlib.sha1(open(path, "rb").read()).hexdigest()[:12]
 
 
 class ClockSampler:
@@ -92,12 +139,22 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
+def cpu_threads():
+    """The reference runs torch with its default intra-op threads = all host cores; torchrun exports
+    OMP_NUM_THREADS=1 for nproc > 1, which would time a single-threaded reference - undo that."""
+    import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)
+    return n
+
+
 def cpu_extract_rate(n_images, warmup=1, flush_denormal=False):
     """images/s of the oracle port (same op sequence as the reference) on all host threads.
     flush_denormal=True is NOT what the reference does: the checkpoint's dead BatchNorm channels
      make its fp32 convolutions run on denormals, which Intel hosts execute
     through microcode assists; the flag shows what the same code does without that penalty."""
     import torch
+    cpu_threads()
     torch.set_flush_denormal(bool(flush_denormal))
     from oracle import sfd2_oracle as orc
     from sfd2_b200.synth import synth_image
@@ -110,11 +167,13 @@ def cpu_extract_rate(n_images, warmup=1, flush_denormal=False):
         t0 = time.perf_counter()
         orc.extract(st, imgs[i % len(imgs)], topK=TOPK, conf_th=CONF)
         t.append(time.perf_counter() - t0)
+    torch.set_flush_denormal(False)
     return n_images / sum(t), min(t), torch.get_num_threads()
 
 
 def cpu_match_rate(n_pairs):
     import torch
+    cpu_threads()
     from oracle import sfd2_oracle as orc
     from sfd2_b200.synth import synth_descriptors
     d0, d1 = synth_descriptors(0, 4096, 4096)
@@ -124,6 +183,25 @@ def cpu_match_rate(n_pairs):
     for _ in range(n_pairs):
         orc.match_hloc(a, b)
     return n_pairs / (time.perf_counter() - t0)
+
+
+def cpu_pair_rate(n_pairs):
+    """C5 on the CPU: 2 extracts + 1 match per pair through the oracle port, measured on n_pairs whole pairs."""
+    import torch
+    cpu_threads()
+    from oracle import sfd2_oracle as orc
+    from sfd2_b200.synth import synth_image_u8, shifted_twin
+    st = orc.load_state(WEIGHTS)
+    elapsed = 0.0
+    for s in range(n_pairs):
+        a = synth_image_u8(s, H, W)                     # (image synthesis is not part of the pair time)
+        fr = [(u.astype(np.float32) / np.float32(255)).transpose(2, 0, 1)[None].copy() for u in (a, shifted_twin(a))]
+        t1 = time.perf_counter()
+        f0, f1 = (orc.extract(st, f, topK=TOPK, conf_th=CONF) for f in fr)
+        orc.match_hloc(torch.from_numpy(f0["descriptors"].T.copy())[None].float(),
+                       torch.from_numpy(f1["descriptors"].T.copy())[None].float())
+        elapsed += time.perf_counter() - t1
+    return n_pairs / elapsed
 
 
 def run_reference(args):
@@ -145,7 +223,12 @@ def run_reference(args):
                              "sample": f"{steps} images of 1600x1200 (+{max(1, warm)} warm-up), best {best:.3f} s"},
             "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "match": {"pairs_per_s": pairs, "unit": "4096x4096 pairs/s", "sample": "10 pairs, hloc NearestNeighbor port"},
+            "pairs": {"pairs_per_s": 1.0 / (2.0 / rate + 1.0 / pairs), "unit": "pairs/s (2 extracts + 1 match)",
+                      "sample": "derived from the measured per-image and per-match times of this run"},
             "gpu_launches": 0}
+    if args.cpu_pairs > 0:
+        line["pairs"] = {"pairs_per_s": cpu_pair_rate(args.cpu_pairs), "unit": "pairs/s (2 extracts + 1 match)",
+                         "sample": f"{args.cpu_pairs} whole pairs through the oracle port"}
     print(json.dumps(line), flush=True)
 
 
@@ -153,8 +236,10 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from sfd2_b200 import Extractor, extract_resnet_return
-    from sfd2_b200.matchers import match_dev, _ctx as match_ctx
+    from sfd2_b200 import Extractor, extract_resnet_return, NearestNeighbor, Matcher, matcher_confs
+    from sfd2_b200.matchers import match_dev, match_sets_dev, match_one_to_many, _ctx as match_ctx
+    from sfd2_b200.shard import shard_indices, gather_table
+    from sfd2_b200.sweep import Sweep
     from sfd2_b200.synth import synth_image_u8, synth_descriptors
 
     rank = int(os.environ.get("RANK", "0"))
@@ -172,12 +257,15 @@ def run_ours(args):
     # distinct synthetic images per rank (images[rank::world] of the C4-style list)
     seeds = [rank + world * i for i in range(pool_n)]
     pool_u8 = np.stack([synth_image_u8(s, H, W) for s in seeds])
-    pool = torch.from_numpy(pool_u8).to(dev).float().div_(255.0).permute(0, 3, 1, 2).contiguous()  # [P,3,H,W] f32
+    pool_dev_u8 = torch.from_numpy(pool_u8).to(dev)                                             # [P,H,W,3] u8
+    pool = pool_dev_u8.float().div_(255.0).permute(0, 3, 1, 2).contiguous()                    # [P,3,H,W] f32
     host_imgs = [torch.from_numpy((pool_u8[i].astype(np.float32) / np.float32(255)).transpose(2, 0, 1)[None].copy()).pin_memory()
                  for i in range(min(pool_n, 8))]
 
-    ex = Extractor(WEIGHTS, use_stability=True, precision=args.precision, topk=TOPK, conf_th=CONF, device=dev)
+    sw = Sweep(WEIGHTS, precision=args.precision, topk=TOPK, conf_th=CONF, use_stability=True, device=dev, batch=B)
+    ex = sw.ex
     ctx = ex.model.ctx
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def step(i):
         j = (i * B) % pool_n
@@ -190,6 +278,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, n):
+        """n calls of fn(i) bracketed by barrier + synchronize on both sides, CUDA events on the current stream."""
+        barrier()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    # ================================================================== extract (configs[1]) - the headline
     for i in range(Wm):
         out = step(i)
     barrier()
@@ -199,26 +298,15 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     ctx.profile(True)
     ctx.profile_read()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        out = step(Wm + i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed(lambda i: step(Wm + i), K)
     prof = ctx.profile_read()
     ctx.profile(False)
     launches = ctx.launch_count() - launches0
     # the same K steps again without per-launch events: this is the reported time
-    barrier()
-    e0.record()
-    for i in range(K):
-        out = step(Wm + i)
-    e1.record()
-    barrier()
-    ms_clean = e0.elapsed_time(e1)
+    ms_clean = timed(lambda i: step(Wm + i), K)
+    ex.check_status()
     clocks = sampler.stop() if rank == 0 else None
+    out = step(0)
 
     # ---- the other tcgen05 precision modes, same device-resident workload, K steps each (reported beside the main number) ----
     other = {}
@@ -229,20 +317,21 @@ def run_ours(args):
             ex2 = Extractor(WEIGHTS, use_stability=True, precision=prec, topk=TOPK, conf_th=CONF, device=dev)
             for i in range(3):
                 ex2(pool[(i % 2) * B:(i % 2) * B + B] if pool_n >= 2 * B else pool[:B])
-            barrier()
-            e0.record()
-            for i in range(K):
-                j = (i * B) % pool_n
-                ex2(pool[j:j + B] if j + B <= pool_n else pool[:B])
-            e1.record()
-            barrier()
-            other[prec] = e0.elapsed_time(e1)
+            other[prec] = timed(lambda i: ex2(pool[(i * B) % pool_n:(i * B) % pool_n + B] if (i * B) % pool_n + B <= pool_n else pool[:B]), K)
             del ex2
 
-    # ---- e2e: HOST buffers in, HOST features out, copies inside the timed region ----
-    # (a) the batched C-ABI call sfd2_extract_host on B pinned host images per step (H2D of image i+1 overlaps
-    #     the kernels of image i); (b) the reference-facing single-image call extract_resnet_return.
+    # ================================================================== e2e: HOST buffers in, HOST features out
+    # (a) the reference-facing plugin call extract_resnet_return, one synchronous call per image (the headline e2e);
+    # (b) the batched C-ABI call sfd2_extract_host on B pinned host images per call (H2D of image i+1 overlaps image i).
     model = ex.model
+    n_single = max(8, min(B * K, 40))
+    for i in range(3):
+        extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_single):
+        r = extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
+    single_s = time.perf_counter() - t0
     host_batch = torch.cat(host_imgs[:min(B, len(host_imgs))] * ((B + len(host_imgs) - 1) // len(host_imgs)))[:B].pin_memory()
     for i in range(2):
         ex.extract_host(host_batch)
@@ -252,34 +341,58 @@ def run_ours(args):
         r = ex.extract_host(host_batch)
     e2e_s = time.perf_counter() - t0
     n_e2e = B * K
-    n_single = max(4, min(B * K, 24))
-    for i in range(2):
-        extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(n_single):
-        r = extract_resnet_return(model, host_imgs[i % len(host_imgs)], topK=TOPK, conf_th=CONF, scales=[1.0])
-    single_s = time.perf_counter() - t0
 
-    # ---- matcher (configs[2]): 4096 x 4096 x 128 mutual NN, device-resident ----
+    # ================================================================== matcher (configs[2]): 4096 x 4096 x 128 mutual NN
     d0, d1 = synth_descriptors(rank, 4096, 4096)
     a, b = torch.from_numpy(d0).to(dev), torch.from_numpy(d1).to(dev)
-    for _ in range(3):
+    for _ in range(5):
         match_dev(a, b, precision=args.precision)
     mctx = match_ctx(local)
+    n_pairs = 200
     mctx.profile(True); mctx.profile_read()
-    n_pairs = 50
-    barrier()
-    e0.record()
-    for _ in range(n_pairs):
-        m0, s0 = match_dev(a, b, precision=args.precision)
-    e1.record()
-    barrier()
-    match_ms = e0.elapsed_time(e1)
+    timed(lambda i: match_dev(a, b, precision=args.precision), n_pairs)
     mprof = mctx.profile_read(); mctx.profile(False)
+    match_ms = timed(lambda i: match_dev(a, b, precision=args.precision), n_pairs)
+    # many pairs in ONE grouped launch (the match_features loop as a batch): 32 distinct pairs of 4096 x 4096
+    G = 32
+    gsets = []
+    for g in range(G):
+        x0, x1 = synth_descriptors(1000 + rank * G + g, 4096, 4096)
+        gsets += [{"data": torch.from_numpy(x0).to(dev)}, {"data": torch.from_numpy(x1).to(dev)}]
+    ga, gb = list(range(0, 2 * G, 2)), list(range(1, 2 * G, 2))
+    for _ in range(2):
+        match_sets_dev(gsets, ga, gb, precision=args.precision)
+    mctx.profile(True); mctx.profile_read()
+    timed(lambda i: match_sets_dev(gsets, ga, gb, precision=args.precision), 5)
+    gprof = mctx.profile_read(); mctx.profile(False)
+    grouped_ms = timed(lambda i: match_sets_dev(gsets, ga, gb, precision=args.precision), 5) / 5
+    # e2e through the two reference plugins, host arrays in, host arrays out (hloc/match_features.py:99-119 loop body;
+    # it_loc/matcher.py:91-119)
+    nn = NearestNeighbor({"do_mutual_check": True, "precision": args.precision}).eval().to(dev)
+    f0, f1 = np.ascontiguousarray(d0.T), np.ascontiguousarray(d1.T)          # [128, N] as the feature file holds them
+
+    def hloc_pair(i):
+        data = {"descriptors0": torch.from_numpy(f0)[None].float().to(dev), "descriptors1": torch.from_numpy(f1)[None].float().to(dev)}
+        pred = nn(data)
+        return pred["matches0"][0].cpu().short().numpy(), pred["matching_scores0"][0].cpu().half().numpy()
+    for i in range(3):
+        hloc_pair(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(50):
+        hloc_pair(i)
+    hloc_s = (time.perf_counter() - t0) / 50
+    itm = Matcher(matcher_confs["NNM"], precision=args.precision)
+    q64, r64 = d0.astype(np.float64), d1.astype(np.float64)              # float64 from the h5 file
+    for i in range(3):
+        itm({"descriptors0": q64, "descriptors1": r64})
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(30):
+        itm({"descriptors0": q64, "descriptors1": r64})
+    itloc_s = (time.perf_counter() - t0) / 30
 
     # ---- localizer pattern: one query (4096) against 50 db images (2000 descriptors each), grouped launch ----
-    from sfd2_b200.matchers import match_one_to_many
     rngm = np.random.RandomState(100 + rank)
     dbs = rngm.randn(50 * 2000, 128).astype(np.float32)
     dbs /= np.linalg.norm(dbs, axis=1, keepdims=True)
@@ -287,47 +400,82 @@ def run_ours(args):
     offs = np.arange(51, dtype=np.int32) * 2000
     for _ in range(2):
         match_one_to_many(a, dbt, offs, precision=args.precision)
-    barrier()
-    e0.record()
-    for _ in range(5):
-        match_one_to_many(a, dbt, offs, precision=args.precision)
-    e1.record()
-    barrier()
-    o2m_ms = e0.elapsed_time(e1) / 5
-    e0.record()
-    for k in range(50):
-        match_dev(a, dbt[k * 2000:(k + 1) * 2000], precision=args.precision)
-    e1.record()
-    barrier()
-    loop_ms = e0.elapsed_time(e1)
+    mctx.profile(True); mctx.profile_read()
+    timed(lambda i: match_one_to_many(a, dbt, offs, precision=args.precision), 5)
+    oprof = mctx.profile_read(); mctx.profile(False)
+    o2m_ms = timed(lambda i: match_one_to_many(a, dbt, offs, precision=args.precision), 5) / 5
+    loop_ms = timed(lambda i: match_dev(a, dbt[i * 2000:(i + 1) * 2000], precision=args.precision), 50)
 
-    # ---- max over ranks, all-gather for the table ----
-    t = torch.tensor([ms_clean, ms, e2e_s, match_ms, float(launches)] + [other.get(k, 0.0) for k in ("exact", "mixed", "fast")],
-                     device=dev, dtype=torch.float64)
-    gather_ms = 0.0
+    # ================================================================== pair pipeline (configs[4], C5)
+    # pair s = (G(s), roll(G(s), (6, 10))): extract both frames + match, P pairs per native batch; pairs[rank::world]
+    P = max(1, B // 2)
+    n_pairs_gpu = args.pairs if args.pairs > 0 else PAIRS_AT_8 // 8
+    n_pair_steps = max(1, n_pairs_gpu // P)
+    twin = torch.roll(pool_dev_u8, shifts=(6, 10), dims=(1, 2))
+
+    def pair_step(i):
+        j = (i * P) % pool_n
+        sl = slice(j, j + P) if j + P <= pool_n else slice(0, P)
+        return sw.pairs(pool_dev_u8[sl], twin[sl])
+    for i in range(3):
+        feats, pm0, ps0 = pair_step(i)
+    pair_launch0 = ctx.launch_count() + mctx.launch_count()
+    pairs_ms = timed(pair_step, n_pair_steps)
+    pair_launches = ctx.launch_count() + mctx.launch_count() - pair_launch0
+    ex.check_status()
+    n_matched = int((pm0 >= 0).sum().item())
+    # host frames in (pinned uint8), host features + matches out
+    hp0 = torch.from_numpy(pool_u8[:P]).pin_memory()
+    hp1 = torch.from_numpy(np.roll(pool_u8[:P], (6, 10), axis=(1, 2))).pin_memory()
+    for i in range(2):
+        sw.pairs_host(hp0, hp1)
+    n_pair_e2e = max(4, min(n_pair_steps, 50))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_pair_e2e):
+        rr = sw.pairs_host(hp0, hp1)
+    pairs_e2e_s = time.perf_counter() - t0
+
+    # ================================================================== dataset sweep (configs[3], C4): strong scaling
+    # image i of the 1040 = roll(G(i mod pool), (7 (i div pool), 13 (i div pool))): distinct images, generated on the device
+    mine = shard_indices(SWEEP_IMAGES, rank, world)
+    sweep_kp = torch.empty(len(mine), TOPK, 2, device=dev)
+    sweep_sc = torch.empty(len(mine), TOPK, device=dev)
+    sweep_cnt = torch.empty(len(mine), dtype=torch.int32, device=dev)
+
+    def sweep_batch(bi):
+        ids = mine[bi * B:(bi + 1) * B]
+        imgs = torch.stack([torch.roll(pool_dev_u8[(i // world) % pool_n], shifts=(7 * (i // pool_n), 13 * (i // pool_n)), dims=(0, 1))
+                            for i in ids])
+        o = ex(imgs)
+        n = len(ids)
+        sweep_kp[bi * B:bi * B + n] = o["keypoints"]; sweep_sc[bi * B:bi * B + n] = o["scores"]; sweep_cnt[bi * B:bi * B + n] = o["counts"]
+    sweep_batch(0)
+    sweep_ms = timed(sweep_batch, (len(mine) + B - 1) // B)
+    ex.check_status()
+    barrier()
+    g0 = time.perf_counter()
+    table, tcnt = gather_table(sweep_kp, sweep_sc, sweep_cnt, SWEEP_IMAGES)          # NCCL all_gather, outside the timed region
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - g0) * 1e3
+    kpts_total = int(tcnt.sum().item())
+
+    # ================================================================== max over ranks
+    vals = [ms_clean, ms, e2e_s, match_ms, single_s, grouped_ms, hloc_s, itloc_s, o2m_ms, loop_ms, pairs_ms, pairs_e2e_s, sweep_ms] + \
+           [other.get(k, 0.0) for k in ("exact", "mixed", "fast")]
+    t = torch.tensor(vals + [float(launches)], device=dev, dtype=torch.float64)
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        table = torch.cat([out["keypoints"], out["scores"][..., None]], -1).contiguous()   # [B, K, 3]
-        allk = torch.empty(world * table.shape[0], TOPK, 3, device=dev)
-        allc = torch.empty(world * B, dtype=torch.int32, device=dev)
-        barrier()
-        g0 = time.perf_counter()
-        dist.all_gather_into_tensor(allk, table)
-        dist.all_gather_into_tensor(allc, out["counts"])
-        torch.cuda.synchronize()
-        gather_ms = (time.perf_counter() - g0) * 1e3
-        ms_clean, ms, e2e_s, match_ms = [float(x) for x in tmax[:4]]
-        other = {k: float(tmax[5 + i]) for i, k in enumerate(("exact", "mixed", "fast")) if k in other}
-        launches = int(tsum[4].item())
-        kpts_total = int(allc.sum().item())
-    else:
-        kpts_total = int(out["counts"].sum().item())
+        (ms_clean, ms, e2e_s, match_ms, single_s, grouped_ms, hloc_s, itloc_s, o2m_ms, loop_ms, pairs_ms, pairs_e2e_s,
+         sweep_ms) = [float(x) for x in tmax[:13]]
+        other = {k: float(tmax[13 + i]) for i, k in enumerate(("exact", "mixed", "fast")) if k in other}
+        launches = int(tsum[-1].item())
 
     if rank == 0:
-        P = peaks()
+        Pk = peaks()
         imgs = world * B * K
         value = imgs / (ms_clean / 1e3)
         tc = {k: v for k, v in prof.items() if k.startswith("tc_conv:") or k.startswith("conv_f32:")}
@@ -336,19 +484,21 @@ def run_ours(args):
         alg_gflop = GFLOP_PER_IMAGE - GFLOP_CONV1A - GFLOP_STA
         n_img_prof = B * K
         achieved = alg_gflop * n_img_prof / conv_ms if conv_ms > 0 else 0.0       # GFLOP/ms = TFLOP/s
-        traffic = None
-        tp = os.path.join(REPO, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))       # written by tools/ncu_summary.py from the committed ncu --set full capture
-            traffic = tj.get(args.precision, tj).get("tc_conv_bytes_per_launch")
-        step_ms_prof = ms / K
+        traffic, traffic_model, traffic_src = traffic_entry(args.precision)
         per_kernel = {}
         for k, (cnt, tot) in prof.items():
             name = k.split(":")[0]
             e = per_kernel.setdefault(name, [0, 0.0])
             e[0] += cnt; e[1] += tot
-        mk = [v for k, v in mprof.items() if k.startswith("match")]
-        match_kernel_ms = sum(v[1] for v in mk) / max(1, sum(v[0] for v in mk))
+
+        def kernel_ms(p, prefix="match_tc"):
+            mk = [v for k, v in p.items() if k.startswith(prefix)]
+            return sum(v[1] for v in mk) / max(1, sum(v[0] for v in mk))
+        mk_ms, mprep_ms = kernel_ms(mprof), kernel_ms(mprof, "match_prep")
+        gk_ms = kernel_ms(gprof)
+        ok_ms = kernel_ms(oprof)
+        o2m_gflop = 2.0 * 4096 * 100000 * 128 / 1e9
+        n_pairs_total = world * n_pair_steps * P
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_clean / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -357,27 +507,56 @@ def run_ours(args):
                                    f"precision={args.precision}", "image": [H, W], "topk": TOPK, "batch_per_gpu": B,
                        "l2": f"inputs cycle through a {pool_n}-image pool ({pool_n * H * W * 12 / 1e6:.0f} MB > 126 MB L2); "
                              "every image rewrites >1 GB of activations", "parallelism": f"dp{world} (images sharded, no data-path collective)"},
-            "e2e": {"value": world * n_e2e / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 * 4,
-                    "d2h_bytes_per_step": B * (TOPK * (2 + 1 + 128) * 4 + 4),
-                    "note": f"sfd2_extract_host (C ABI) on {B} pinned host images per step, results to pinned host buffers",
-                    "single_image_call": {"value": world * n_single / single_s, "unit": "images/s",
-                                          "note": "extract_resnet_return(model, pinned host image): one synchronous call per image"}},
+            "e2e": {"value": world * n_single / single_s, "unit": "images/s", "h2d_bytes_per_step": H * W * 3 * 4,
+                    "d2h_bytes_per_step": TOPK * (2 + 1 + 128) * 4 + 4,
+                    "note": "the reference-facing plugin call extract_resnet_return(model, pinned host image, topK=4096): one "
+                            "synchronous call per image (a step = one image), float64 dict out",
+                    "batched": {"value": world * n_e2e / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * H * W * 3 * 4,
+                                "d2h_bytes_per_step": B * (TOPK * (2 + 1 + 128) * 4 + 4),
+                                "note": f"sfd2_extract_host (C ABI) on {B} pinned host images per call, results to pinned host buffers"}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel" if args.precision != "fp32" else "conv_f32_kernel",
-                         "achieved": achieved, "peak": P["tflops"], "unit": "TFLOP/s", "frac": achieved / P["tflops"],
-                         "peak_source": P["src"] + " (bf16 sustained)", "traffic": traffic,
+                         "achieved": achieved, "peak": Pk["tflops"], "unit": "TFLOP/s", "frac": achieved / Pk["tflops"],
+                         "peak_source": Pk["src"] + " (bf16 sustained)", "traffic": traffic, "traffic_model": traffic_model,
+                         "traffic_source": traffic_src,
                          "launches": conv_launches, "avg_launch_ms": conv_ms / max(1, conv_launches),
                          "algorithmic_gflop_per_image": alg_gflop, "share_of_step": conv_ms / ms if ms else None},
             "kernels_ms_per_image": {k: v[1] / n_img_prof for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][1])},
             "layers_ms_per_image": {k.split(":")[1]: v[1] / n_img_prof for k, v in tc.items()},
-            "match": {"pairs_per_s": world * n_pairs / (match_ms / 1e3), "unit": "4096x4096x128 pairs/s",
-                      "ms_per_pair": match_ms / n_pairs, "kernel_ms": match_kernel_ms,
-                      "tflops": GFLOP_PER_PAIR / match_kernel_ms if match_kernel_ms else None,
-                      "frac_of_peak": (GFLOP_PER_PAIR / match_kernel_ms / P["tflops_burst"]) if match_kernel_ms else None,
-                      "one_to_many": {"workload": "4096 query x 50 db sets of 2000 descriptors", "grouped_ms": o2m_ms,
+            "match": {"value": world * n_pairs / (match_ms / 1e3), "pairs_per_s": world * n_pairs / (match_ms / 1e3),
+                      "unit": "4096x4096x128 pairs/s", "workload": "mutual NN of two 4096 x 128 descriptor sets resident in HBM, one sfd2_match_dev call per pair",
+                      "ms_per_pair": match_ms / n_pairs, "kernel_ms": mk_ms, "prep_kernel_ms": mprep_ms,
+                      "roofline": {"bound": "tensor", "kernel": "tc_match_kernel", "achieved": GFLOP_PER_PAIR / mk_ms if mk_ms else None,
+                                   "peak": Pk["tflops_burst"], "unit": "TFLOP/s",
+                                   "frac": (GFLOP_PER_PAIR / mk_ms / Pk["tflops_burst"]) if mk_ms else None,
+                                   "peak_source": Pk["src"] + " (bf16 burst: a 20 us kernel)", "algorithmic_gflop_per_pair": GFLOP_PER_PAIR,
+                                   "traffic": None},
+                      "grouped": {"workload": f"{G} pairs of 4096 x 4096 in one sfd2_match_pairs_dev launch",
+                                  "pairs_per_s": world * G / (grouped_ms / 1e3), "kernel_ms": gk_ms,
+                                  "tflops": G * GFLOP_PER_PAIR / gk_ms if gk_ms else None,
+                                  "frac_of_peak": (G * GFLOP_PER_PAIR / gk_ms / Pk["tflops"]) if gk_ms else None},
+                      "e2e": {"value": world / hloc_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * 4096 * 128 * 4, "d2h_bytes_per_step": 4096 * (8 + 4),
+                              "note": "hloc plugin NearestNeighbor({'do_mutual_check': True}) inside the match_features.py:99-119 loop body: "
+                                      "[128,N] host arrays -> [1,128,N] CUDA tensors -> model(data) -> .cpu().short() / .cpu().half()",
+                              "itloc": {"value": world / itloc_s, "unit": "pairs/s",
+                                        "note": "it_loc Matcher(confs['NNM'])({'descriptors0': float64 ndarray [N,128], ...}) -> numpy"}},
+                      "one_to_many": {"workload": "4096 query x 50 db sets of 2000 descriptors", "grouped_ms": o2m_ms, "kernel_ms": ok_ms,
+                                      "tflops": o2m_gflop / ok_ms if ok_ms else None,
+                                      "frac_of_peak": (o2m_gflop / ok_ms / Pk["tflops_burst"]) if ok_ms else None,
                                       "per_pair_loop_ms": loop_ms, "pairs_per_s_grouped": 50 / (o2m_ms / 1e3)}},
-            "table": {"keypoints_last_step": kpts_total, "allgather_ms": gather_ms},
+            "pairs": {"value": n_pairs_total / (pairs_ms / 1e3), "unit": "pairs/s (2 extracts @1600x1200 top-4096 + 1 mutual-NN match)",
+                      "n_pairs": n_pairs_total, "pairs_per_gpu": n_pair_steps * P, "pairs_per_batch": P, "scaling": "weak",
+                      "workload": f"C5: pair s = (G(s), roll(G(s),(6,10))), frames resident in HBM as uint8, pairs[rank::world]; "
+                                  f"{PAIRS_AT_8} pairs at 8 GPUs = {PAIRS_AT_8 // 8} per GPU",
+                      "mutual_matches_last_batch": n_matched, "gpu_launches": pair_launches,
+                      "e2e": {"value": world * n_pair_e2e * P / pairs_e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * P * H * W * 3,
+                              "d2h_bytes_per_step": 2 * P * (TOPK * (2 + 1 + 128) * 4 + 4) + P * TOPK * 8,
+                              "note": "pinned uint8 host frames in; features of both frames + matches0 / sim0 to host"}},
+            "sweep": {"value": SWEEP_IMAGES / (sweep_ms / 1e3), "unit": "images/s", "images": SWEEP_IMAGES, "seconds": sweep_ms / 1e3,
+                      "scaling": "strong", "images_per_gpu": len(mine),
+                      "workload": "C4: 1040 distinct 1600x1200 images (Aachen v1.1 query count), images[rank::world] via sfd2_b200.shard, "
+                                  "uint8 frames resident in HBM", "keypoints_total": kpts_total, "allgather_ms": gather_ms},
             "other_modes": {k: {"value": world * B * K / (v / 1e3), "unit": "images/s", "note": "device-resident, same workload"}
                             for k, v in other.items()},
         }
@@ -386,10 +565,16 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_images} images of 1600x1200 top-4096 through the oracle port "
                                               f"(1 warm-up), best {best:.3f} s/image"}
-            r2, b2, _ = cpu_extract_rate(3, flush_denormal=True)
+            r2, b2, _ = cpu_extract_rate(2, flush_denormal=True)
             line["cpu_baseline_flush_denormal"] = {"value": r2, "unit": "images/s", "cores": threads, "kind": "port",
-                                                   "sample": f"3 images, torch.set_flush_denormal(True) (not the reference's "
+                                                   "sample": f"2 images, torch.set_flush_denormal(True) (not the reference's "
                                                              f"setting), best {b2:.3f} s/image"}
+            mrate = cpu_match_rate(10)
+            line["match"]["cpu_baseline"] = {"value": mrate, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                             "sample": "10 pairs of 4096 x 4096 through the hloc NearestNeighbor port"}
+            line["pairs"]["cpu_baseline"] = {"value": 1.0 / (2.0 / rate + 1.0 / mrate), "unit": "pairs/s", "cores": threads, "kind": "port",
+                                             "sample": "derived: 2 x measured per-image time + measured per-match time of this run "
+                                                       "(bench.py --impl reference --cpu-pairs N times whole pairs)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -408,6 +593,8 @@ def main():
     ap.add_argument("--no-other-modes", action="store_true", help="skip the short exact / fast timings reported beside the main one")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-images", type=int, default=2)
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="--impl reference: also time this many WHOLE pairs (2 extracts + match)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU in the C5 section (default 1250 = 10k at 8 GPUs)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -92,7 +92,7 @@ struct sfd2_ctx {
     unsigned* sec = nullptr; size_t cap_sec = 0;
     int *remap = nullptr, *efflen = nullptr, *done = nullptr; size_t cap_remap = 0, cap_efflen = 0, cap_done = 0;
     uint8_t* tab = nullptr; size_t cap_tab = 0;
-    static constexpr int kRing = 8;
+    static constexpr int kRing = 32;
     struct Slot { void* host = nullptr; size_t cap = 0; cudaEvent_t ev = nullptr; } ring[kRing];
     unsigned next = 0;
   } mws;
@@ -676,31 +676,40 @@ static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, con
   if (any_ids && (rc = reserve(m.remap, m.cap_remap, (size_t)prow * sizeof(int)))) return rc;
   if ((rc = reserve(m.efflen, m.cap_efflen, (size_t)nsets * sizeof(int)))) return rc;
   if ((rc = reserve(m.done, m.cap_done, (size_t)npairs * sizeof(int)))) return rc;
-  const size_t tab_bytes = opers.size() * sizeof(MOperD) + probs.size() * sizeof(MProbD);
-  if ((rc = reserve(m.tab, m.cap_tab, tab_bytes))) return rc;
-  // tables: pinned staging ring -> device (stream-ordered behind the previous call's kernels)
-  sfd2_ctx::MatchWs::Slot& slot = m.ring[m.next++ % sfd2_ctx::MatchWs::kRing];
-  if (!slot.ev) SFD2_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
-  else SFD2_CUDA(cudaEventSynchronize(slot.ev));      // the copy that last used this slot has completed
-  if (tab_bytes > slot.cap) {
-    if (slot.host) cudaFreeHost(slot.host);
-    slot.host = nullptr; slot.cap = 0;
-    SFD2_CUDA(cudaMallocHost(&slot.host, tab_bytes * 2));
-    slot.cap = tab_bytes * 2;
+  // tables: a single pair rides in the kernel parameters; bigger calls go through a pinned staging ring -> device
+  // (stream-ordered behind the previous call's kernels)
+  MTabInline inl{};
+  const MOperD* opers_dev = nullptr;
+  const MProbD* probs_dev = nullptr;
+  if (nsets <= 2 && npairs == 1) {
+    for (int i = 0; i < nsets; ++i) inl.opers[i] = opers[i];
+    inl.probs[0] = probs[0];
+  } else {
+    const size_t tab_bytes = opers.size() * sizeof(MOperD) + probs.size() * sizeof(MProbD);
+    if ((rc = reserve(m.tab, m.cap_tab, tab_bytes))) return rc;
+    sfd2_ctx::MatchWs::Slot& slot = m.ring[m.next++ % sfd2_ctx::MatchWs::kRing];
+    if (!slot.ev) SFD2_CUDA(cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+    else SFD2_CUDA(cudaEventSynchronize(slot.ev));      // the copy that last used this slot has completed
+    if (tab_bytes > slot.cap) {
+      if (slot.host) cudaFreeHost(slot.host);
+      slot.host = nullptr; slot.cap = 0;
+      SFD2_CUDA(cudaMallocHost(&slot.host, tab_bytes * 2));
+      slot.cap = tab_bytes * 2;
+    }
+    memcpy(slot.host, opers.data(), opers.size() * sizeof(MOperD));
+    memcpy(static_cast<uint8_t*>(slot.host) + opers.size() * sizeof(MOperD), probs.data(), probs.size() * sizeof(MProbD));
+    SFD2_CUDA(cudaMemcpyAsync(m.tab, slot.host, tab_bytes, cudaMemcpyHostToDevice, st));
+    SFD2_CUDA(cudaEventRecord(slot.ev, st));
+    opers_dev = reinterpret_cast<const MOperD*>(m.tab);
+    probs_dev = reinterpret_cast<const MProbD*>(m.tab + opers.size() * sizeof(MOperD));
   }
-  memcpy(slot.host, opers.data(), opers.size() * sizeof(MOperD));
-  memcpy(static_cast<uint8_t*>(slot.host) + opers.size() * sizeof(MOperD), probs.data(), probs.size() * sizeof(MProbD));
-  SFD2_CUDA(cudaMemcpyAsync(m.tab, slot.host, tab_bytes, cudaMemcpyHostToDevice, st));
-  SFD2_CUDA(cudaEventRecord(slot.ev, st));
-  const MOperD* opers_dev = reinterpret_cast<const MOperD*>(m.tab);
-  const MProbD* probs_dev = reinterpret_cast<const MProbD*>(m.tab + opers.size() * sizeof(MOperD));
   prof_begin(c, "match_prep", st);
-  rc = launch_match_prep(opers_dev, nsets, (int)prow, any_ids, m.hi, m.lo, m.remap, m.efflen, m.keys, passes == 2 ? m.sec : nullptr,
+  rc = launch_match_prep(opers_dev, &inl, nsets, (int)prow, any_ids, m.hi, m.lo, m.remap, m.efflen, m.keys, passes == 2 ? m.sec : nullptr,
                          koff, m.done, npairs, c->num_sms, st);
   prof_end(c, st);
   if (rc) return rc;
   TcMatchArgs a{};
-  a.opers = opers_dev; a.probs = probs_dev;
+  a.opers = opers_dev; a.probs = probs_dev; a.inl = inl;
   a.nprob = npairs; a.total_tiles = (int)tiles;
   a.passes = passes;
   a.cols = (passes == 1 && p->do_mutual_check) ? 1 : 0;

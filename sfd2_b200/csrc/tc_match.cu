@@ -23,6 +23,8 @@
 // into one fp32 accumulator, which reproduces the fp32 reference arg-max on real SFD2 descriptors; split==1 is single-pass.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "tc_match.cuh"
@@ -51,7 +53,9 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // ids -> order-preserving compaction table (desc_db[db_3D_ids != -1], it_loc/localize_cv2.py:540-555): one block per
 // operand with ids; remap[prow0 + k] = k-th row whose id != -1, efflen = number of such rows.
 __global__ void __launch_bounds__(1024)
-match_scan_ids_kernel(const MOperD* __restrict__ opers, int noper, int* __restrict__ efflen, int* __restrict__ remap) {
+match_scan_ids_kernel(const MOperD* __restrict__ opers_dev, const __grid_constant__ MTabInline inl, int noper,
+                      int* __restrict__ efflen, int* __restrict__ remap) {
+  const MOperD* opers = opers_dev ? opers_dev : inl.opers;
   __shared__ int warp_sums[32];
   __shared__ int base;
   for (int o = blockIdx.x; o < noper; o += gridDim.x) {
@@ -84,11 +88,12 @@ match_scan_ids_kernel(const MOperD* __restrict__ opers, int noper, int* __restri
 // fp32 descriptors -> fp16 hi / lo plane rows [prow][128] (rows >= the set's effective length are zero up to the next
 // multiple of 128), key / second-best / done-counter reset, effective lengths.  Block = 256 threads = 32 plane rows.
 __global__ void __launch_bounds__(256)
-match_prep_kernel(const MOperD* __restrict__ opers, int noper, int total_prows, __half* __restrict__ hi,
-                  __half* __restrict__ lo, const int* __restrict__ remap, int* __restrict__ efflen,
+match_prep_kernel(const MOperD* __restrict__ opers_dev, const __grid_constant__ MTabInline inl, int noper, int total_prows,
+                  __half* __restrict__ hi, __half* __restrict__ lo, const int* __restrict__ remap, int* __restrict__ efflen,
                   unsigned long long* __restrict__ keys, unsigned* __restrict__ sec, long long nkeys,
                   int* __restrict__ done, int nprob) {
   __shared__ float tile[128][33];
+  const MOperD* opers = opers_dev ? opers_dev : inl.opers;
   pdl_launch_dependents();   // the matcher kernel may start its prologue; it waits (griddepcontrol.wait) before reading
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   for (long long i = gtid; i < nkeys; i += gsz) { keys[i] = 0ull; if (sec) sec[i] = 0u; }
@@ -154,7 +159,7 @@ constexpr int TM_OP_BYTES = 128 * 128;   // 128 rows x 64 fp16 (one K half of on
 constexpr int TM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TM_EPI_THREADS = 256;
 constexpr int TM_ACC_BUFS = 4;           // 4 x 128 fp32 columns = the whole TMEM: the MMAs run up to three tiles ahead
-constexpr int TM_MAX_STAGES = 8;
+constexpr int TM_MAX_STAGES = 10;
 
 struct TileInfo {
   int p, pass, mt, nt;
@@ -168,14 +173,16 @@ struct TileInfo {
 // Linear tile -> (problem, pass, mt, nt).  Problems are laid out by their CAPACITY tile counts (host-known);
 // tiles beyond the effective extents (device-side counts) are skipped identically by all three warp roles.
 __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, int& p_cache, TileInfo& t) {
+  const MProbD* probs = a.probs ? a.probs : a.inl.probs;
+  const MOperD* opers = a.opers ? a.opers : a.inl.opers;
   int p = p_cache;
-  if (p < 0 || tile < a.probs[p].tile0 || tile >= a.probs[p].tile0 + a.probs[p].ntiles) {
+  if (p < 0 || tile < probs[p].tile0 || tile >= probs[p].tile0 + probs[p].ntiles) {
     int lo = 0, hi = a.nprob - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.probs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (probs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
     p = lo;
     p_cache = p;
   }
-  const MProbD pr = a.probs[p];
+  const MProbD pr = probs[p];
   int r = tile - pr.tile0;
   const int t0 = pr.tm * pr.tn;
   t.p = p;
@@ -186,7 +193,7 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, int& p
   t.nt = r - t.mt * tn;
   const int oa = t.pass ? pr.b : pr.a, ob = t.pass ? pr.a : pr.b;
   t.a_len = a.efflen[oa]; t.b_len = a.efflen[ob];
-  t.a_prow = a.opers[oa].prow0; t.b_prow = a.opers[ob].prow0;
+  t.a_prow = opers[oa].prow0; t.b_prow = opers[ob].prow0;
   t.ka = t.pass ? pr.key_b : pr.key_a;
   t.kb = t.pass ? pr.key_a : pr.key_b;
   t.rb = pr.tile0 + (t.pass ? t0 : 0) + t.mt * tn;     // linear index of the strip's first tile: unique per (p, pass, mt)
@@ -206,47 +213,70 @@ __device__ __forceinline__ bool tm_ratio_ok(float s0, unsigned second_ord, float
 // Tail of a problem (run by the 256 epilogue threads of the CTA that completed its last tile): decode keys, ratio /
 // distance tests, mutual check, index remap -> matches0 / sim0.  Same decisions as match_finish_kernel (match.cu).
 __device__ void tm_finish(const TcMatchArgs& a, int p, int et) {
-  const MProbD pr = a.probs[p];
+  const MProbD* probs = a.probs ? a.probs : a.inl.probs;
+  const MOperD* opers = a.opers ? a.opers : a.inl.opers;
+  const MProbD pr = probs[p];
   const int n0 = a.efflen[pr.a];
-  const int cap0 = a.opers[pr.a].cap;
-  const int* remap_b = a.opers[pr.b].ids ? a.remap + a.opers[pr.b].prow0 : nullptr;
+  const int cap0 = opers[pr.a].cap;
+  const int* remap_b = opers[pr.b].ids ? a.remap + opers[pr.b].prow0 : nullptr;
   // feature_matching (it_loc/localize_cv2.py:537-538): a db image with <= 3 keypoints that have a 3-D point yields no matches
   const bool too_few = remap_b && a.efflen[pr.b] <= 3;
-  const volatile unsigned long long* rk = a.keys + pr.key_a;
-  const volatile unsigned long long* ck = a.keys + pr.key_b;
-  const volatile unsigned* rs = a.sec ? a.sec + pr.key_a : nullptr;
-  const volatile unsigned* cs = a.sec ? a.sec + pr.key_b : nullptr;
+  const unsigned long long* rk = a.keys + pr.key_a;
+  const unsigned long long* ck = a.keys + pr.key_b;
+  const unsigned* rs = a.sec ? a.sec + pr.key_a : nullptr;
+  const unsigned* cs = a.sec ? a.sec + pr.key_b : nullptr;
   const bool plain = (a.ratio_mode & SFD2_MATCH_PLAIN_CODES) != 0;
   const bool hloc_scores = (a.ratio_mode & SFD2_MATCH_HLOC_SCORES) != 0;
   const bool i64 = (a.ratio_mode & SFD2_MATCH_I64) != 0;
   const int rmode = a.ratio_mode & 0xFF;
-  for (int i = et; i < cap0; i += TM_EPI_THREADS) {
-    int m = -1;
-    float s = 0.f;
-    bool keep_score = false;
-    const unsigned long long k = (i < n0 && !too_few) ? rk[i] : 0ull;
-    if (k != 0ull) {
-      const int j = m_key_idx(k);
-      s = m_key_sim(k);
-      bool ok = true;
-      if (a.ratio_th > 0.f) ok = tm_ratio_ok(s, rs[i], a.ratio_th, rmode);
-      if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - s)) <= a.dist_th * a.dist_th;     // nearest_neighbor.py:8,12-13
-      const bool row_ok = ok;   // find_nn's own mask for this row (decides whether hloc keeps its score)
-      keep_score = row_ok;
-      if (ok && a.mutual) {
-        const unsigned long long kc = ck[j];
-        ok = (kc != 0ull) && (m_key_idx(kc) == i);                                      // mutual_check, :19-24
-        if (ok && a.ratio_th > 0.f) ok = tm_ratio_ok(m_key_sim(kc), cs[j], a.ratio_th, rmode);
-        if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - m_key_sim(kc))) <= a.dist_th * a.dist_th;
-      }
-      // -1: rejected by the row's own tests, -2: only by the mutual check; matches report ORIGINAL db rows (remap)
-      m = ok ? (remap_b ? remap_b[j] : j) : ((row_ok && !plain) ? -2 : -1);
+  const bool ratio = a.ratio_th > 0.f;
+  // the tail is latency-bound (row key -> column key of the row's arg-max): R rows per thread per sweep, all loads of
+  // one level in flight together (one thread walking its rows one at a time cost 12 us for 4096 rows)
+  constexpr int R = 8;
+  for (int base = et; base < cap0; base += TM_EPI_THREADS * R) {
+    unsigned long long k[R], kc[R];
+    unsigned s2r[R], s2c[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int i = base + u * TM_EPI_THREADS;
+      k[u] = (i < n0 && !too_few) ? __ldcg(rk + i) : 0ull;
+      s2r[u] = (ratio && i < n0) ? __ldcg(rs + i) : 0u;
     }
-    // hloc's find_nn (nearest_neighbor.py:14-15): (sim + 1) / 2 where the row passed its own tests, else 0
-    if (hloc_scores) s = keep_score ? (s + 1.f) * 0.5f : 0.f;
-    if (i64) reinterpret_cast<long long*>(a.matches0)[pr.out_off + i] = (long long)m;
-    else a.matches0[pr.out_off + i] = m;
-    a.sim0[pr.out_off + i] = s;
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const bool need = k[u] != 0ull && a.mutual;
+      kc[u] = need ? __ldcg(ck + m_key_idx(k[u])) : 0ull;
+      s2c[u] = (need && ratio) ? __ldcg(cs + m_key_idx(k[u])) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const int i = base + u * TM_EPI_THREADS;
+      if (i >= cap0) continue;
+      int m = -1;
+      float s = 0.f;
+      bool keep_score = false;
+      if (k[u] != 0ull) {
+        const int j = m_key_idx(k[u]);
+        s = m_key_sim(k[u]);
+        bool ok = true;
+        if (ratio) ok = tm_ratio_ok(s, s2r[u], a.ratio_th, rmode);
+        if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - s)) <= a.dist_th * a.dist_th;     // nearest_neighbor.py:8,12-13
+        const bool row_ok = ok;   // find_nn's own mask for this row (decides whether hloc keeps its score)
+        keep_score = row_ok;
+        if (ok && a.mutual) {
+          ok = (kc[u] != 0ull) && (m_key_idx(kc[u]) == i);                                // mutual_check, :19-24
+          if (ok && ratio) ok = tm_ratio_ok(m_key_sim(kc[u]), s2c[u], a.ratio_th, rmode);
+          if (ok && a.dist_th > 0.f) ok = (2.f * (1.f - m_key_sim(kc[u]))) <= a.dist_th * a.dist_th;
+        }
+        // -1: rejected by the row's own tests, -2: only by the mutual check; matches report ORIGINAL db rows (remap)
+        m = ok ? (remap_b ? remap_b[j] : j) : ((row_ok && !plain) ? -2 : -1);
+      }
+      // hloc's find_nn (nearest_neighbor.py:14-15): (sim + 1) / 2 where the row passed its own tests, else 0
+      if (hloc_scores) s = keep_score ? (s + 1.f) * 0.5f : 0.f;
+      if (i64) reinterpret_cast<long long*>(a.matches0)[pr.out_off + i] = (long long)m;
+      else a.matches0[pr.out_off + i] = m;
+      a.sim0[pr.out_off + i] = s;
+    }
   }
 }
 
@@ -258,7 +288,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   const int nops = (a.split == 3) ? 2 : 1;
   const int a_slot_bytes = 2 * nops * TM_OP_BYTES;                 // resident A: [kb][plane] x 16 KB, two slots
   uint8_t* aslot = smem;
-  uint8_t* bring = smem + 2 * a_slot_bytes;                        // B ring: stage = one plane of one K half (16 KB)
+  uint8_t* bring = smem + (size_t)a.aslots * a_slot_bytes;                        // B ring: stage = one plane of one K half (16 KB)
   uint8_t* tail = bring + (size_t)a.stages * TM_OP_BYTES;
   unsigned long long* thr_key = reinterpret_cast<unsigned long long*>(tail);        // [2][128] column keys at tile start
   float* thr_sim = reinterpret_cast<float*>(tail + 2048);                           // [2][128] their similarities
@@ -299,7 +329,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         tm_locate(a, tile, pc, t);
         if (t.skip) continue;
         if (t.rb != prev_rb) {                    // new strip: load its A operand into the other slot
-          if (prev_rb >= 0) as ^= 1;
+          if (prev_rb >= 0) as = (as + 1 == a.aslots) ? 0 : as + 1;
           mbar_wait(&aempty[as], ((aph >> as) & 1u) ^ 1u);
           aph ^= 1u << as;
           uint8_t* dst = aslot + (size_t)as * a_slot_bytes;
@@ -331,7 +361,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         tm_locate(a, tile, pc, t);
         if (t.skip) continue;
         if (t.rb != prev_rb) {
-          if (prev_rb >= 0) as ^= 1;
+          if (prev_rb >= 0) as = (as + 1 == a.aslots) ? 0 : as + 1;
           mbar_wait(&afull[as], (aph >> as) & 1u);
           aph ^= 1u << as;
           prev_rb = t.rb;
@@ -410,7 +440,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (et == 0) {
         const int old = atomicAdd(a.done + cur_p, p_tiles);
-        *last_flag = (old + p_tiles == a.probs[cur_p].ntiles) ? 1 : 0;
+        *last_flag = (old + p_tiles == (a.probs ? a.probs : a.inl.probs)[cur_p].ntiles) ? 1 : 0;
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (*last_flag) {
@@ -551,14 +581,14 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------ host side
 constexpr size_t TM_TAIL_BYTES = 3072 + 512;      // thresholds + barriers
 
-size_t tm_smem_bytes(int split, int stages) {
+size_t tm_smem_bytes(int split, int aslots, int stages) {
   const int nops = split == 3 ? 2 : 1;
-  return 1024 + (size_t)2 * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
+  return 1024 + (size_t)aslots * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
 }
 
-int tm_stages(int split) {
+int tm_stages(int split, int aslots) {
   const int nops = split == 3 ? 2 : 1;
-  const size_t fixed = 1024 + (size_t)2 * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
+  const size_t fixed = 1024 + (size_t)aslots * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
   int s = (int)((227 * 1024 - fixed) / (size_t)TM_OP_BYTES);
   return s > TM_MAX_STAGES ? TM_MAX_STAGES : s;
 }
@@ -570,25 +600,29 @@ int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows) {
   return make_tmap_f16(tm, base, 2, dims, strides, box);
 }
 
-int launch_match_prep(const MOperD* opers_dev, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
+int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
                       int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
                       int num_sms, cudaStream_t st) {
   if (any_ids) {
-    match_scan_ids_kernel<<<noper < 4 * num_sms ? noper : 4 * num_sms, 1024, 0, st>>>(opers_dev, noper, efflen, remap);
+    match_scan_ids_kernel<<<noper < 4 * num_sms ? noper : 4 * num_sms, 1024, 0, st>>>(opers_dev, *inl, noper, efflen, remap);
     ++g_launches;
   }
   int blocks = total_prows / 32;
   if (blocks > 8 * num_sms) blocks = 8 * num_sms;
   if (blocks < 1) blocks = 1;
-  match_prep_kernel<<<blocks, 256, 0, st>>>(opers_dev, noper, total_prows, hi, lo, remap, efflen, keys, sec, nkeys, done, nprob);
+  match_prep_kernel<<<blocks, 256, 0, st>>>(opers_dev, *inl, noper, total_prows, hi, lo, remap, efflen, keys, sec, nkeys, done, nprob);
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
 }
 
 int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st) {
-  a.stages = tm_stages(a.split);
-  const size_t smem = tm_smem_bytes(a.split, a.stages);
+  // exact mode: ONE resident A slot (64 KB) leaves nine 16 KB B stages = 2.25 tiles in flight; with two A slots only five
+  // stages fit, fewer bytes in flight than TMA latency x the MMA's consumption rate (42 B/clk).  Single-pass: two slots.
+  static const int env_aslots = getenv("SFD2_TM_ASLOTS") ? atoi(getenv("SFD2_TM_ASLOTS")) : 0;
+  a.aslots = env_aslots ? env_aslots : (a.split == 3 ? 1 : 2);
+  a.stages = tm_stages(a.split, a.aslots);
+  const size_t smem = tm_smem_bytes(a.split, a.aslots, a.stages);
   SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (a.total_tiles <= 0) return SFD2_OK;
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;

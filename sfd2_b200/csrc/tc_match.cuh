@@ -25,13 +25,20 @@ struct MProbD {
   long long out_off;        // matches0 / sim0 rows of this pair start here (cap(a) rows)
 };
 
+// a single pair travels inside the kernel parameters (constant bank): no table upload on the latency path
+struct MTabInline {
+  MOperD opers[2];
+  MProbD probs[1];
+};
+
 struct TcMatchArgs {
-  const MOperD* opers;
+  const MOperD* opers;    // device tables; NULL = use `inl`
   const MProbD* probs;
+  MTabInline inl;
   int nprob, total_tiles;
   int passes;             // 1: one product, rows thread-local + columns through the threshold filter; 2: both products, rows only (top-2)
   int cols;               // passes == 1: reduce the columns too (mutual check)
-  int split, stages;
+  int split, stages, aslots;
   int mutual, ratio_mode;
   float dist_th, ratio_th;
   unsigned long long* keys;
@@ -43,10 +50,10 @@ struct TcMatchArgs {
   float* sim0;
 };
 
-size_t tm_smem_bytes(int split, int stages);
-int tm_stages(int split);
+size_t tm_smem_bytes(int split, int aslots, int stages);
+int tm_stages(int split, int aslots);
 int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows);
-int launch_match_prep(const MOperD* opers_dev, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
+int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
                       int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
                       int num_sms, cudaStream_t st);
 int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st);

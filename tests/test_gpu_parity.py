@@ -529,9 +529,20 @@ def test_pair_pipeline_matches_reference(golden):
     pairs = [(a, shifted_twin(a)), (synth_image_u8(77, H, W), shifted_twin(synth_image_u8(77, H, W)))]
     res = pair_sweep(pairs, WEIGHTS, precision="mixed", topk=K, conf_th=0.001, keep=True)
     r0 = res["pairs"][0]
-    assert np.array_equal(r0["keypoints0"].astype(np.int16), g["kp_xy"])
-    assert np.array_equal(r0["keypoints1"].astype(np.int16), g["kp_xy_b"])
-    m0 = r0["matches0"]
+    # same keypoint SETS as the reference on both frames (order may differ among near-equal scores): translate our row /
+    # column numbering into the fixture's before comparing matches
+    def to_ref(ours, ref):
+        idx = {tuple(k): i for i, k in enumerate(ref.astype(np.int64))}
+        perm = np.array([idx.get(tuple(k), -1) for k in ours.astype(np.int64)])
+        assert (perm >= 0).all() and len(set(perm.tolist())) == len(ref), "keypoint sets differ from the reference"
+        return perm
+    p0, p1 = to_ref(r0["keypoints0"], g["kp_xy"]), to_ref(r0["keypoints1"], g["kp_xy_b"])
+    _log_count("pair_pipeline_rows_out_of_order[mixed-c2]", int((p0 != np.arange(len(p0))).sum()))
+    m0 = np.full(len(p0), -1, np.int64)
+    ours = r0["matches0"]
+    m0[p0] = np.where(ours >= 0, p1[np.maximum(ours, 0)], -1)
+    sim = np.zeros(len(p0), np.float32)
+    sim[p0] = r0["sim0"]
     bad = np.nonzero(m0 != g["hloc_matches0"])[0]
     _log_count("pair_pipeline_rows_differing[mixed-c2]", int(len(bad)))
     # our descriptors differ from the reference's by <= 1e-3 (single-pass head), so a near-tied arg-max may flip
@@ -541,7 +552,7 @@ def test_pair_pipeline_matches_reference(golden):
         cols = {int(c) for c in (m0[i], g["hloc_matches0"][i], nn12[i]) if c >= 0}
         assert gap[i] < 4e-3 or any(cgap[c] < 4e-3 for c in cols), (int(i), float(gap[i]))
     assert len(bad) <= 0.01 * len(m0)
-    assert np.abs((r0["sim0"] + 1) / 2 - g["hloc_scores0"]).max() <= TOL
+    assert np.abs((sim + 1) / 2 - g["hloc_scores0"]).max() <= TOL
     assert res["pairs"][1]["matches0"].shape == (len(res["pairs"][1]["keypoints0"]),)
     assert (res["pairs"][1]["matches0"] >= 0).sum() > 1000
 
