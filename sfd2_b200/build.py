@@ -17,7 +17,8 @@ SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_match.cu"
 # hardware probes (tools/umma_probe.py, tools/mma_rate_probe.py): measurement scaffolding, only on request
 if os.environ.get("SFD2_WITH_PROBES") == "1":
     SOURCES.append("umma_probe.cu")
-HEADERS = ["common.cuh", "ptx.cuh", "probes.h", os.path.join("..", "..", "include", "sfd2_b200.h")]
+# every header under csrc/ (a stale api.o once ran against a changed TcMatchArgs layout: tc_match.cuh was missing here)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "sfd2_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -55,11 +55,10 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __global__ void __launch_bounds__(1024)
 match_scan_ids_kernel(const MOperD* __restrict__ opers_dev, const __grid_constant__ MTabInline inl, int noper,
                       int* __restrict__ efflen, int* __restrict__ remap) {
-  const MOperD* opers = opers_dev ? opers_dev : inl.opers;
   __shared__ int warp_sums[32];
   __shared__ int base;
   for (int o = blockIdx.x; o < noper; o += gridDim.x) {
-    const MOperD op = opers[o];
+    const MOperD op = opers_dev ? opers_dev[o] : (o ? inl.opers[1] : inl.opers[0]);
     if (!op.ids) continue;
     int n = op.cap;
     if (op.count) n = min(n, max(0, *op.count));
@@ -93,16 +92,22 @@ match_prep_kernel(const MOperD* __restrict__ opers_dev, const __grid_constant__ 
                   unsigned long long* __restrict__ keys, unsigned* __restrict__ sec, long long nkeys,
                   int* __restrict__ done, int nprob) {
   __shared__ float tile[128][33];
-  const MOperD* opers = opers_dev ? opers_dev : inl.opers;
   pdl_launch_dependents();   // the matcher kernel may start its prologue; it waits (griddepcontrol.wait) before reading
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
   for (long long i = gtid; i < nkeys; i += gsz) { keys[i] = 0ull; if (sec) sec[i] = 0u; }
   for (int i = gtid; i < nprob; i += gsz) done[i] = 0;
   for (int g = blockIdx.x; g < total_prows / 32; g += gridDim.x) {
     const int R0 = g * 32;
-    int a = 0, b = noper - 1;
-    while (a < b) { const int mid = (a + b + 1) >> 1; if (opers[mid].prow0 <= R0) a = mid; else b = mid - 1; }
-    const MOperD op = opers[a];
+    int a = 0;
+    MOperD op;
+    if (opers_dev) {
+      int b = noper - 1;
+      while (a < b) { const int mid = (a + b + 1) >> 1; if (__ldg(&opers_dev[mid].prow0) <= R0) a = mid; else b = mid - 1; }
+      op = opers_dev[a];
+    } else {               // single pair: tables in the kernel parameters, static indices only (constant bank)
+      a = (noper > 1 && R0 >= inl.opers[1].prow0) ? 1 : 0;
+      op = a ? inl.opers[1] : inl.opers[0];
+    }
     int n = op.cap;
     if (op.ids) n = efflen[a];                            // written by match_scan_ids_kernel (earlier launch)
     else if (op.count) n = min(n, max(0, *op.count));
@@ -170,33 +175,58 @@ struct TileInfo {
   bool skip;
 };
 
+// Everything tm_locate needs about one problem, fetched ONCE per problem per thread: the tables live in global memory
+// or in the kernel's parameter space, and a handful of dependent loads per tile (through a generic pointer into the
+// parameter window they cost ~1 us each) made the single-pair call take 58 us instead of 33.
+struct ProbCache {
+  int p = -1;
+  int tile0 = 0, ntiles = 0, tm = 0, tn = 0;
+  int len_a = 0, len_b = 0, prow_a = 0, prow_b = 0;
+  long long key_a = 0, key_b = 0;
+};
+
 // Linear tile -> (problem, pass, mt, nt).  Problems are laid out by their CAPACITY tile counts (host-known);
 // tiles beyond the effective extents (device-side counts) are skipped identically by all three warp roles.
-__device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, int& p_cache, TileInfo& t) {
-  const MProbD* probs = a.probs ? a.probs : a.inl.probs;
-  const MOperD* opers = a.opers ? a.opers : a.inl.opers;
-  int p = p_cache;
-  if (p < 0 || tile < probs[p].tile0 || tile >= probs[p].tile0 + probs[p].ntiles) {
-    int lo = 0, hi = a.nprob - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (probs[mid].tile0 <= tile) lo = mid; else hi = mid - 1; }
-    p = lo;
-    p_cache = p;
+__device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCache& c, TileInfo& t) {
+  if (c.p < 0 || tile < c.tile0 || tile >= c.tile0 + c.ntiles) {
+    MProbD pr;
+    MOperD oa, ob;
+    int p = 0;
+    if (a.probs) {
+      int lo = 0, hi = a.nprob - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (__ldg(&a.probs[mid].tile0) <= tile) lo = mid; else hi = mid - 1; }
+      p = lo;
+      pr = a.probs[p];
+      oa = a.opers[pr.a];
+      ob = a.opers[pr.b];
+    } else {                 // single pair: the tables are kernel parameters (constant bank, static indices)
+      pr = a.inl.probs[0];
+      oa = a.inl.opers[0];
+      ob = a.inl.opers[1];
+      if (pr.a == pr.b) ob = oa;
+      else if (pr.a == 1) { oa = a.inl.opers[1]; ob = a.inl.opers[0]; }
+    }
+    c.p = p;
+    c.tile0 = pr.tile0; c.ntiles = pr.ntiles; c.tm = pr.tm; c.tn = pr.tn;
+    // host-known sizes need no round trip to the prep kernel's output
+    c.len_a = (oa.count || oa.ids) ? a.efflen[pr.a] : oa.cap;
+    c.len_b = (ob.count || ob.ids) ? a.efflen[pr.b] : ob.cap;
+    c.prow_a = oa.prow0; c.prow_b = ob.prow0;
+    c.key_a = pr.key_a; c.key_b = pr.key_b;
   }
-  const MProbD pr = probs[p];
-  int r = tile - pr.tile0;
-  const int t0 = pr.tm * pr.tn;
-  t.p = p;
+  int r = tile - c.tile0;
+  const int t0 = c.tm * c.tn;
+  t.p = c.p;
   t.pass = (r >= t0) ? 1 : 0;
   if (t.pass) r -= t0;
-  const int tn = t.pass ? pr.tm : pr.tn;
+  const int tn = t.pass ? c.tm : c.tn;
   t.mt = r / tn;
   t.nt = r - t.mt * tn;
-  const int oa = t.pass ? pr.b : pr.a, ob = t.pass ? pr.a : pr.b;
-  t.a_len = a.efflen[oa]; t.b_len = a.efflen[ob];
-  t.a_prow = opers[oa].prow0; t.b_prow = opers[ob].prow0;
-  t.ka = t.pass ? pr.key_b : pr.key_a;
-  t.kb = t.pass ? pr.key_a : pr.key_b;
-  t.rb = pr.tile0 + (t.pass ? t0 : 0) + t.mt * tn;     // linear index of the strip's first tile: unique per (p, pass, mt)
+  t.a_len = t.pass ? c.len_b : c.len_a; t.b_len = t.pass ? c.len_a : c.len_b;
+  t.a_prow = t.pass ? c.prow_b : c.prow_a; t.b_prow = t.pass ? c.prow_a : c.prow_b;
+  t.ka = t.pass ? c.key_b : c.key_a;
+  t.kb = t.pass ? c.key_a : c.key_b;
+  t.rb = c.tile0 + (t.pass ? t0 : 0) + t.mt * tn;     // linear index of the strip's first tile: unique per (p, pass, mt)
   t.skip = (t.mt * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
 }
 
@@ -213,12 +243,17 @@ __device__ __forceinline__ bool tm_ratio_ok(float s0, unsigned second_ord, float
 // Tail of a problem (run by the 256 epilogue threads of the CTA that completed its last tile): decode keys, ratio /
 // distance tests, mutual check, index remap -> matches0 / sim0.  Same decisions as match_finish_kernel (match.cu).
 __device__ void tm_finish(const TcMatchArgs& a, int p, int et) {
-  const MProbD* probs = a.probs ? a.probs : a.inl.probs;
-  const MOperD* opers = a.opers ? a.opers : a.inl.opers;
-  const MProbD pr = probs[p];
+  MProbD pr;
+  MOperD oa, ob;
+  if (a.probs) { pr = a.probs[p]; oa = a.opers[pr.a]; ob = a.opers[pr.b]; }
+  else {
+    pr = a.inl.probs[0]; oa = a.inl.opers[0]; ob = a.inl.opers[1];
+    if (pr.a == pr.b) ob = oa;
+    else if (pr.a == 1) { oa = a.inl.opers[1]; ob = a.inl.opers[0]; }
+  }
   const int n0 = a.efflen[pr.a];
-  const int cap0 = opers[pr.a].cap;
-  const int* remap_b = opers[pr.b].ids ? a.remap + opers[pr.b].prow0 : nullptr;
+  const int cap0 = oa.cap;
+  const int* remap_b = ob.ids ? a.remap + ob.prow0 : nullptr;
   // feature_matching (it_loc/localize_cv2.py:537-538): a db image with <= 3 keypoints that have a 3-D point yields no matches
   const bool too_few = remap_b && a.efflen[pr.b] <= 3;
   const unsigned long long* rk = a.keys + pr.key_a;
@@ -280,6 +315,21 @@ __device__ void tm_finish(const TcMatchArgs& a, int p, int et) {
   }
 }
 
+// Column slow path (rare once a column has seen a few hundred rows): warp arg-max of the candidates of ONE column
+// (lowest row wins among equal values) and one atomicMax by the winner.  Kept out of line so that the common path
+// of the filter stays a compare and a predicated bit-set per column (inlined, the compiler hoisted a CREDUX per column
+// into the common path: 7000 cycles per tile).
+__device__ __noinline__ void tm_col_slow(float v, bool cand, int lane, int row, unsigned long long seen,
+                                         unsigned long long* gaddr) {
+  const unsigned s = cand ? m_ord_f32(v) : 0u;
+  const unsigned mx = __reduce_max_sync(0xffffffffu, s);
+  const unsigned w = __ballot_sync(0xffffffffu, cand && s == mx);
+  if (lane == __ffs(w) - 1) {
+    const unsigned long long key = ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+    if (key > seen) atomicMax(gaddr, key);
+  }
+}
+
 __global__ void __launch_bounds__(TM_THREADS, 1)
 tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const __grid_constant__ TcMatchArgs a) {
@@ -322,7 +372,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (one elected lane)
     if (elect_one()) {
-      int stage = 0, prev_rb = -1, as = 0, pc = -1;
+      int stage = 0, prev_rb = -1, as = 0;
+      ProbCache pc;
       uint32_t phase = 0, aph = 0u;             // bit s of aph = phase of A slot s
       TileInfo t;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -354,7 +405,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     // ---------------------------------------------------------------- MMA issuer (one elected lane)
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(128, 128);
-      int stage = 0, buf = 0, prev_rb = -1, as = 0, pc = -1, pc2 = -1;
+      int stage = 0, buf = 0, prev_rb = -1, as = 0;
+      ProbCache pc, pc2;
       uint32_t phase = 0, bphase = 0, aph = 0u;
       TileInfo t, t2;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
@@ -411,9 +463,10 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const int et = (int)threadIdx.x - 64;
     const int q = warp & 3, h = (warp - 2) >> 2;
     const bool top2 = a.passes == 2;
-    int buf = 0, pc = -1, par = 0;
+    int buf = 0, par = 0;
+    ProbCache pc;
     uint32_t bphase = 0;
-    int cur_rb = -1, cur_p = -1, p_tiles = 0;
+    int cur_rb = -1, cur_p = -1, p_tiles = 0, cur_ntiles = 0;
     long long cur_ka = 0;
     int cur_i = 0;
     bool cur_valid = false;
@@ -424,8 +477,10 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     auto flush_rows = [&]() {          // merge this thread's strip result into the row keys
       if (cur_rb >= 0 && cur_valid && rbest_j >= 0) {
         const unsigned long long key = m_key(rbest, rbest_j);
-        const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i, key);
-        if (top2) {
+        if (!top2) {
+          atomicMax(a.keys + cur_ka + cur_i, key);
+        } else {
+          const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i, key);
           // every partial best except the final winner loses exactly one atomicMax: it is a second-best candidate
           float cand = rsec;
           if (old != 0ull) cand = fmaxf(cand, fminf(m_key_sim(old), rbest));
@@ -436,17 +491,16 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     };
     auto leave_problem = [&]() {       // count this CTA's tiles of problem cur_p; the CTA completing the problem finishes it
       if (cur_p < 0) return;
-      __threadfence();
+      // release: the CTA barrier orders every epilogue thread's atomics before thread 0's acq_rel RMW on the counter
+      // (cumulativity); acquire: the finisher's loads (ld.global.cg, L2) come after that RMW and the second barrier
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (et == 0) {
-        const int old = atomicAdd(a.done + cur_p, p_tiles);
-        *last_flag = (old + p_tiles == (a.probs ? a.probs : a.inl.probs)[cur_p].ntiles) ? 1 : 0;
+        int old;
+        asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(a.done + cur_p), "r"(p_tiles) : "memory");
+        *last_flag = (old + p_tiles == cur_ntiles) ? 1 : 0;
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");
-      if (*last_flag) {
-        __threadfence();
-        tm_finish(a, cur_p, et);
-      }
+      if (*last_flag && !(a.debug & 4)) tm_finish(a, cur_p, et);
       asm volatile("bar.sync 2, 256;" ::: "memory");    // last_flag is rewritten by the next problem
       p_tiles = 0;
     };
@@ -458,6 +512,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         cur_rb = -1;
         leave_problem();
         cur_p = t.p;
+        cur_ntiles = pc.ntiles;
       }
       ++p_tiles;
       if (t.skip) continue;
@@ -468,7 +523,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         cur_i = t.mt * TM_TILE + q * 32 + lane;
         cur_valid = cur_i < t.a_len;
       }
-      const bool want_cols = a.cols && t.pass == 0;
+      const bool want_cols = a.cols && t.pass == 0 && !(a.debug & 2);
       const int c0 = t.nt * TM_TILE;
       unsigned long long kc = 0ull;
       if (want_cols && et < 128) kc = __ldcg(a.keys + t.kb + c0 + et);      // in flight while the MMAs finish
@@ -477,7 +532,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       if (want_cols) {
         if (et < 128) {
           thr_key[par * 128 + et] = kc;
-          thr_sim[par * 128 + et] = kc ? m_key_sim(kc) : -CUDART_INF_F;
+          thr_sim[par * 128 + et] = kc ? m_key_sim(kc) : -3.0e38f;    // cold column: every VALID value passes (-inf = invalid never does)
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -489,6 +544,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);   // this warp's share of the accumulator is in registers
+      if (a.debug & 1) { if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; } continue; }
       float f[64];
       const int cols_valid = t.b_len - c0 - h * 64;           // valid columns among this warp's 64
       if (cols_valid >= 64 && cur_valid) {
@@ -547,6 +603,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         const float* ts = thr_sim + par * 128 + h * 64;
         const unsigned long long* tk = thr_key + par * 128 + h * 64;
         unsigned long long* gk = a.keys + t.kb + c0 + h * 64;
+        unsigned m0 = 0u, m1 = 0u;                    // this thread's candidate columns (invalid entries are -inf: never >=)
 #pragma unroll
         for (int j4 = 0; j4 < 16; ++j4) {
           const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
@@ -554,16 +611,15 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const int j = j4 * 4 + jj;
-            const bool pj = f[j] >= thv[jj] && f[j] > -CUDART_INF_F;
-            if (__any_sync(0xffffffffu, pj)) {
-              const unsigned s = pj ? m_ord_f32(f[j]) : 0u;
-              const unsigned mx = __reduce_max_sync(0xffffffffu, s);
-              const unsigned w = __ballot_sync(0xffffffffu, pj && s == mx);
-              if (lane == __ffs(w) - 1) {                        // lowest row of the warp among equal maxima
-                const unsigned long long key = ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)cur_i);
-                if (key > tk[j]) atomicMax(gk + j, key);
-              }
-            }
+            if (f[j] >= thv[jj]) { if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
+          }
+        }
+        const unsigned w0 = __reduce_or_sync(0xffffffffu, m0), w1 = __reduce_or_sync(0xffffffffu, m1);
+        if (w0 | w1) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const unsigned wj = j < 32 ? w0 : w1, mj = j < 32 ? m0 : m1;
+            if ((wj >> (j & 31)) & 1u) tm_col_slow(f[j], (mj >> (j & 31)) & 1u, lane, cur_i, tk[j], gk + j);
           }
         }
         par ^= 1;
@@ -621,6 +677,8 @@ int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchA
   // stages fit, fewer bytes in flight than TMA latency x the MMA's consumption rate (42 B/clk).  Single-pass: two slots.
   static const int env_aslots = getenv("SFD2_TM_ASLOTS") ? atoi(getenv("SFD2_TM_ASLOTS")) : 0;
   a.aslots = env_aslots ? env_aslots : (a.split == 3 ? 1 : 2);
+  static const int env_debug = getenv("SFD2_TM_DEBUG") ? atoi(getenv("SFD2_TM_DEBUG")) : 0;
+  a.debug = env_debug;
   a.stages = tm_stages(a.split, a.aslots);
   const size_t smem = tm_smem_bytes(a.split, a.aslots, a.stages);
   SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -40,6 +40,7 @@ struct TcMatchArgs {
   int cols;               // passes == 1: reduce the columns too (mutual check)
   int split, stages, aslots;
   int mutual, ratio_mode;
+  int debug;              // SFD2_TM_DEBUG (experiments only): 1 = epilogue handshakes without reductions, 2 = no column path, 4 = no finish tail
   float dist_th, ratio_th;
   unsigned long long* keys;
   unsigned* sec;          // second-best similarities (ordered uint), passes == 2 only
