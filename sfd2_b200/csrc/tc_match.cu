@@ -46,6 +46,15 @@ __device__ __forceinline__ unsigned long long m_key(float sim, int idx) {
 __device__ __forceinline__ int m_key_idx(unsigned long long k) { return (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull)); }
 __device__ __forceinline__ float m_key_sim(unsigned long long k) { return m_unord_f32((unsigned)(k >> 32)); }
 
+// fire-and-forget 64-bit max (REDG): atomicMax() compiles to ATOMG even when the result is unused, and the warp then
+// waits out the L2 round trip of every key update (~2.9 us per tile in the column path)
+__device__ __forceinline__ void red_max_u64(unsigned long long* addr, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_u32(unsigned* addr, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -221,7 +230,9 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCa
   if (t.pass) r -= t0;
   const int tn = t.pass ? c.tm : c.tn;
   t.mt = r / tn;
-  t.nt = r - t.mt * tn;
+  // strips start at skewed columns: CTAs working on different row-blocks of one problem at the same time then sit on
+  // different column tiles, so a column's threshold is established by whoever comes first instead of being cold for all
+  t.nt = (r - t.mt * tn + t.mt * 5) % tn;
   t.a_len = t.pass ? c.len_b : c.len_a; t.b_len = t.pass ? c.len_a : c.len_b;
   t.a_prow = t.pass ? c.prow_b : c.prow_a; t.b_prow = t.pass ? c.prow_a : c.prow_b;
   t.ka = t.pass ? c.key_b : c.key_a;
@@ -315,18 +326,24 @@ __device__ void tm_finish(const TcMatchArgs& a, int p, int et) {
   }
 }
 
-// Column slow path (rare once a column has seen a few hundred rows): warp arg-max of the candidates of ONE column
-// (lowest row wins among equal values) and one atomicMax by the winner.  Kept out of line so that the common path
-// of the filter stays a compare and a predicated bit-set per column (inlined, the compiler hoisted a CREDUX per column
-// into the common path: 7000 cycles per tile).
-__device__ __noinline__ void tm_col_slow(float v, bool cand, int lane, int row, unsigned long long seen,
-                                         unsigned long long* gaddr) {
-  const unsigned s = cand ? m_ord_f32(v) : 0u;
-  const unsigned mx = __reduce_max_sync(0xffffffffu, s);
-  const unsigned w = __ballot_sync(0xffffffffu, cand && s == mx);
-  if (lane == __ffs(w) - 1) {
-    const unsigned long long key = ((unsigned long long)mx << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
-    if (key > seen) atomicMax(gaddr, key);
+// Column reduction of a COLD tile (thresholds not yet established: most of a warp's 64 columns have candidates):
+// butterfly transpose-reduce over the warp's 32 rows.  Each step halves the columns a lane is responsible for and
+// exchanges the other half with lane ^ half; after five steps lane L holds (max value, lowest row lane attaining it)
+// of column L.  31 exchange steps per 32 columns instead of 5 shuffles per column, and no REDUX (a CREDUX per column
+// cost ~100 cycles each: 7000 cycles per tile).
+__device__ __forceinline__ void tm_butterfly32(unsigned (&v)[32], unsigned (&id)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const unsigned mv = up ? v[j + half] : v[j], mi = up ? id[j + half] : id[j];
+      const unsigned ov = up ? v[j] : v[j + half], oi = up ? id[j] : id[j + half];
+      const unsigned rv = __shfl_xor_sync(0xffffffffu, ov, half), ri = __shfl_xor_sync(0xffffffffu, oi, half);
+      const bool take = (rv > mv) || (rv == mv && ri < mi);
+      v[j] = take ? rv : mv;
+      id[j] = take ? ri : mi;
+    }
   }
 }
 
@@ -478,13 +495,13 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       if (cur_rb >= 0 && cur_valid && rbest_j >= 0) {
         const unsigned long long key = m_key(rbest, rbest_j);
         if (!top2) {
-          atomicMax(a.keys + cur_ka + cur_i, key);
+          red_max_u64(a.keys + cur_ka + cur_i, key);
         } else {
           const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i, key);
           // every partial best except the final winner loses exactly one atomicMax: it is a second-best candidate
           float cand = rsec;
           if (old != 0ull) cand = fmaxf(cand, fminf(m_key_sim(old), rbest));
-          if (cand > -CUDART_INF_F) atomicMax(a.sec + cur_ka + cur_i, m_ord_f32(cand));
+          if (cand > -CUDART_INF_F) red_max_u32(a.sec + cur_ka + cur_i, m_ord_f32(cand));
         }
       }
       rbest = -CUDART_INF_F; rsec = -CUDART_INF_F; rbest_j = -1;
@@ -541,10 +558,18 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       tmem_ld32(taddr, v0);
       tmem_ld32(taddr + 32, v1);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);   // this warp's share of the accumulator is in registers
-      if (a.debug & 1) { if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; } continue; }
+      // the accumulator is in registers: hand the buffer back now - unless the column path may come back for single
+      // columns (warm tiles re-read the few candidate columns from TMEM instead of indexing registers dynamically)
+      if (!want_cols) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+      }
+      if (a.debug & 1) {
+        if (want_cols) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty[buf]); par ^= 1; }
+        if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
+        continue;
+      }
       float f[64];
       const int cols_valid = t.b_len - c0 - h * 64;           // valid columns among this warp's 64
       if (cols_valid >= 64 && cur_valid) {
@@ -615,13 +640,51 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           }
         }
         const unsigned w0 = __reduce_or_sync(0xffffffffu, m0), w1 = __reduce_or_sync(0xffffffffu, m1);
-        if (w0 | w1) {
+        const int hot = __popc(w0) + __popc(w1);          // columns in which some row of this warp is a candidate
+        if (hot >= 12 && !(a.debug & 8)) {
+          // cold tile: full warp arg-max of all 64 columns (two butterflies), one atomicMax per column by the lane that
+          // ends up owning it
+          const int row0 = cur_i - lane;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const unsigned wj = j < 32 ? w0 : w1, mj = j < 32 ? m0 : m1;
-            if ((wj >> (j & 31)) & 1u) tm_col_slow(f[j], (mj >> (j & 31)) & 1u, lane, cur_i, tk[j], gk + j);
+          for (int g = 0; g < 2; ++g) {
+            unsigned v[32], id[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = f[g * 32 + j];
+              v[j] = (x > -CUDART_INF_F) ? m_ord_f32(x) : 0u;      // 0 = invalid row / column: never wins
+              id[j] = (unsigned)lane;
+            }
+            tm_butterfly32(v, id, lane);
+            if (v[0] != 0u) {
+              const unsigned long long key = ((unsigned long long)v[0] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row0 + (int)id[0]));
+              if (key > tk[g * 32 + lane]) red_max_u64(gk + g * 32 + lane, key);
+            }
+          }
+        } else if ((w0 | w1) && !(a.debug & 8)) {
+          // warm tile: a handful of columns have a candidate somewhere in the warp.  Walk the set bits of the warp-wide
+          // mask (uniform loop), fetch that ONE column from TMEM again, and let the candidate lanes push their keys
+          // (atomic max resolves ties: lowest row wins).  [A fully unrolled predicated loop over all 64 columns cost
+          // ~650 instructions per warp per tile.]
+#pragma unroll 1
+          for (int g = 0; g < 2; ++g) {
+            unsigned wm = g ? w1 : w0;
+            const unsigned mm = g ? m1 : m0;
+            while (wm) {
+              const int jb = __ffs(wm) - 1;
+              wm &= wm - 1u;
+              const int j = g * 32 + jb;
+              const float x = __uint_as_float(tmem_ld1(taddr + (uint32_t)j));
+              tmem_ld_wait();
+              if ((mm >> jb) & 1u) {
+                const unsigned long long key = m_key(x, cur_i);
+                if (key > tk[j]) red_max_u64(gk + j, key);
+              }
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);   // now the buffer may be overwritten
         par ^= 1;
       }
       if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
