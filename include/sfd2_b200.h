@@ -144,6 +144,13 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* ctx, const void* img_host, int img_dtyp
  * sfd2_extract_host calls it itself.  (The reference has no such limit: nets/extractor.py:158 uses nonzero().) */
 SFD2_API int sfd2_extract_status(sfd2_ctx* ctx, void* stream);
 
+/* Replaces the arithmetic of ImageDataset.__getitem__ (extract_localization.py:158-190): decoded uint8 image [h, w, 3]
+ * (DEVICE pointer; swap_rb = 1 for cv2.imread's BGR order) -> float32 RGB [3, h_new, w_new] in the reference's value
+ * range (cv2.resize INTER_CUBIC on the float image, then / 255; no clamping).  h_new == h && w_new == w: conversion only.
+ * The output is what sfd2_extract_dev takes as SFD2_IMG_F32_NCHW.  Asynchronous on `stream`. */
+SFD2_API int sfd2_preprocess_dev(sfd2_ctx* ctx, const uint8_t* img_u8_dev, int h, int w, int swap_rb, int h_new, int w_new,
+                                 float* out_dev, void* stream);
+
 /* Replaces NearestNeighbor._forward (hloc/matchers/nearest_neighbor.py:38-57) and
  * Matcher.mutual_nn_matcher (it_loc/matcher.py:122-130).
  *   d0 float32 [n0, d] row-major, d1 float32 [n1, d]   (d = 128)

@@ -345,3 +345,70 @@ def mutual_nn_exact(d0: np.ndarray, d1: np.ndarray):
     part = np.partition(sim, -2, axis=1) if sim.shape[1] > 1 else None
     gap = (part[:, -1] - part[:, -2]) if part is not None else np.full(sim.shape[0], np.inf)
     return nn12, nn21, gap, sim.max(1)
+
+
+# ---------------------------------------------------------------------------------------------- input leg
+def resize_target(h: int, w: int, resize_max=None, resize_force=False):
+    """extract_localization.py:171-175: (h_new, w_new) of ImageDataset's resize, or (h, w) when none happens."""
+    if resize_max and (resize_force or max(w, h) > resize_max):
+        scale = resize_max / max(h, w)
+        return int(round(h * scale)), int(round(w * scale))
+    return h, w
+
+
+def _cubic_coeffs(x: np.ndarray) -> np.ndarray:
+    """OpenCV interpolateCubic (imgproc/resize.cpp, opencv-python 4.13 in this image; the reference pins no version),
+    A = -0.75, float32 arithmetic, c3 = 1 - c0 - c1 - c2."""
+    x = x.astype(np.float32)
+    A = np.float32(-0.75)
+    one = np.float32(1)
+    x1 = x + one
+    c0 = ((A * x1 - np.float32(5) * A) * x1 + np.float32(8) * A) * x1 - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    y = one - x
+    c2 = ((A + np.float32(2)) * y - (A + np.float32(3))) * y * y + one
+    c3 = one - c0 - c1 - c2
+    return np.stack([c0, c1, c2, c3], -1).astype(np.float32)
+
+
+def cv2_resize_cubic_f32(img: np.ndarray, w_new: int, h_new: int) -> np.ndarray:
+    """cv2.resize(img_float32_HWC, (w_new, h_new), interpolation=cv2.INTER_CUBIC) restated with numpy float32
+    operations in the scalar code's order: horizontal 4-tap pass on the clamped source rows, then the vertical
+    4-tap combination; no rounding, no saturation.  Pinned against cv2 itself in tests/test_preprocess.py."""
+    h, w = img.shape[:2]
+    img = img.astype(np.float32)
+
+    def axis(n_dst, n_src):
+        scale = 1.0 / (float(n_dst) / float(n_src))
+        f = ((np.arange(n_dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        frac = f - s.astype(np.float32)
+        idx = np.clip(s[:, None] - 1 + np.arange(4)[None], 0, n_src - 1)
+        return idx, _cubic_coeffs(frac)
+    xi, xa = axis(w_new, w)
+    yi, yb = axis(h_new, h)
+    # horizontal pass on every source row that is needed
+    hor = img[:, xi[:, 0]] * xa[None, :, 0, None]
+    for k in range(1, 4):
+        hor = hor + img[:, xi[:, k]] * xa[None, :, k, None]
+    out = hor[yi[:, 0]] * yb[:, 0, None, None]
+    for k in range(1, 4):
+        out = out + hor[yi[:, k]] * yb[:, k, None, None]
+    return out.astype(np.float32)
+
+
+def image_dataset_item(bgr_u8: np.ndarray, resize_max=None, resize_force=False, use_cv2=False):
+    """ImageDataset.__getitem__ (extract_localization.py:158-190) from the decoded BGR uint8 image on:
+    -> {'image': float32 [3, h', w'] RGB / 255 (not clamped), 'original_size': [w, h]}."""
+    image = bgr_u8[:, :, ::-1].astype(np.float32)
+    h, w = image.shape[:2]
+    hn, wn = resize_target(h, w, resize_max, resize_force)
+    if (hn, wn) != (h, w):
+        if use_cv2:
+            import cv2
+            image = cv2.resize(image, (wn, hn), interpolation=cv2.INTER_CUBIC)
+        else:
+            image = cv2_resize_cubic_f32(image, wn, hn)
+    image = image.transpose((2, 0, 1))
+    image = image / 255.
+    return {"image": image.astype(np.float32), "original_size": np.array([w, h])}

@@ -60,6 +60,8 @@ _PROTOS = {
     "sfd2_extract_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(ExtractParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_extract_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sfd2_preprocess_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
     "sfd2_match_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.POINTER(MatchParams), C.c_void_p, C.c_void_p, C.c_void_p]),
     "sfd2_match_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,

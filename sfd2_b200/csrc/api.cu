@@ -582,6 +582,16 @@ SFD2_API int sfd2_extract_status(sfd2_ctx* c, void* stream) {
   return SFD2_OK;
 }
 
+SFD2_API int sfd2_preprocess_dev(sfd2_ctx* c, const uint8_t* img, int h, int w, int swap_rb, int hn, int wn, float* out, void* stream) {
+  SFD2_CHECK(c && img && out, SFD2_ERR_ARG, "sfd2_preprocess_dev: NULL argument");
+  SFD2_CHECK(h >= 1 && w >= 1 && hn >= 1 && wn >= 1 && hn <= 65535, SFD2_ERR_ARG, "sfd2_preprocess_dev: bad size %d x %d -> %d x %d", h, w, hn, wn);
+  SFD2_CUDA(cudaSetDevice(c->device));
+  const long long before = g_launches;
+  const int rc = launch_preprocess(img, h, w, swap_rb ? 1 : 0, hn, wn, out, static_cast<cudaStream_t>(stream));
+  c->launches += g_launches - before;
+  return rc;
+}
+
 // ---- matcher -----------------------------------------------------------------------------------------------
 static int ensure_match_ws_simt(sfd2_ctx* c, int n0, int n1) {
   const size_t need = (size_t)(n0 > n1 ? n0 : n1) + 128;

@@ -103,6 +103,8 @@ int launch_select(unsigned long long* cand, int cap, const int* counter, int W, 
                   cudaStream_t st);
 int launch_sample(const float* desc_map, int H4, int W4, int H, int W, const float* kpts, const int32_t* count,
                   int topk, float* desc_out, cudaStream_t st);
+// preprocess.cu
+int launch_preprocess(const uint8_t* src, int h, int w, int swap_rb, int hn, int wn, float* out, cudaStream_t st);
 // match.cu
 int launch_match_simt(const float* d0, int n0, const float* d1, int n1, int d, unsigned long long* row_key,
                       unsigned long long* col_key, cudaStream_t st);

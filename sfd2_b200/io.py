@@ -3,9 +3,11 @@
 The reference writes HDF5 (extract_localization.py:235-272, hloc/match_features.py:84-121):
   features:  group <image name> -> keypoints f64[K,2], descriptors f64[128,K], scores f64[K], image_size
   matches :  group names_to_pair(a, b) -> matches0 int16[N], matching_scores0 float16[N]
-h5py is used when it is installed; otherwise the same groups/datasets are kept in an .npz archive
-("<group>/<dataset>" keys) so the loops below can run - and be tested - without it.  Nothing here
-computes: extraction and matching go through the CUDA library via extractor.py / matchers.py.
+A path ending in .h5 is a real HDF5 file: written / read with h5py when it is installed, otherwise with the bundled
+pure-Python subset writer (h5lite.py: superblock v0, old-style groups, contiguous datasets - what h5py's default writes),
+so the files are interchangeable with the reference's.  Any other path is an .npz archive ("<group>/<dataset>" keys).
+Descriptors may be stored as float16 (fp16=True): half the bytes of the dominant dataset; readers cast back.
+Nothing here computes: extraction and matching go through the CUDA library via extractor.py / matchers.py.
 """
 import os
 
@@ -35,15 +37,20 @@ class Store:
     """Group -> {dataset: array} container with the reference's HDF5 layout.
     path ending in .h5 uses h5py (must be installed); anything else is an .npz archive."""
 
-    def __init__(self, path, mode="a"):
-        self.path, self.mode = str(path), mode
+    def __init__(self, path, mode="a", fp16=False, backend=None):
+        """fp16: store 'descriptors' as float16 (the reference stores float64: 4.2 MB per 4096 x 128 image -> 1 MB).
+        backend: 'h5py' | 'h5lite' | None (h5py when installed)."""
+        self.path, self.mode, self.fp16 = str(path), mode, bool(fp16)
         self.h5 = None
         self.groups = {}
         if self.path.endswith(".h5"):
-            if not HAVE_H5PY:
-                raise RuntimeError("h5py is not installed: use an .npz path")
-            import h5py
-            self.h5 = h5py.File(self.path, mode)
+            use_h5py = HAVE_H5PY if backend is None else (backend == "h5py")
+            if use_h5py:
+                import h5py
+                self.h5 = h5py.File(self.path, mode)
+            else:
+                from . import h5lite
+                self.h5 = h5lite.File(self.path, mode)
         elif mode in ("a", "r") and os.path.exists(self.path):
             z = np.load(self.path, allow_pickle=False)
             for key in z.files:
@@ -69,9 +76,13 @@ class Store:
         if self.h5 is not None:
             grp = self.h5.create_group(group)
             for k, v in datasets.items():
-                grp.create_dataset(k, data=v)
+                grp.create_dataset(k, data=self._cast(k, v))
         else:
-            self.groups[group] = {k: np.asarray(v) for k, v in datasets.items()}
+            self.groups[group] = {k: self._cast(k, v) for k, v in datasets.items()}
+
+    def _cast(self, key, value):
+        a = np.asarray(value)
+        return a.astype(np.float16) if (self.fp16 and key == "descriptors") else a
 
     def close(self):
         if self.h5 is not None:
