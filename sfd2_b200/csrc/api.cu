@@ -383,6 +383,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   }
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_TC_PDL")) g_tc_pdl = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_NSPLIT")) g_tc_nsplit = atoi(e) != 0;
   if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;

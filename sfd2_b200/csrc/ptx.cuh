@@ -86,6 +86,12 @@ __device__ __forceinline__ void bulk_wait_read() {  // <= N groups still reading
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// (prologue: barrier init, TMEM allocation, bias / descriptor prefetch) while its predecessor's last wave drains; it must
+// execute pdl_wait() before touching anything the predecessor writes or reads.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- thread-block clusters ------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

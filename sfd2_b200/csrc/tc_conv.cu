@@ -113,6 +113,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
                const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
                const __grid_constant__ TcConvArgs a, const __grid_constant__ TcStaW sw) {
+  pdl_launch_dependents();       // the next layer's prologue may overlap this layer's last wave (it waits below)
   const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
   extern __shared__ uint8_t smem_raw[];
@@ -154,6 +155,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   __syncthreads();
   if (a.mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
+  pdl_wait();                          // everything above touched only weights / parameters; activations from here on
   const uint32_t tmem_base = *tmem_slot;
   const int nkb = a.taps * a.kchunks;
   // tile of iteration `it`; a cluster whose FIRST tile is out of range skips the iteration as a whole,
@@ -623,6 +625,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // ------------------------------------------------------------------------------------ host side
 int g_fuse_sta = 1;       // SFD2_FUSE_STA=0: run ConvSta as its own kernel (sta_kernel) instead of in rb2c3's epilogue
 int g_tc_multicast = 1;   // SFD2_TC_MULTICAST=0 in the environment disables the 2-CTA weight multicast
+int g_tc_pdl = 1;         // SFD2_TC_PDL=0: launch the conv layers without programmatic dependent launch
 
 PFN_encodeTiled get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -890,13 +893,15 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)a.mc;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_tc_pdl ? 2 : 1;
   // weight-slab boxes: full slab = n_mma rows; with multicast each CTA fetches n_mma/2 rows
   const int box_rows = (a.mc > 1) ? a.n_mma / 2 : a.n_mma;
   const int full_rows = a.cat ? 128 : (diag ? 64 : L.cout_tc);

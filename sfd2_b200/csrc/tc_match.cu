@@ -55,8 +55,6 @@ __device__ __forceinline__ void red_max_u32(unsigned* addr, unsigned v) {
   asm volatile("red.relaxed.gpu.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ prep
 // ids -> order-preserving compaction table (desc_db[db_3D_ids != -1], it_loc/localize_cv2.py:540-555): one block per

@@ -83,6 +83,56 @@ class ResSegNetV2(torch.nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("training forward is out of scope; use extract_resnet_return / Extractor")
 
+    def prefetch(self, img):
+        """Start the host -> device copy of the NEXT image now, on a side stream, so that it overlaps the extraction of the
+        current one.  The next extract_resnet_return(model, img, ...) call with this same tensor finds it on the device.
+        One line in the reference loop (extract_localization.py:240): call it on item i+1 before extracting item i.
+        img: CPU float tensor [1,3,H,W] (pinned memory makes the copy asynchronous)."""
+        t = torch.as_tensor(img)
+        if t.is_cuda:
+            return
+        dev = torch.device("cuda", self.ctx.device)
+        if self.__dict__.get("_pf_stream") is None:
+            self.__dict__["_pf_stream"] = torch.cuda.Stream(dev)
+        with torch.cuda.stream(self._pf_stream):
+            d = t.to(dev, dtype=torch.float32, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._pf_stream)
+        pf = self.__dict__.setdefault("_pf", {})
+        while len(pf) >= 3:                      # a few images in flight at most (23 MB each at 1600 x 1200)
+            pf.pop(next(iter(pf)))
+        pf[t.data_ptr()] = (t.numel(), d, ev, t)
+
+    def _take_prefetched(self, img):
+        pf = self.__dict__.get("_pf")
+        if not pf or img.is_cuda:
+            return None
+        e = pf.get(img.data_ptr())
+        if e is None or e[0] != img.numel():
+            return None
+        del pf[img.data_ptr()]
+        d, ev = e[1], e[2]
+        torch.cuda.current_stream(d.device).wait_event(ev)
+        d.record_stream(torch.cuda.current_stream(d.device))
+        return d.reshape(-1, *d.shape[-2:])
+
+    def _dev_outputs(self, cap, dev):
+        st = self.__dict__.get("_dev_out")
+        if st is None or st[0].shape[0] < cap or st[0].device != dev:
+            st = (torch.empty((cap, 2), dtype=torch.float32, device=dev), torch.empty((cap,), dtype=torch.float32, device=dev),
+                  torch.empty((cap, _lib.DESC_DIM), dtype=torch.float32, device=dev), torch.empty((1,), dtype=torch.int32, device=dev))
+            self.__dict__["_dev_out"] = st
+        return st[0][:cap], st[1][:cap], st[2][:cap], st[3]
+
+    def _host_staging(self, cap):
+        """Pinned (kpts, scores, desc, count) buffers of the host entry point, reused across calls."""
+        st = self.__dict__.get("_staging")
+        if st is None or st[0].shape[0] < cap:
+            st = (torch.empty((cap, 2), dtype=torch.float32).pin_memory(), torch.empty((cap,), dtype=torch.float32).pin_memory(),
+                  torch.empty((cap, _lib.DESC_DIM), dtype=torch.float32).pin_memory(), torch.empty((1,), dtype=torch.int32).pin_memory())
+            self.__dict__["_staging"] = st
+        return st[0][:cap], st[1][:cap], st[2][:cap], st[3]
+
     # -- test hook -----------------------------------------------------------------------
     def debug_fetch(self, name: str, shape) -> np.ndarray:
         out = np.empty(int(np.prod(shape)), np.float32)
@@ -141,30 +191,31 @@ def extract_resnet_return(model, img, conf_th=0.001, mask=None, topK=-1, **kwarg
     cap = int(topK) if topK and topK > 0 else (H * W) // 16 + 4096
     p = _params(model, conf_th, cap)
     lib = _lib.lib()
+    pre = model._take_prefetched(img)
+    if pre is not None:
+        img = pre                       # uploaded ahead of time by model.prefetch(img): no H2D on the critical path
     if img.is_cuda:
         img = img.contiguous()
         dev = img.device
         _same_device(ctx, dev)
         # every row of the outputs is written by the kernels (rows beyond the count read zero): no fills
-        kp = torch.empty(cap, 2, dtype=torch.float32, device=dev)
-        sc = torch.empty(cap, dtype=torch.float32, device=dev)
-        de = torch.empty(cap, _lib.DESC_DIM, dtype=torch.float32, device=dev)
-        cnt = torch.empty(1, dtype=torch.int32, device=dev)
+        kp_d, sc_d, de_d, cnt_d = model._dev_outputs(cap, dev)
         st = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.sfd2_extract_dev(ctx.handle, img.data_ptr(), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
-                                        kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr(), st),
+                                        kp_d.data_ptr(), sc_d.data_ptr(), de_d.data_ptr(), cnt_d.data_ptr(), st),
                    "sfd2_extract_dev")
+        kp, sc, de, cnt = model._host_staging(cap)
+        kp.copy_(kp_d, non_blocking=True); sc.copy_(sc_d, non_blocking=True)
+        de.copy_(de_d, non_blocking=True); cnt.copy_(cnt_d, non_blocking=True)
         _lib.check(lib.sfd2_extract_status(ctx.handle, st), "sfd2_extract_dev")     # synchronises; raises on candidate overflow
-        n = int(cnt.item())
-        return _pack(kp[:n].cpu().numpy(), sc[:n].cpu().numpy(), de[:n].cpu().numpy(), n)
-    a = np.ascontiguousarray(img.numpy())
-    kp = np.zeros((cap, 2), np.float32)
-    sc = np.zeros((cap,), np.float32)
-    de = np.zeros((cap, _lib.DESC_DIM), np.float32)
-    cnt = np.zeros((1,), np.int32)
-    _lib.check(lib.sfd2_extract_host(ctx.handle, _np_ptr(a), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
-                                     _np_ptr(kp), _np_ptr(sc), _np_ptr(de), _np_ptr(cnt)), "sfd2_extract_host")
-    return _pack(kp, sc, de, int(cnt[0]))
+        return _pack(kp.numpy(), sc.numpy(), de.numpy(), int(cnt[0]))
+    # host path: results land in persistent PINNED staging (asynchronous D2H, no per-call 2 MB allocations); _pack copies
+    # them into the fresh float64 arrays the caller owns
+    img = img.contiguous()
+    kp, sc, de, cnt = model._host_staging(cap)
+    _lib.check(lib.sfd2_extract_host(ctx.handle, img.data_ptr(), _lib.IMG_F32_NCHW, 1, H, W, C.byref(p),
+                                     kp.data_ptr(), sc.data_ptr(), de.data_ptr(), cnt.data_ptr()), "sfd2_extract_host")
+    return _pack(kp.numpy(), sc.numpy(), de.numpy(), int(cnt[0]))
 
 
 def _extract_multiscale(model, img, conf_th, topK, scales):

@@ -631,3 +631,26 @@ def test_localizer_subset_and_remap_on_device():
     assert np.array_equal(single, out[0])
     plain = feature_matching(q, dbs[0])
     assert (plain == orc.feature_matching(q, dbs[0])).mean() > 0.999
+
+
+def test_prefetch_overlaps_upload_without_changing_results(golden):
+    """model.prefetch(next_image) + extract_resnet_return(model, next_image) == the plain call, for the image that was
+    prefetched; a call with a different tensor ignores the prefetched one."""
+    from gpu_util import model
+    from sfd2_b200 import extract_resnet_return
+    m = model("mixed")
+    imgs = [torch.from_numpy(synth_image(70 + i, 240, 320)).pin_memory() for i in range(3)]
+    plain = [extract_resnet_return(m, im, topK=500, conf_th=0.001, scales=[1.0]) for im in imgs]
+    m.prefetch(imgs[0])
+    for i in range(3):
+        if i + 1 < 3:
+            cur = extract_resnet_return(m, imgs[i], topK=500, conf_th=0.001, scales=[1.0])    # consumes the prefetched copy
+            m.prefetch(imgs[i + 1])
+        else:
+            cur = extract_resnet_return(m, imgs[i], topK=500, conf_th=0.001, scales=[1.0])
+        for k in cur:
+            assert np.array_equal(cur[k], plain[i][k]), (i, k)
+    m.prefetch(imgs[0])
+    other = extract_resnet_return(m, imgs[2], topK=500, conf_th=0.001, scales=[1.0])           # not the prefetched tensor
+    for k in other:
+        assert np.array_equal(other[k], plain[2][k]), k
