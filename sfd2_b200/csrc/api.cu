@@ -658,7 +658,7 @@ static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, con
     const int na = sets[q.a].n, nb = sets[q.b].n;
     q.tm = cdiv(na, 128); q.tn = cdiv(nb, 128);
     q.tile0 = (int)tiles;
-    q.ntiles = q.tm * q.tn * passes;
+    q.ntiles = tm_units(q.tm, q.tn, passes);
     tiles += q.ntiles;
     q.key_a = koff; koff += round_up(na > 0 ? na : 1, 128);
     q.key_b = koff; koff += round_up(nb > 0 ? nb : 1, 128);

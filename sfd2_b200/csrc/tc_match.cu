@@ -14,6 +14,10 @@
 //             both products with the thread-local (best, second) reduction on each - still tensor cores, no CUDA-core pass.
 //   * the mutual check / thresholds / index remap run in the tail of the CTA that completes a pair's last tile.
 //
+// Work unit = TWO row-blocks (256 rows of the A operand, resident in shared memory) x one 128-row B tile: every B tile
+// fetched from L2 feeds two accumulators, which halves the L2 -> SM traffic per MMA.  With one row-block per unit the
+// kernel was bound by exactly that traffic (64 KB of B per 128 x 128 x 128 tile in exact mode = 5.8 TB/s chip-wide).
+//
 // One launch serves MANY pairs: a table of descriptor sets (operands) and of (set a, set b) problems; tiles of all
 // problems form one list cut into contiguous per-CTA ranges.  Set sizes may live in DEVICE memory (the extractor's counts),
 // so an extract -> match pipeline never synchronises with the host.
@@ -170,7 +174,8 @@ constexpr int TM_TILE = 128;
 constexpr int TM_OP_BYTES = 128 * 128;   // 128 rows x 64 fp16 (one K half of one plane)
 constexpr int TM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TM_EPI_THREADS = 256;
-constexpr int TM_ACC_BUFS = 4;           // 4 x 128 fp32 columns = the whole TMEM: the MMAs run up to three tiles ahead
+constexpr int TM_SUB = 2;                // row-blocks per work unit
+constexpr int TM_ACC_BUFS = 2;           // 2 x (2 x 128) fp32 columns = the whole TMEM: the MMAs of unit k+1 overlap the epilogue of unit k
 constexpr int TM_MAX_STAGES = 10;
 
 struct TileInfo {
@@ -222,12 +227,12 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCa
     c.key_a = pr.key_a; c.key_b = pr.key_b;
   }
   int r = tile - c.tile0;
-  const int t0 = c.tm * c.tn;
+  const int u0 = ((c.tm + 1) >> 1) * c.tn;           // units of the first product: super-blocks of a x column tiles of b
   t.p = c.p;
-  t.pass = (r >= t0) ? 1 : 0;
-  if (t.pass) r -= t0;
+  t.pass = (r >= u0) ? 1 : 0;
+  if (t.pass) r -= u0;
   const int tn = t.pass ? c.tm : c.tn;
-  t.mt = r / tn;
+  t.mt = r / tn;                                     // super-block: rows [256 mt, 256 mt + 256) of the A operand
   // strips start at skewed columns: CTAs working on different row-blocks of one problem at the same time then sit on
   // different column tiles, so a column's threshold is established by whoever comes first instead of being cold for all
   t.nt = (r - t.mt * tn + t.mt * 5) % tn;
@@ -235,8 +240,8 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCa
   t.a_prow = t.pass ? c.prow_b : c.prow_a; t.b_prow = t.pass ? c.prow_a : c.prow_b;
   t.ka = t.pass ? c.key_b : c.key_a;
   t.kb = t.pass ? c.key_a : c.key_b;
-  t.rb = c.tile0 + (t.pass ? t0 : 0) + t.mt * tn;     // linear index of the strip's first tile: unique per (p, pass, mt)
-  t.skip = (t.mt * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
+  t.rb = c.tile0 + (t.pass ? u0 : 0) + t.mt * tn;     // linear index of the strip's first unit: unique per (p, pass, mt)
+  t.skip = (t.mt * TM_SUB * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
 }
 
 // Lowe ratio test on (best, second-best) similarity.  mode 1 = hloc find_nn (nearest_neighbor.py:8-11):
@@ -351,7 +356,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nops = (a.split == 3) ? 2 : 1;
-  const int a_slot_bytes = 2 * nops * TM_OP_BYTES;                 // resident A: [kb][plane] x 16 KB, two slots
+  const int a_sub_bytes = 2 * nops * TM_OP_BYTES;                  // one row-block of A: [kb][plane] x 16 KB
+  const int a_slot_bytes = TM_SUB * a_sub_bytes;                   // resident A of a unit: [sub][kb][plane]
   uint8_t* aslot = smem;
   uint8_t* bring = smem + (size_t)a.aslots * a_slot_bytes;                        // B ring: stage = one plane of one K half (16 KB)
   uint8_t* tail = bring + (size_t)a.stages * TM_OP_BYTES;
@@ -365,6 +371,7 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
+  int* cold_cnt = last_flag + 1;                                                     // [2][4] never-reported columns per 32-group
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); }
@@ -400,10 +407,13 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           aph ^= 1u << as;
           uint8_t* dst = aslot + (size_t)as * a_slot_bytes;
           mbar_expect_tx(&afull[as], (uint32_t)a_slot_bytes);
-          for (int kb = 0; kb < 2; ++kb) {
-            tma_load_2d(dst + (kb * nops) * TM_OP_BYTES, &tm_hi, &afull[as], kb * 64, t.a_prow + t.mt * TM_TILE);
-            if (nops == 2) tma_load_2d(dst + (kb * nops + 1) * TM_OP_BYTES, &tm_lo, &afull[as], kb * 64, t.a_prow + t.mt * TM_TILE);
-          }
+          for (int sub = 0; sub < TM_SUB; ++sub)
+            for (int kb = 0; kb < 2; ++kb) {
+              const int row = t.a_prow + (t.mt * TM_SUB + sub) * TM_TILE;     // rows past the set read zeros / a neighbour: masked later
+              uint8_t* d = dst + (size_t)sub * a_sub_bytes + (kb * nops) * TM_OP_BYTES;
+              tma_load_2d(d, &tm_hi, &afull[as], kb * 64, row);
+              if (nops == 2) tma_load_2d(d + TM_OP_BYTES, &tm_lo, &afull[as], kb * 64, row);
+            }
           prev_rb = t.rb;
         }
         for (int kb = 0; kb < 2; ++kb)
@@ -436,25 +446,28 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         const uint32_t abase = smem_u32(aslot + (size_t)as * a_slot_bytes);
-        const uint32_t dcol = tmem_base + (uint32_t)(buf * 128);
         for (int kb = 0; kb < 2; ++kb)
           for (int pl = 0; pl < nops; ++pl) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t sa = abase + (uint32_t)((kb * nops) * TM_OP_BYTES);
-            const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
             const uint64_t db = make_desc_sw128(smem_u32(bring + (size_t)stage * TM_OP_BYTES));
-            if (pl == 0) {                          // b_hi: a_hi * b_hi, then (exact mode) a_lo * b_hi
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (kb == 0 && k == 0) ? 0u : 1u);
-              if (nops == 2) {
+            for (int sub = 0; sub < TM_SUB; ++sub) {      // the B stage feeds both row-blocks of the unit
+              const uint32_t dcol = tmem_base + (uint32_t)(buf * (TM_SUB * 128) + sub * 128);
+              const uint32_t sa = abase + (uint32_t)(sub * a_sub_bytes + (kb * nops) * TM_OP_BYTES);
+              const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
+              if (pl == 0) {                          // b_hi: a_hi * b_hi, then (exact mode) a_lo * b_hi
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, 1u);
+                for (int k = 0; k < 4; ++k)
+                  umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (kb == 0 && k == 0) ? 0u : 1u);
+                if (nops == 2) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, 1u);
+                }
+              } else {                                // b_lo: a_hi * b_lo
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
               }
-            } else {                                // b_lo: a_hi * b_lo
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
             }
             umma_commit(&empty[stage]);
             if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -474,7 +487,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
   } else {
     // ---------------------------------------------------------------- epilogue (warps 2..9)
-    // warp (q, h): TMEM lanes 32q.. (q = warp % 4, the hardware's lane-quarter rule), columns [64h, 64h + 64) of each tile
+    // warp (q, h): TMEM lanes 32q.. (q = warp % 4, the hardware's lane-quarter rule), columns [64h, 64h + 64) of each of
+    // the unit's two accumulators (row-blocks)
     const int et = (int)threadIdx.x - 64;
     const int q = warp & 3, h = (warp - 2) >> 2;
     const bool top2 = a.passes == 2;
@@ -483,28 +497,33 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t bphase = 0;
     int cur_rb = -1, cur_p = -1, p_tiles = 0, cur_ntiles = 0;
     long long cur_ka = 0;
-    int cur_i = 0;
-    bool cur_valid = false;
-    float rbest = -CUDART_INF_F, rsec = -CUDART_INF_F;
-    int rbest_j = -1;
+    int cur_i[TM_SUB] = {0, 0};
+    bool cur_valid[TM_SUB] = {false, false};
+    float rbest[TM_SUB], rsec[TM_SUB];
+    int rbest_j[TM_SUB];
+#pragma unroll
+    for (int s_ = 0; s_ < TM_SUB; ++s_) { rbest[s_] = -CUDART_INF_F; rsec[s_] = -CUDART_INF_F; rbest_j[s_] = -1; }
     TileInfo t;
 
-    auto flush_rows = [&]() {          // merge this thread's strip result into the row keys
-      if (cur_rb >= 0 && cur_valid && rbest_j >= 0) {
-        const unsigned long long key = m_key(rbest, rbest_j);
-        if (!top2) {
-          red_max_u64(a.keys + cur_ka + cur_i, key);
-        } else {
-          const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i, key);
-          // every partial best except the final winner loses exactly one atomicMax: it is a second-best candidate
-          float cand = rsec;
-          if (old != 0ull) cand = fmaxf(cand, fminf(m_key_sim(old), rbest));
-          if (cand > -CUDART_INF_F) red_max_u32(a.sec + cur_ka + cur_i, m_ord_f32(cand));
+    auto flush_rows = [&]() {          // merge this thread's strip results into the row keys
+#pragma unroll
+      for (int s_ = 0; s_ < TM_SUB; ++s_) {
+        if (cur_rb >= 0 && cur_valid[s_] && rbest_j[s_] >= 0) {
+          const unsigned long long key = m_key(rbest[s_], rbest_j[s_]);
+          if (!top2) {
+            red_max_u64(a.keys + cur_ka + cur_i[s_], key);
+          } else {
+            const unsigned long long old = atomicMax(a.keys + cur_ka + cur_i[s_], key);
+            // every partial best except the final winner loses exactly one atomicMax: it is a second-best candidate
+            float cand = rsec[s_];
+            if (old != 0ull) cand = fmaxf(cand, fminf(m_key_sim(old), rbest[s_]));
+            if (cand > -CUDART_INF_F) red_max_u32(a.sec + cur_ka + cur_i[s_], m_ord_f32(cand));
+          }
         }
+        rbest[s_] = -CUDART_INF_F; rsec[s_] = -CUDART_INF_F; rbest_j[s_] = -1;
       }
-      rbest = -CUDART_INF_F; rsec = -CUDART_INF_F; rbest_j = -1;
     };
-    auto leave_problem = [&]() {       // count this CTA's tiles of problem cur_p; the CTA completing the problem finishes it
+    auto leave_problem = [&]() {       // count this CTA's units of problem cur_p; the CTA completing the problem finishes it
       if (cur_p < 0) return;
       // release: the CTA barrier orders every epilogue thread's atomics before thread 0's acq_rel RMW on the counter
       // (cumulativity); acquire: the finisher's loads (ld.global.cg, L2) come after that RMW and the second barrier
@@ -535,8 +554,11 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         flush_rows();
         cur_rb = t.rb;
         cur_ka = t.ka;
-        cur_i = t.mt * TM_TILE + q * 32 + lane;
-        cur_valid = cur_i < t.a_len;
+#pragma unroll
+        for (int s_ = 0; s_ < TM_SUB; ++s_) {
+          cur_i[s_] = (t.mt * TM_SUB + s_) * TM_TILE + q * 32 + lane;
+          cur_valid[s_] = cur_i[s_] < t.a_len;
+        }
       }
       const bool want_cols = a.cols && t.pass == 0 && !(a.debug & 2);
       const int c0 = t.nt * TM_TILE;
@@ -548,143 +570,125 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         if (et < 128) {
           thr_key[par * 128 + et] = kc;
           thr_sim[par * 128 + et] = kc ? m_key_sim(kc) : -3.0e38f;    // cold column: every VALID value passes (-inf = invalid never does)
+          const unsigned cb = __ballot_sync(0xffffffffu, kc == 0ull);
+          if (lane == 0) cold_cnt[par * 4 + (et >> 5)] = __popc(cb);   // columns of this 32-group nobody has reported yet
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + h * 64);
-      uint32_t v0[32], v1[32];
-      tmem_ld32(taddr, v0);
-      tmem_ld32(taddr + 32, v1);
-      tmem_ld_wait();
-      // the accumulator is in registers: hand the buffer back now - unless the column path may come back for single
-      // columns (warm tiles re-read the few candidate columns from TMEM instead of indexing registers dynamically)
-      if (!want_cols) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);
-      }
-      if (a.debug & 1) {
-        if (want_cols) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty[buf]); par ^= 1; }
-        if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
-        continue;
-      }
-      float f[64];
       const int cols_valid = t.b_len - c0 - h * 64;           // valid columns among this warp's 64
-      if (cols_valid >= 64 && cur_valid) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
-      } else {
+      for (int s_ = 0; s_ < TM_SUB; ++s_) {
+        if (a.debug & 1) break;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TM_SUB * 128) + s_ * 128 + h * 64);
+        uint32_t v0[32], v1[32];
+        tmem_ld32(taddr, v0);
+        tmem_ld32(taddr + 32, v1);
+        tmem_ld_wait();
+        float f[64];
+        if (cols_valid >= 64 && cur_valid[s_]) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = (cur_valid && j < cols_valid) ? __uint_as_float(v0[j]) : -CUDART_INF_F;
-          f[32 + j] = (cur_valid && 32 + j < cols_valid) ? __uint_as_float(v1[j]) : -CUDART_INF_F;
+          for (int j = 0; j < 32; ++j) { f[j] = __uint_as_float(v0[j]); f[32 + j] = __uint_as_float(v1[j]); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = (cur_valid[s_] && j < cols_valid) ? __uint_as_float(v0[j]) : -CUDART_INF_F;
+            f[32 + j] = (cur_valid[s_] && 32 + j < cols_valid) ? __uint_as_float(v1[j]) : -CUDART_INF_F;
+          }
         }
-      }
-      // ---- rows: tree max of the values, then (only when it beats the running best) tree min of the indices attaining it
-      {
-        float m32[32], m16[16], m8[8], m4[4];
+        // ---- rows: tree max of the values, then (only when it beats the running best) tree min of the indices attaining it
+        {
+          float m32[32], m16[16], m8[8], m4[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m32[j] = fmaxf(f[2 * j], f[2 * j + 1]);
+          for (int j = 0; j < 32; ++j) m32[j] = fmaxf(f[2 * j], f[2 * j + 1]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) m16[j] = fmaxf(m32[2 * j], m32[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) m16[j] = fmaxf(m32[2 * j], m32[2 * j + 1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m8[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
+          for (int j = 0; j < 8; ++j) m8[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
-        const float cmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        if (top2) {
-          // second best of this tile = max over everything except ONE instance of the maximum
-          int amin = 64;
+          for (int j = 0; j < 4; ++j) m4[j] = fmaxf(m8[2 * j], m8[2 * j + 1]);
+          const float cmax = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          if (top2) {
+            // second best of this tile = max over everything except ONE instance of the maximum
+            int amin = 64;
 #pragma unroll
-          for (int j = 63; j >= 0; --j) amin = (f[j] == cmax) ? j : amin;
-          float s2 = -CUDART_INF_F;
+            for (int j = 63; j >= 0; --j) amin = (f[j] == cmax) ? j : amin;
+            float s2 = -CUDART_INF_F;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) s2 = fmaxf(s2, (j == amin) ? -CUDART_INF_F : f[j]);
-          if (cmax > rbest) {           // strict: an equal value in a later tile keeps the earlier column
-            rsec = fmaxf(rbest, fmaxf(rsec, s2));
-            rbest = cmax;
-            rbest_j = c0 + h * 64 + amin;
+            for (int j = 0; j < 64; ++j) s2 = fmaxf(s2, (j == amin) ? -CUDART_INF_F : f[j]);
+            if (cmax > rbest[s_]) {           // strict: an equal value in a later tile keeps the earlier column
+              rsec[s_] = fmaxf(rbest[s_], fmaxf(rsec[s_], s2));
+              rbest[s_] = cmax;
+              rbest_j[s_] = c0 + h * 64 + amin;
+            } else {
+              rsec[s_] = fmaxf(rsec[s_], cmax);
+            }
+          } else if (cmax > rbest[s_]) {
+            int i32[32], i16[16], i8[8], i4[4];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) i32[j] = min((f[2 * j] == cmax) ? 2 * j : 64, (f[2 * j + 1] == cmax) ? 2 * j + 1 : 64);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) i16[j] = min(i32[2 * j], i32[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) i8[j] = min(i16[2 * j], i16[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) i4[j] = min(i8[2 * j], i8[2 * j + 1]);
+            rbest[s_] = cmax;
+            rbest_j[s_] = c0 + h * 64 + min(min(i4[0], i4[1]), min(i4[2], i4[3]));
+          }
+        }
+        // ---- columns: threshold filter against the column's best so far; the rare candidates update the column keys
+        if (want_cols && !(a.debug & 8)) {
+          const float* ts = thr_sim + par * 128 + h * 64;
+          const unsigned long long* tk = thr_key + par * 128 + h * 64;
+          unsigned long long* gk = a.keys + t.kb + c0 + h * 64;
+          // a tile whose thresholds are not established yet (most columns never seen): full warp arg-max of all 64
+          // columns by butterfly, one key update per column by the lane that ends up owning it
+          const int ncold = cold_cnt[par * 4 + h * 2] + cold_cnt[par * 4 + h * 2 + 1];
+          if (ncold >= 16 || (a.debug & 32)) {
+            const int row0 = cur_i[s_] - lane;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              unsigned v[32], id[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = f[g * 32 + j];
+                v[j] = (x > -CUDART_INF_F) ? m_ord_f32(x) : 0u;      // 0 = invalid row / column: never wins
+                id[j] = (unsigned)lane;
+              }
+              tm_butterfly32(v, id, lane);
+              if (v[0] != 0u) {
+                const unsigned long long key = ((unsigned long long)v[0] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row0 + (int)id[0]));
+                if (key > tk[g * 32 + lane]) red_max_u64(gk + g * 32 + lane, key);
+              }
+            }
           } else {
-            rsec = fmaxf(rsec, cmax);
-          }
-        } else if (cmax > rbest) {
-          int i32[32], i16[16], i8[8], i4[4];
+            // established thresholds: one compare + one vote per column; only where some row of the warp reaches the
+            // column's best so far (a few columns per tile) do the candidate lanes build their key and push it - the
+            // atomic max resolves ties (lowest row wins).  Values stay in registers: static indices only.
 #pragma unroll
-          for (int j = 0; j < 32; ++j) i32[j] = min((f[2 * j] == cmax) ? 2 * j : 64, (f[2 * j + 1] == cmax) ? 2 * j + 1 : 64);
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
+              const float thv[4] = {th.x, th.y, th.z, th.w};
 #pragma unroll
-          for (int j = 0; j < 16; ++j) i16[j] = min(i32[2 * j], i32[2 * j + 1]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) i8[j] = min(i16[2 * j], i16[2 * j + 1]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) i4[j] = min(i8[2 * j], i8[2 * j + 1]);
-          rbest = cmax;
-          rbest_j = c0 + h * 64 + min(min(i4[0], i4[1]), min(i4[2], i4[3]));
-        }
-      }
-      // ---- columns: threshold filter against the column's best so far; rare slow path = warp arg-max + one atomicMax
-      if (want_cols) {
-        const float* ts = thr_sim + par * 128 + h * 64;
-        const unsigned long long* tk = thr_key + par * 128 + h * 64;
-        unsigned long long* gk = a.keys + t.kb + c0 + h * 64;
-        unsigned m0 = 0u, m1 = 0u;                    // this thread's candidate columns (invalid entries are -inf: never >=)
-#pragma unroll
-        for (int j4 = 0; j4 < 16; ++j4) {
-          const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
-          const float thv[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = j4 * 4 + jj;
-            if (f[j] >= thv[jj]) { if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
-          }
-        }
-        const unsigned w0 = __reduce_or_sync(0xffffffffu, m0), w1 = __reduce_or_sync(0xffffffffu, m1);
-        const int hot = __popc(w0) + __popc(w1);          // columns in which some row of this warp is a candidate
-        if (hot >= 12 && !(a.debug & 8)) {
-          // cold tile: full warp arg-max of all 64 columns (two butterflies), one atomicMax per column by the lane that
-          // ends up owning it
-          const int row0 = cur_i - lane;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            unsigned v[32], id[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = f[g * 32 + j];
-              v[j] = (x > -CUDART_INF_F) ? m_ord_f32(x) : 0u;      // 0 = invalid row / column: never wins
-              id[j] = (unsigned)lane;
-            }
-            tm_butterfly32(v, id, lane);
-            if (v[0] != 0u) {
-              const unsigned long long key = ((unsigned long long)v[0] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(row0 + (int)id[0]));
-              if (key > tk[g * 32 + lane]) red_max_u64(gk + g * 32 + lane, key);
-            }
-          }
-        } else if ((w0 | w1) && !(a.debug & 8)) {
-          // warm tile: a handful of columns have a candidate somewhere in the warp.  Walk the set bits of the warp-wide
-          // mask (uniform loop), fetch that ONE column from TMEM again, and let the candidate lanes push their keys
-          // (atomic max resolves ties: lowest row wins).  [A fully unrolled predicated loop over all 64 columns cost
-          // ~650 instructions per warp per tile.]
-#pragma unroll 1
-          for (int g = 0; g < 2; ++g) {
-            unsigned wm = g ? w1 : w0;
-            const unsigned mm = g ? m1 : m0;
-            while (wm) {
-              const int jb = __ffs(wm) - 1;
-              wm &= wm - 1u;
-              const int j = g * 32 + jb;
-              const float x = __uint_as_float(tmem_ld1(taddr + (uint32_t)j));
-              tmem_ld_wait();
-              if ((mm >> jb) & 1u) {
-                const unsigned long long key = m_key(x, cur_i);
-                if (key > tk[j]) red_max_u64(gk + j, key);
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j4 * 4 + jj;
+                const bool pj = f[j] >= thv[jj];
+                if (__builtin_expect(__any_sync(0xffffffffu, pj), 0)) {
+                  if (pj) {
+                    const unsigned long long key = m_key(f[j], cur_i[s_]);
+                    if (key > tk[j]) red_max_u64(gk + j, key);
+                  }
+                }
               }
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);   // now the buffer may be overwritten
-        par ^= 1;
       }
+      // both accumulators of the unit are consumed: the buffer may be overwritten
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (want_cols) par ^= 1;
       if (++buf == TM_ACC_BUFS) { buf = 0; bphase ^= 1; }
     }
     flush_rows();
@@ -700,14 +704,19 @@ constexpr size_t TM_TAIL_BYTES = 3072 + 512;      // thresholds + barriers
 
 size_t tm_smem_bytes(int split, int aslots, int stages) {
   const int nops = split == 3 ? 2 : 1;
-  return 1024 + (size_t)aslots * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
+  return 1024 + (size_t)aslots * TM_SUB * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
 }
 
 int tm_stages(int split, int aslots) {
   const int nops = split == 3 ? 2 : 1;
-  const size_t fixed = 1024 + (size_t)aslots * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
+  const size_t fixed = 1024 + (size_t)aslots * TM_SUB * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
   int s = (int)((227 * 1024 - fixed) / (size_t)TM_OP_BYTES);
   return s > TM_MAX_STAGES ? TM_MAX_STAGES : s;
+}
+
+// work units of one pair: super-blocks (2 row-blocks) of the A operand x column tiles, for each product
+int tm_units(int tm, int tn, int passes) {
+  return ((tm + 1) / 2) * tn + (passes == 2 ? ((tn + 1) / 2) * tm : 0);
 }
 
 int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows) {
@@ -734,8 +743,8 @@ int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper,
 }
 
 int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st) {
-  // exact mode: ONE resident A slot (64 KB) leaves nine 16 KB B stages = 2.25 tiles in flight; with two A slots only five
-  // stages fit, fewer bytes in flight than TMA latency x the MMA's consumption rate (42 B/clk).  Single-pass: two slots.
+  // exact mode: the unit's A operand (2 row-blocks x 64 KB) is resident, five 16 KB B stages stream behind it - each
+  // stage now feeds 16 / 8 MMAs (1024 / 512 cycles), so five cover the TMA latency.  Single-pass mode: two A slots.
   static const int env_aslots = getenv("SFD2_TM_ASLOTS") ? atoi(getenv("SFD2_TM_ASLOTS")) : 0;
   a.aslots = env_aslots ? env_aslots : (a.split == 3 ? 1 : 2);
   static const int env_debug = getenv("SFD2_TM_DEBUG") ? atoi(getenv("SFD2_TM_DEBUG")) : 0;

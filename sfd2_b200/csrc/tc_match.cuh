@@ -16,8 +16,9 @@ struct MOperD {
   const int* ids;         // optional DEVICE int32 [cap]: rows with id == -1 are dropped (order-preserving compaction)
 };
 
-// One pair (set a, set b).  Tiles [tile0, tile0 + ntiles) of the launch's list: tm x tn tiles of a * b^T, followed
-// (two-product mode) by tn x tm tiles of b * a^T.
+// One pair (set a, set b).  Work units [tile0, tile0 + ntiles) of the launch's list: ceil(tm/2) x tn units of a * b^T
+// (a unit = two 128-row blocks of a against one 128-row tile of b), followed (two-product mode) by ceil(tn/2) x tm units
+// of b * a^T.  tm / tn = 128-row tile counts of a / b.
 struct MProbD {
   int a, b;
   int tile0, ntiles, tm, tn;
@@ -53,6 +54,7 @@ struct TcMatchArgs {
 
 size_t tm_smem_bytes(int split, int aslots, int stages);
 int tm_stages(int split, int aslots);
+int tm_units(int tm, int tn, int passes);
 int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows);
 int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
                       int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
