@@ -649,6 +649,9 @@ static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, con
     SFD2_CHECK(prow < (1ll << 30), SFD2_ERR_ARG, "match: too many descriptor rows in one call");
   }
   const int passes = p->ratio_threshold > 0.f ? 2 : 1;
+  // mutual mode (one product + column reduction) is bound by its epilogue: one row-block per unit; the row-only modes are
+  // bound by the B traffic: two row-blocks share every B tile
+  const int sub = (passes == 1 && p->do_mutual_check) ? 1 : 2;
   std::vector<MProbD> probs(npairs);
   long long koff = 0, ooff = 0, tiles = 0;
   for (int k = 0; k < npairs; ++k) {
@@ -658,7 +661,7 @@ static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, con
     const int na = sets[q.a].n, nb = sets[q.b].n;
     q.tm = cdiv(na, 128); q.tn = cdiv(nb, 128);
     q.tile0 = (int)tiles;
-    q.ntiles = tm_units(q.tm, q.tn, passes);
+    q.ntiles = tm_units(q.tm, q.tn, passes, sub);
     tiles += q.ntiles;
     q.key_a = koff; koff += round_up(na > 0 ? na : 1, 128);
     q.key_b = koff; koff += round_up(nb > 0 ? nb : 1, 128);
@@ -723,6 +726,7 @@ static int match_pairs_tc(sfd2_ctx* c, const sfd2_desc_set* sets, int nsets, con
   a.opers = opers_dev; a.probs = probs_dev; a.inl = inl;
   a.nprob = npairs; a.total_tiles = (int)tiles;
   a.passes = passes;
+  a.sub = sub;
   a.cols = (passes == 1 && p->do_mutual_check) ? 1 : 0;
   a.split = p->precision != SFD2_PREC_TC_FAST ? 3 : 1;
   a.mutual = p->do_mutual_check ? 1 : 0;

@@ -174,9 +174,11 @@ constexpr int TM_TILE = 128;
 constexpr int TM_OP_BYTES = 128 * 128;   // 128 rows x 64 fp16 (one K half of one plane)
 constexpr int TM_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TM_EPI_THREADS = 256;
-constexpr int TM_SUB = 2;                // row-blocks per work unit
-constexpr int TM_ACC_BUFS = 2;           // 2 x (2 x 128) fp32 columns = the whole TMEM: the MMAs of unit k+1 overlap the epilogue of unit k
+// row-blocks per work unit: SUB = 2 halves the L2 -> SM traffic per MMA (rows-only and two-product modes, which are bound
+// by it); the mutual mode is bound by its column epilogue and runs SUB = 1 (more accumulator buffers, finer work units).
+// Accumulator buffers = 512 TMEM columns / (SUB x 128).
 constexpr int TM_MAX_STAGES = 10;
+constexpr int TM_MAX_ACC_BUFS = 4;
 
 struct TileInfo {
   int p, pass, mt, nt;
@@ -227,12 +229,13 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCa
     c.key_a = pr.key_a; c.key_b = pr.key_b;
   }
   int r = tile - c.tile0;
-  const int u0 = ((c.tm + 1) >> 1) * c.tn;           // units of the first product: super-blocks of a x column tiles of b
+  const int sub = a.sub;
+  const int u0 = ((c.tm + sub - 1) / sub) * c.tn;    // units of the first product: super-blocks of a x column tiles of b
   t.p = c.p;
   t.pass = (r >= u0) ? 1 : 0;
   if (t.pass) r -= u0;
   const int tn = t.pass ? c.tm : c.tn;
-  t.mt = r / tn;                                     // super-block: rows [256 mt, 256 mt + 256) of the A operand
+  t.mt = r / tn;                                     // super-block: rows [128 sub mt, 128 sub (mt + 1)) of the A operand
   // strips start at skewed columns: CTAs working on different row-blocks of one problem at the same time then sit on
   // different column tiles, so a column's threshold is established by whoever comes first instead of being cold for all
   t.nt = (r - t.mt * tn + t.mt * 5) % tn;
@@ -241,7 +244,7 @@ __device__ __forceinline__ void tm_locate(const TcMatchArgs& a, int tile, ProbCa
   t.ka = t.pass ? c.key_b : c.key_a;
   t.kb = t.pass ? c.key_a : c.key_b;
   t.rb = c.tile0 + (t.pass ? u0 : 0) + t.mt * tn;     // linear index of the strip's first unit: unique per (p, pass, mt)
-  t.skip = (t.mt * TM_SUB * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
+  t.skip = (t.mt * sub * TM_TILE >= t.a_len) || (t.nt * TM_TILE >= t.b_len);
 }
 
 // Lowe ratio test on (best, second-best) similarity.  mode 1 = hloc find_nn (nearest_neighbor.py:8-11):
@@ -350,14 +353,16 @@ __device__ __forceinline__ void tm_butterfly32(unsigned (&v)[32], unsigned (&id)
   }
 }
 
+template <int SUB>
 __global__ void __launch_bounds__(TM_THREADS, 1)
 tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const __grid_constant__ TcMatchArgs a) {
+  constexpr int TM_ACC_BUFS = 4 / SUB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nops = (a.split == 3) ? 2 : 1;
   const int a_sub_bytes = 2 * nops * TM_OP_BYTES;                  // one row-block of A: [kb][plane] x 16 KB
-  const int a_slot_bytes = TM_SUB * a_sub_bytes;                   // resident A of a unit: [sub][kb][plane]
+  const int a_slot_bytes = SUB * a_sub_bytes;                   // resident A of a unit: [sub][kb][plane]
   uint8_t* aslot = smem;
   uint8_t* bring = smem + (size_t)a.aslots * a_slot_bytes;                        // B ring: stage = one plane of one K half (16 KB)
   uint8_t* tail = bring + (size_t)a.stages * TM_OP_BYTES;
@@ -366,12 +371,11 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint64_t* full = reinterpret_cast<uint64_t*>(tail + 3072);
   uint64_t* empty = full + TM_MAX_STAGES;
   uint64_t* tfull = empty + TM_MAX_STAGES;
-  uint64_t* tempty = tfull + TM_ACC_BUFS;
-  uint64_t* afull = tempty + TM_ACC_BUFS;
+  uint64_t* tempty = tfull + TM_MAX_ACC_BUFS;
+  uint64_t* afull = tempty + TM_MAX_ACC_BUFS;
   uint64_t* aempty = afull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
   int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
-  int* cold_cnt = last_flag + 1;                                                     // [2][4] never-reported columns per 32-group
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tm_hi); prefetch_tmap(&tm_lo); }
@@ -407,9 +411,9 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           aph ^= 1u << as;
           uint8_t* dst = aslot + (size_t)as * a_slot_bytes;
           mbar_expect_tx(&afull[as], (uint32_t)a_slot_bytes);
-          for (int sub = 0; sub < TM_SUB; ++sub)
+          for (int sub = 0; sub < SUB; ++sub)
             for (int kb = 0; kb < 2; ++kb) {
-              const int row = t.a_prow + (t.mt * TM_SUB + sub) * TM_TILE;     // rows past the set read zeros / a neighbour: masked later
+              const int row = t.a_prow + (t.mt * SUB + sub) * TM_TILE;     // rows past the set read zeros / a neighbour: masked later
               uint8_t* d = dst + (size_t)sub * a_sub_bytes + (kb * nops) * TM_OP_BYTES;
               tma_load_2d(d, &tm_hi, &afull[as], kb * 64, row);
               if (nops == 2) tma_load_2d(d + TM_OP_BYTES, &tm_lo, &afull[as], kb * 64, row);
@@ -452,8 +456,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             tc_fence_after();
             const uint64_t db = make_desc_sw128(smem_u32(bring + (size_t)stage * TM_OP_BYTES));
 #pragma unroll
-            for (int sub = 0; sub < TM_SUB; ++sub) {      // the B stage feeds both row-blocks of the unit
-              const uint32_t dcol = tmem_base + (uint32_t)(buf * (TM_SUB * 128) + sub * 128);
+            for (int sub = 0; sub < SUB; ++sub) {      // the B stage feeds both row-blocks of the unit
+              const uint32_t dcol = tmem_base + (uint32_t)(buf * (SUB * 128) + sub * 128);
               const uint32_t sa = abase + (uint32_t)(sub * a_sub_bytes + (kb * nops) * TM_OP_BYTES);
               const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TM_OP_BYTES);
               if (pl == 0) {                          // b_hi: a_hi * b_hi, then (exact mode) a_lo * b_hi
@@ -497,17 +501,19 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t bphase = 0;
     int cur_rb = -1, cur_p = -1, p_tiles = 0, cur_ntiles = 0;
     long long cur_ka = 0;
-    int cur_i[TM_SUB] = {0, 0};
-    bool cur_valid[TM_SUB] = {false, false};
-    float rbest[TM_SUB], rsec[TM_SUB];
-    int rbest_j[TM_SUB];
+    int cur_i[SUB];
+    bool cur_valid[SUB];
 #pragma unroll
-    for (int s_ = 0; s_ < TM_SUB; ++s_) { rbest[s_] = -CUDART_INF_F; rsec[s_] = -CUDART_INF_F; rbest_j[s_] = -1; }
+    for (int s_ = 0; s_ < SUB; ++s_) { cur_i[s_] = 0; cur_valid[s_] = false; }
+    float rbest[SUB], rsec[SUB];
+    int rbest_j[SUB];
+#pragma unroll
+    for (int s_ = 0; s_ < SUB; ++s_) { rbest[s_] = -CUDART_INF_F; rsec[s_] = -CUDART_INF_F; rbest_j[s_] = -1; }
     TileInfo t;
 
     auto flush_rows = [&]() {          // merge this thread's strip results into the row keys
 #pragma unroll
-      for (int s_ = 0; s_ < TM_SUB; ++s_) {
+      for (int s_ = 0; s_ < SUB; ++s_) {
         if (cur_rb >= 0 && cur_valid[s_] && rbest_j[s_] >= 0) {
           const unsigned long long key = m_key(rbest[s_], rbest_j[s_]);
           if (!top2) {
@@ -555,8 +561,8 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         cur_rb = t.rb;
         cur_ka = t.ka;
 #pragma unroll
-        for (int s_ = 0; s_ < TM_SUB; ++s_) {
-          cur_i[s_] = (t.mt * TM_SUB + s_) * TM_TILE + q * 32 + lane;
+        for (int s_ = 0; s_ < SUB; ++s_) {
+          cur_i[s_] = (t.mt * SUB + s_) * TM_TILE + q * 32 + lane;
           cur_valid[s_] = cur_i[s_] < t.a_len;
         }
       }
@@ -570,16 +576,14 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         if (et < 128) {
           thr_key[par * 128 + et] = kc;
           thr_sim[par * 128 + et] = kc ? m_key_sim(kc) : -3.0e38f;    // cold column: every VALID value passes (-inf = invalid never does)
-          const unsigned cb = __ballot_sync(0xffffffffu, kc == 0ull);
-          if (lane == 0) cold_cnt[par * 4 + (et >> 5)] = __popc(cb);   // columns of this 32-group nobody has reported yet
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const int cols_valid = t.b_len - c0 - h * 64;           // valid columns among this warp's 64
 #pragma unroll
-      for (int s_ = 0; s_ < TM_SUB; ++s_) {
+      for (int s_ = 0; s_ < SUB; ++s_) {
         if (a.debug & 1) break;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (TM_SUB * 128) + s_ * 128 + h * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * (SUB * 128) + s_ * 128 + h * 64);
         uint32_t v0[32], v1[32];
         tmem_ld32(taddr, v0);
         tmem_ld32(taddr + 32, v1);
@@ -641,10 +645,22 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           const float* ts = thr_sim + par * 128 + h * 64;
           const unsigned long long* tk = thr_key + par * 128 + h * 64;
           unsigned long long* gk = a.keys + t.kb + c0 + h * 64;
-          // a tile whose thresholds are not established yet (most columns never seen): full warp arg-max of all 64
-          // columns by butterfly, one key update per column by the lane that ends up owning it
-          const int ncold = cold_cnt[par * 4 + h * 2] + cold_cnt[par * 4 + h * 2 + 1];
-          if (ncold >= 16 || (a.debug & 32)) {
+          unsigned m0 = 0u, m1 = 0u;                    // this thread's candidate columns (invalid entries are -inf: never >=)
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
+            const float thv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 * 4 + jj;
+              if (f[j] >= thv[jj]) { if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
+            }
+          }
+          const unsigned w0 = __reduce_or_sync(0xffffffffu, m0), w1 = __reduce_or_sync(0xffffffffu, m1);
+          const int hot = __popc(w0) + __popc(w1);          // columns in which some row of this warp is a candidate
+          if (hot >= 12) {
+            // cold tile (thresholds not established): full warp arg-max of all 64 columns by butterfly, one key update
+            // per column by the lane that ends up owning it
             const int row0 = cur_i[s_] - lane;
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
@@ -661,23 +677,25 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 if (key > tk[g * 32 + lane]) red_max_u64(gk + g * 32 + lane, key);
               }
             }
-          } else {
-            // established thresholds: one compare + one vote per column; only where some row of the warp reaches the
-            // column's best so far (a few columns per tile) do the candidate lanes build their key and push it - the
-            // atomic max resolves ties (lowest row wins).  Values stay in registers: static indices only.
-#pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4) {
-              const float4 th = *reinterpret_cast<const float4*>(ts + j4 * 4);
-              const float thv[4] = {th.x, th.y, th.z, th.w};
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 * 4 + jj;
-                const bool pj = f[j] >= thv[jj];
-                if (__builtin_expect(__any_sync(0xffffffffu, pj), 0)) {
-                  if (pj) {
-                    const unsigned long long key = m_key(f[j], cur_i[s_]);
-                    if (key > tk[j]) red_max_u64(gk + j, key);
-                  }
+          } else if (w0 | w1) {
+            // warm tile: a handful of columns have a candidate somewhere in the warp.  Walk the set bits of the warp-wide
+            // mask (uniform loop), fetch that ONE column from TMEM again, and let the candidate lanes push their keys
+            // (the atomic max resolves ties: lowest row wins).  Measured alternatives, all slower: a fully unrolled
+            // predicated loop over the 64 columns (~650 instructions per warp per tile), a vote + branch per column
+            // (2x slower end to end), four re-reads per round, REDUX-based per-column arg-max (a CREDUX costs ~100 cycles).
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+              unsigned wm = g ? w1 : w0;
+              const unsigned mm = g ? m1 : m0;
+              while (wm) {
+                const int jb = __ffs(wm) - 1;
+                wm &= wm - 1u;
+                const int j = g * 32 + jb;
+                const float x = __uint_as_float(tmem_ld1(taddr + (uint32_t)j));
+                tmem_ld_wait();
+                if ((mm >> jb) & 1u) {
+                  const unsigned long long key = m_key(x, cur_i[s_]);
+                  if (key > tk[j]) red_max_u64(gk + j, key);
                 }
               }
             }
@@ -702,21 +720,21 @@ tc_match_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 // ------------------------------------------------------------------------------------------------ host side
 constexpr size_t TM_TAIL_BYTES = 3072 + 512;      // thresholds + barriers
 
-size_t tm_smem_bytes(int split, int aslots, int stages) {
+size_t tm_smem_bytes(int split, int sub, int aslots, int stages) {
   const int nops = split == 3 ? 2 : 1;
-  return 1024 + (size_t)aslots * TM_SUB * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
+  return 1024 + (size_t)aslots * sub * 2 * nops * TM_OP_BYTES + (size_t)stages * TM_OP_BYTES + TM_TAIL_BYTES;
 }
 
-int tm_stages(int split, int aslots) {
+int tm_stages(int split, int sub, int aslots) {
   const int nops = split == 3 ? 2 : 1;
-  const size_t fixed = 1024 + (size_t)aslots * TM_SUB * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
+  const size_t fixed = 1024 + (size_t)aslots * sub * 2 * nops * TM_OP_BYTES + TM_TAIL_BYTES;
   int s = (int)((227 * 1024 - fixed) / (size_t)TM_OP_BYTES);
   return s > TM_MAX_STAGES ? TM_MAX_STAGES : s;
 }
 
-// work units of one pair: super-blocks (2 row-blocks) of the A operand x column tiles, for each product
-int tm_units(int tm, int tn, int passes) {
-  return ((tm + 1) / 2) * tn + (passes == 2 ? ((tn + 1) / 2) * tm : 0);
+// work units of one pair: super-blocks (`sub` row-blocks) of the A operand x column tiles, for each product
+int tm_units(int tm, int tn, int passes, int sub) {
+  return ((tm + sub - 1) / sub) * tn + (passes == 2 ? ((tn + sub - 1) / sub) * tm : 0);
 }
 
 int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows) {
@@ -743,15 +761,16 @@ int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper,
 }
 
 int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchArgs a, int num_sms, cudaStream_t st) {
-  // exact mode: the unit's A operand (2 row-blocks x 64 KB) is resident, five 16 KB B stages stream behind it - each
-  // stage now feeds 16 / 8 MMAs (1024 / 512 cycles), so five cover the TMA latency.  Single-pass mode: two A slots.
+  // exact mode: ONE resident A slot (sub x 64 KB); the rest of shared memory is the B ring of 16 KB stages (nine at
+  // sub = 1, five at sub = 2 where each stage feeds twice the MMAs).  Single-pass mode: two A slots.
   static const int env_aslots = getenv("SFD2_TM_ASLOTS") ? atoi(getenv("SFD2_TM_ASLOTS")) : 0;
   a.aslots = env_aslots ? env_aslots : (a.split == 3 ? 1 : 2);
   static const int env_debug = getenv("SFD2_TM_DEBUG") ? atoi(getenv("SFD2_TM_DEBUG")) : 0;
   a.debug = env_debug;
-  a.stages = tm_stages(a.split, a.aslots);
-  const size_t smem = tm_smem_bytes(a.split, a.aslots, a.stages);
-  SFD2_CUDA(cudaFuncSetAttribute(tc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  a.stages = tm_stages(a.split, a.sub, a.aslots);
+  const size_t smem = tm_smem_bytes(a.split, a.sub, a.aslots, a.stages);
+  auto kern = a.sub == 2 ? tc_match_kernel<2> : tc_match_kernel<1>;
+  SFD2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (a.total_tiles <= 0) return SFD2_OK;
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   cudaLaunchConfig_t cfg{};
@@ -764,7 +783,7 @@ int launch_match_tc(const CUtensorMap& tm_hi, const CUtensorMap& tm_lo, TcMatchA
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_match_kernel, tm_hi, tm_lo, a));
+  SFD2_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_hi, tm_lo, a));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

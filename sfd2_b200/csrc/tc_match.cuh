@@ -40,6 +40,7 @@ struct TcMatchArgs {
   int passes;             // 1: one product, rows thread-local + columns through the threshold filter; 2: both products, rows only (top-2)
   int cols;               // passes == 1: reduce the columns too (mutual check)
   int split, stages, aslots;
+  int sub;                // row-blocks per work unit (1 or 2), see tc_match.cu
   int mutual, ratio_mode;
   int debug;              // SFD2_TM_DEBUG (experiments only): 1 = epilogue handshakes without reductions, 2 = no column path, 4 = no finish tail
   float dist_th, ratio_th;
@@ -52,9 +53,9 @@ struct TcMatchArgs {
   float* sim0;
 };
 
-size_t tm_smem_bytes(int split, int aslots, int stages);
-int tm_stages(int split, int aslots);
-int tm_units(int tm, int tn, int passes);
+size_t tm_smem_bytes(int split, int sub, int aslots, int stages);
+int tm_stages(int split, int sub, int aslots);
+int tm_units(int tm, int tn, int passes, int sub);
 int tm_make_plane_map(CUtensorMap* tm, const __half* base, size_t rows);
 int launch_match_prep(const MOperD* opers_dev, const MTabInline* inl, int noper, int total_prows, bool any_ids, __half* hi, __half* lo, int* remap,
                       int* efflen, unsigned long long* keys, unsigned* sec, long long nkeys, int* done, int nprob,
