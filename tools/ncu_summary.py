@@ -46,7 +46,10 @@ if len(sys.argv) > 5:
             tot += float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
             n += 1
     tj = json.load(open(tj_path)) if os.path.exists(tj_path) else {}
+    import hashlib
+    ksrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sfd2_b200", "csrc", "tc_conv.cu")
     tj[prec] = {"tc_conv_bytes_per_launch": tot / max(n, 1), "launches": n, "source": os.path.basename(rep),
+                "kernel_sha": hashlib.sha1(open(ksrc, "rb").read()).hexdigest()[:12],
                 "metric": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full"}
     json.dump(tj, open(tj_path, "w"), indent=1)
     print("traffic", prec, tot / max(n, 1))
