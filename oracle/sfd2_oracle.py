@@ -357,7 +357,8 @@ def resize_target(h: int, w: int, resize_max=None, resize_force=False):
 
 
 def _cubic_coeffs(x: np.ndarray) -> np.ndarray:
-    """OpenCV interpolateCubic (imgproc/resize.cpp, opencv-python 4.13 in this image; the reference pins no version),
+    """OpenCV interpolateCubic (imgproc/resize.cpp; the reference's requirements.txt:12 pins opencv-python 4.5.5.64, this image
+    has 4.13.0 - same float cubic path),
     A = -0.75, float32 arithmetic, c3 = 1 - c0 - c1 - c2."""
     x = x.astype(np.float32)
     A = np.float32(-0.75)
