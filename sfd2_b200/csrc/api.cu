@@ -77,6 +77,7 @@ struct sfd2_ctx {
   cudaStream_t copy_stream = nullptr;          // H2D of batched host inputs
   std::vector<cudaEvent_t> img_ready;
   int debug_flags = 0;
+  int cand_cap_override = 0;     // SFD2_CAND_CAP (test hook): cap the NMS candidate list to exercise the overflow report
   int last_prec = -1;
   // host-API staging
   void* img_dev = nullptr; size_t img_cap = 0;
@@ -189,6 +190,7 @@ static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
     if ((rc = reserve(w.nmsdbg, w.cap_nmsdbg, (size_t)H * W * sizeof(float)))) return rc;
     // NMS survivors are >= 5 px apart except on exact plateaus: H*W/16 leaves 1.5x headroom.
     w.cap = (int)(((size_t)H * W) / 16) + 4096;
+    if (c->cand_cap_override > 0 && c->cand_cap_override < w.cap) w.cap = c->cand_cap_override;
     int cap2 = 1;
     while (cap2 < w.cap) cap2 <<= 1;
     if ((rc = reserve(w.cand, w.cap_cand, (size_t)w.cap * sizeof(unsigned long long)))) return rc;
@@ -394,6 +396,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   sfd2_ctx* c = new sfd2_ctx();
   c->device = device;
   if (env_streams) c->nstreams = atoi(env_streams);
+  if (const char* e = getenv("SFD2_CAND_CAP")) c->cand_cap_override = atoi(e);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; set_error("cudaGetDeviceProperties failed"); return SFD2_ERR_CUDA; }
   c->num_sms = prop.multiProcessorCount;

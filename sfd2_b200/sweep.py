@@ -65,16 +65,28 @@ class Sweep:
 
     def pairs_host(self, frames0, frames1):
         """Same with HOST frames (pinned uint8 [P,H,W,3]) in and host numpy out: features of both frames as the
-        extract stage stores them, matches0 / sim0 as match_features stores them."""
-        P = frames0.shape[0]
-        both = torch.cat([torch.as_tensor(frames0), torch.as_tensor(frames1)])
-        out = {"keypoints": [], "scores": [], "descriptors": [], "counts": [], "matches0": None, "sim0": None}
-        dev = both.to(self.device, non_blocking=True)
+        extract stage stores them, matches0 / sim0 as match_features stores them.  Frames go straight into a persistent
+        device buffer (no host-side concatenation), results come back through persistent pinned buffers with one
+        synchronisation; the returned arrays are views of those buffers (valid until the next call)."""
+        f0, f1 = torch.as_tensor(frames0), torch.as_tensor(frames1)
+        P = f0.shape[0]
+        shape = (2 * P,) + tuple(f0.shape[1:])
+        st = self.__dict__.setdefault("_pairs_stage", {})
+        dev = st.get("dev")
+        if dev is None or tuple(dev.shape) != shape:
+            dev = st["dev"] = torch.empty(shape, dtype=torch.uint8, device=self.device)
+        dev[:P].copy_(f0, non_blocking=True)
+        dev[P:].copy_(f1, non_blocking=True)
         feats, m0, s0 = self.pairs(dev[:P], dev[P:])
-        self.ex.check_status()
-        res = {k: v.cpu().numpy() for k, v in feats.items()}
-        res["matches0"], res["sim0"] = m0.cpu().numpy(), s0.cpu().numpy()
-        return res
+        out = {}
+        for k, v in list(feats.items()) + [("matches0", m0), ("sim0", s0)]:
+            h = st.get(k)
+            if h is None or tuple(h.shape) != tuple(v.shape) or h.dtype != v.dtype:
+                h = st[k] = torch.empty(tuple(v.shape), dtype=v.dtype).pin_memory()
+            h.copy_(v, non_blocking=True)
+            out[k] = h
+        self.ex.check_status()                # synchronises the stream: the copies above are complete
+        return {k: v.numpy() for k, v in out.items()}
 
 
 def image_sweep(images_u8, weight_path, rank=0, world=1, **kw):
@@ -103,8 +115,9 @@ def pair_sweep(pairs, weight_path, rank=0, world=1, keep=False, **kw):
             m0 = r["matches0"][p, :n0]
             out["n_matches"].append(int((m0 >= 0).sum()))
             if keep:
-                out["pairs"].append({"keypoints0": r["keypoints"][p, :n0], "keypoints1": r["keypoints"][P + p, :n1],
-                                     "scores0": r["scores"][p, :n0], "descriptors0": r["descriptors"][p, :n0],
-                                     "descriptors1": r["descriptors"][P + p, :n1], "matches0": m0.copy(),
+                # copies: r's arrays are views of pinned buffers that the next batch overwrites
+                out["pairs"].append({"keypoints0": r["keypoints"][p, :n0].copy(), "keypoints1": r["keypoints"][P + p, :n1].copy(),
+                                     "scores0": r["scores"][p, :n0].copy(), "descriptors0": r["descriptors"][p, :n0].copy(),
+                                     "descriptors1": r["descriptors"][P + p, :n1].copy(), "matches0": m0.copy(),
                                      "sim0": r["sim0"][p, :n0].copy()})
     return out

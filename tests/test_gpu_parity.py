@@ -654,3 +654,30 @@ def test_prefetch_overlaps_upload_without_changing_results(golden):
     other = extract_resnet_return(m, imgs[2], topK=500, conf_th=0.001, scales=[1.0])           # not the prefetched tensor
     for k in other:
         assert np.array_equal(other[k], plain[2][k]), k
+
+
+def test_candidate_overflow_is_reported_on_every_path(monkeypatch):
+    """More NMS candidates than the workspace holds (H*W/16 + 4096; cannot happen without exact plateaus, so the test
+    hook SFD2_CAND_CAP shrinks the list): the synchronous calls must raise - host path AND device path - the batched
+    device path must report it through check_status(), and the flag must not leak into the next call.  The standalone
+    NMS entry point is exercised with a real plateau."""
+    from gpu_util import WEIGHTS, nms_select
+    from sfd2_b200 import get_model, extract_resnet_return, Extractor, _lib
+    with pytest.raises(_lib.Sfd2Error, match="overflow"):
+        nms_select(np.full((200, 300), 0.5, np.float32), conf_th=0.001, border=4, topk=100)      # every pixel ties
+    monkeypatch.setenv("SFD2_CAND_CAP", "64")
+    m, _ = get_model("ressegnetv2", WEIGHTS, use_stability=True, precision="exact")
+    m.cuda()
+    ex = Extractor(WEIGHTS, precision="exact", topk=32, conf_th=0.001)
+    monkeypatch.delenv("SFD2_CAND_CAP")
+    img = torch.from_numpy(synth_image(9, 160, 200))                     # ~100 candidates > 64
+    with pytest.raises(_lib.Sfd2Error, match="candidates"):
+        extract_resnet_return(m, img, topK=32, conf_th=0.001, scales=[1.0])
+    with pytest.raises(_lib.Sfd2Error, match="candidates"):
+        extract_resnet_return(m, img.cuda(), topK=32, conf_th=0.001, scales=[1.0])
+    few = extract_resnet_return(m, img, topK=32, conf_th=0.05, scales=[1.0])     # few candidates: fine, and the flag was cleared
+    assert len(few["scores"]) <= 32
+    ex(img.cuda())
+    with pytest.raises(_lib.Sfd2Error, match="candidates"):
+        ex.check_status()
+    ex.check_status()                                                     # cleared by the failing query
