@@ -79,6 +79,7 @@ struct TcConvArgs {
   // (4 chunks) and the weight slabs a shallow one - the combined (A + B) stages left room for only two in flight
   int hw, hoff, a_plane_bytes, a_plane_off;
   int tile_w, tile_h, epi_rows, ring_bytes;
+  int dbg_nob;     // experiment: skip weight reloads (timing only)
   int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
   const float* bias;
@@ -167,7 +168,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (a.halo) {
       const int planes = (a.split == 3) ? 2 : 1;
       uint8_t* bring = smem + (size_t)a.a_slots * a.a_slot_bytes;
-      int sa = 0, sb = 0;
+      int sa = 0, sb = 0, nb_loaded = 0;
       uint32_t pha = 0, phb = 0;
       for (int it = 0; it < a.iters; ++it) {
         if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
@@ -192,6 +193,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               uint8_t* bs = bring + (size_t)sb * a.b_bytes;
               const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
               if (elect_one()) {
+                if (a.dbg_nob && nb_loaded >= a.b_stages) {
+                  mbar_arrive(&full[sb]);            // EXPERIMENT (SFD2_TC_DEBUG_NOB): no weight traffic after the first fill
+                } else {
                 mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
                 if (a.mc > 1) {
                   const int ro = (int)crank * (a.n_mma / 2);
@@ -199,7 +203,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 } else {
                   tma_load_2d(bs, tb, &full[sb], bcol, brow);
                 }
+                }
               }
+              ++nb_loaded;
               __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
@@ -884,6 +890,11 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
   a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
+  {
+    static const int nob = getenv("SFD2_TC_DEBUG_NOB") ? atoi(getenv("SFD2_TC_DEBUG_NOB")) : 0;
+    a.dbg_nob = (nob == 1 && a.cat) || nob == 2 ? 1 : 0;     // 1: grouped layers only, 2: every halo-mode layer
+    if (a.dbg_nob) a.mc = 1;
+  }
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
   if (a.mc > 1 && grid > num_sms) grid -= 2;
