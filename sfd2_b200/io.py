@@ -61,7 +61,22 @@ class Store:
         return (group in self.h5) if self.h5 is not None else (group in self.groups)
 
     def names(self):
-        return list(self.h5.keys()) if self.h5 is not None else list(self.groups)
+        """Record names (image names / pair keys).  In an HDF5 file a name like 'db/1.jpg' is a nested group: walk down to
+        the groups that hold datasets."""
+        if self.h5 is None:
+            return list(self.groups)
+        out = []
+
+        def walk(g, prefix):
+            for k in g.keys():
+                v = g[k]
+                if hasattr(v, "keys"):
+                    if any(not hasattr(v[c], "keys") for c in v.keys()):
+                        out.append(prefix + k)
+                    else:
+                        walk(v, prefix + k + "/")
+        walk(self.h5, "")
+        return out
 
     def read(self, group):
         if self.h5 is not None:

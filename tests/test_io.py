@@ -27,10 +27,12 @@ def test_names_to_pair():
     assert names_to_pair("db/1.jpg", "query/night/2.jpg") == "db-1.jpg_query-night-2.jpg"
 
 
-def test_feature_store_layout_and_match_loop(tmp_path):
+@pytest.mark.parametrize("ext", ["npz", "h5"])
+def test_feature_store_layout_and_match_loop(tmp_path, ext):
+    """ext = h5: a real HDF5 file (h5py when installed, else the bundled h5lite writer / reader)."""
     imgs = [{"name": f"db/{i}.jpg", "image": torch.full((1, 3, 40, 60), 0.1 * (i + 1)), "original_size": (120, 80)}
             for i in range(3)]
-    fpath = tmp_path / "feats.npz"
+    fpath = tmp_path / f"feats.{ext}"
     with Store(fpath, "w") as st:
         n = extract_to_store(None, _fake_extractor, imgs, st, {"max_keypoints": 12, "conf_th": 0.001, "scales": [1.0]})
         assert n == 3
@@ -46,7 +48,7 @@ def test_feature_store_layout_and_match_loop(tmp_path):
     ref = _fake_extractor(None, imgs[1]["image"], 12, None, 0.001, [1.0])["keypoints"]
     np.testing.assert_allclose(f["keypoints"], (ref + .5) * 2 - .5)
     pairs = ["db/0.jpg db/1.jpg", "db/1.jpg db/0.jpg", "db/0.jpg db/2.jpg", "db/0.jpg db/1.jpg"]
-    mpath = tmp_path / "matches.npz"
+    mpath = tmp_path / f"matches.{ext}"
     with Store(mpath, "w") as ms:
         assert match_to_store(_FakeMatcher(), pairs, feats, ms, device="cpu") == 2   # reversed + repeated pair skipped
     ms = Store(mpath, "r")
