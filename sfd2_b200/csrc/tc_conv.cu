@@ -424,6 +424,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (ch >= nstore || it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
       int x0, y0;
       tile_xy(it, x0, y0);
+      if (a.dbg_nob & 8) { mbar_arrive(wres); return; }
       mbar_expect_tx(wres, a.has_res == 2 ? 4096u : 2048u);
       tma_load_3d(st, &tmR_hi, wres, ch * 32, x0, y0);
       if (a.has_res == 2) tma_load_3d(st + 2048, &tmR_lo, wres, ch * 32, x0, y0);
@@ -509,6 +510,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // (atomicAdd on a zeroed map: two addends, so the result does not depend on their order)
       float sta0 = h ? 0.f : a.sta_b[0], sta1 = h ? 0.f : a.sta_b[1], sta2 = h ? 0.f : a.sta_b[2];
       for (int ch = h; ch < nstore; ch += 2) {
+        if (a.dbg_nob & 16) break;                 // experiment: null epilogue (timing only)
         const int c0 = ch * 32;
         // accumulator column of channel c0: diag-cat keeps [main 64 | correction 64] per 64-channel chunk
         const uint32_t tcol = a.cat ? (uint32_t)((c0 >> 6) * 128 + (c0 & 63)) : (uint32_t)c0;
@@ -517,7 +519,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         float x[32];
         tmem_ld32(taddr + tcol, v);
         if (!a.has_res) {                         // this warp's previous store must have finished reading the
-          if (lane == 0) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
+          if (lane == 0 && !(a.dbg_nob & 2)) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
           __syncwarp();
         }
         tmem_ld_wait();
@@ -598,11 +600,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
+          if (!(a.dbg_nob & 4)) {
           tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
           if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
+          }
           bulk_commit();
           if (a.has_res) {                        // refill the tile with the residual of this warp's next chunk
-            bulk_wait_read<0>();
+            if (!(a.dbg_nob & 2)) bulk_wait_read<0>();
             if (ch + 2 < nstore) issue_res(it, ch + 2); else issue_res(it + 1, h);
           }
         }
@@ -894,6 +898,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     static const int nob = getenv("SFD2_TC_DEBUG_NOB") ? atoi(getenv("SFD2_TC_DEBUG_NOB")) : 0;
     a.dbg_nob = (nob == 1 && a.cat) || nob == 2 ? 1 : 0;     // 1: grouped layers only, 2: every halo-mode layer
     if (a.dbg_nob) a.mc = 1;
+    if (nob == 4) a.dbg_nob = 2;
+    if (nob == 8) a.dbg_nob = 4;                              // 8: epilogue computes but issues no output stores (timing only)
+    if (nob == 16) a.dbg_nob = 8;
+    if (nob == 32) a.dbg_nob = 16 | 8;                        // 32: null epilogue - accumulators are handed back untouched (timing only)                             // 16: residual tiles are not loaded (timing only)                              // 4: epilogue does not wait for its TMA stores to drain (RACY, timing only)
   }
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
