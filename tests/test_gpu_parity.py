@@ -681,3 +681,69 @@ def test_candidate_overflow_is_reported_on_every_path(monkeypatch):
     with pytest.raises(_lib.Sfd2Error, match="candidates"):
         ex.check_status()
     ex.check_status()                                                     # cleared by the failing query
+
+
+def test_matcher_fuzz_against_fp64():
+    """Random shapes (1 .. 1700 rows, tile-boundary and prime sizes), all modes, single calls and grouped calls with
+    device-side counts: every row must equal the float64 evaluation unless its decision is near-tied (< 2e-6)."""
+    from sfd2_b200.matchers import match_dev, match_sets_dev
+    rng = np.random.RandomState(123)
+    sizes = [1, 2, 127, 128, 129, 255, 256, 257, 383, 511, 640, 769, 1021, 1279, 1700]
+
+    def make(n, seed):
+        base, _ = synth_descriptors(seed % 7, 1800, 10)
+        d = base[rng.permutation(1800)[:n]] + 0.3 * rng.randn(n, 128).astype(np.float32)
+        return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+    def expect(d0, d1, mutual, ratio):
+        sim = d0.astype(np.float64) @ d1.astype(np.float64).T
+        nn12 = sim.argmax(1)
+        ok = np.ones(len(d0), bool)
+        srt = np.sort(sim, axis=1)
+        gap = srt[:, -1] - srt[:, -2] if sim.shape[1] > 1 else np.full(len(d0), np.inf)
+        cs = np.sort(sim, axis=0)
+        cgap = cs[-1] - cs[-2] if sim.shape[0] > 1 else np.full(sim.shape[1], np.inf)
+        if ratio:
+            if sim.shape[1] > 1:
+                ok &= 2 * (1 - srt[:, -1]) <= ratio * ratio * 2 * (1 - srt[:, -2])
+        if mutual:
+            nn21 = sim.argmax(0)
+            ok &= nn21[nn12] == np.arange(len(d0))
+            if ratio and sim.shape[0] > 1:
+                ok &= (2 * (1 - cs[-1]) <= ratio * ratio * 2 * (1 - cs[-2]))[nn12]
+        return np.where(ok, nn12, -1), gap, cgap, nn12
+
+    ncase = 0
+    for it in range(24):
+        n0, n1 = int(rng.choice(sizes)), int(rng.choice(sizes))
+        d0, d1 = make(n0, it), make(n1, it + 100)
+        a, b = torch.from_numpy(d0).cuda(), torch.from_numpy(d1).cuda()
+        for mutual, ratio in ((True, None), (False, None), (True, 0.9)):
+            m, _ = match_dev(a, b, mutual=mutual, ratio_th=ratio, precision="exact")
+            ref, gap, cgap, nn12 = expect(d0, d1, mutual, ratio)
+            bad = np.nonzero(m.cpu().numpy() != ref)[0]
+            for i in bad:
+                near = gap[i] < 2e-6 or cgap[nn12[i]] < 2e-6 or ratio is not None
+                assert near, (n0, n1, mutual, ratio, int(i), float(gap[i]))
+            assert len(bad) <= max(2, n0 // 100), (n0, n1, mutual, ratio, len(bad))
+            ncase += 1
+    # grouped call: capacity 1700 per set, valid counts on the device
+    K = 1700
+    counts = [int(rng.choice(sizes)) for _ in range(10)]
+    D = np.zeros((len(counts), K, 128), np.float32)
+    for i, c in enumerate(counts):
+        D[i, :c] = make(c, 50 + i)
+    dd, cc = torch.from_numpy(D).cuda(), torch.tensor(counts, dtype=torch.int32, device="cuda")
+    sets = [{"data": dd[i], "count": cc[i:i + 1]} for i in range(len(counts))]
+    pa = [int(x) for x in rng.randint(0, len(counts), 16)]
+    pb = [int(x) for x in rng.randint(0, len(counts), 16)]
+    m, _ = match_sets_dev(sets, pa, pb, precision="exact")
+    m = m.view(16, K).cpu().numpy()
+    for k, (ia, ib) in enumerate(zip(pa, pb)):
+        ref, gap, cgap, nn12 = expect(D[ia, :counts[ia]], D[ib, :counts[ib]], True, None)
+        got = m[k, :counts[ia]]
+        bad = np.nonzero(got != ref)[0]
+        for i in bad:
+            assert gap[i] < 2e-6 or cgap[nn12[i]] < 2e-6, (k, ia, ib, int(i))
+        assert (m[k, counts[ia]:] == -1).all()
+    assert ncase == 72
