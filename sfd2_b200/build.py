@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsfd2_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_match.cu", "post.cu", "match.cu", "preprocess.cu"]
+SOURCES = ["api.cu", "simt_conv.cu", "tc_conv.cu", "tc_conv1a.cu", "tc_desc_sparse.cu", "tc_match.cu", "post.cu", "match.cu", "preprocess.cu"]
 # hardware probes (tools/umma_probe.py, tools/mma_rate_probe.py): measurement scaffolding, only on request
 if os.environ.get("SFD2_WITH_PROBES") == "1":
     SOURCES.append("umma_probe.cu")

@@ -57,6 +57,7 @@ struct Ws {
   int H2 = 0, W2 = 0, H4 = 0, W4 = 0, H8 = 0, W8 = 0;
   float4* nimg = nullptr;  // normalised image, NHWC4 fp32
   float *logits = nullptr, *semi = nullptr, *descmap = nullptr, *sta = nullptr, *heat = nullptr, *nmsdbg = nullptr;
+  float* drows = nullptr; size_t cap_drows = 0;     // [4 * topk][128] tap descriptors of the sparse descriptor head
   unsigned long long *cand = nullptr, *scratch = nullptr;
   size_t cap_nimg = 0, cap_logits = 0, cap_semi = 0, cap_descmap = 0, cap_sta = 0, cap_heat = 0, cap_nmsdbg = 0,
          cap_cand = 0, cap_scratch = 0;
@@ -142,7 +143,8 @@ static void free_workspace(Ws& w) {
   }
   cudaFree(w.nimg); w.nimg = nullptr;
   cudaFree(w.logits); cudaFree(w.semi); cudaFree(w.descmap); cudaFree(w.sta); cudaFree(w.heat); cudaFree(w.nmsdbg);
-  cudaFree(w.cand); cudaFree(w.scratch); cudaFree(w.counter); cudaFree(w.status);
+  cudaFree(w.cand); cudaFree(w.scratch); cudaFree(w.counter); cudaFree(w.status); cudaFree(w.drows);
+  w.drows = nullptr; w.cap_drows = 0;
   w.logits = w.semi = w.descmap = w.sta = w.heat = w.nmsdbg = nullptr;
   w.cand = w.scratch = nullptr; w.counter = w.status = nullptr;
   w.cap_nimg = w.cap_logits = w.cap_semi = w.cap_descmap = w.cap_sta = w.cap_heat = w.cap_nmsdbg = w.cap_cand = w.cap_scratch = 0;
@@ -161,8 +163,11 @@ static int reserve(T*& p, size_t& cap, size_t bytes, bool* grew = nullptr) {
   return SFD2_OK;
 }
 
-static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec) {
+static int ensure_workspace(const sfd2_ctx* c, Ws& w, int H, int W, int prec, int topk) {
   int rc;
+  if (g_sparse_desc && (prec == SFD2_PREC_TC_MIXED || prec == SFD2_PREC_TC_FAST) &&
+      (rc = reserve(w.drows, w.cap_drows, (size_t)4 * topk * SFD2_DESC_DIM * sizeof(float))))
+    return rc;
   const bool want_tc = (prec != SFD2_PREC_FP32);
   if (w.wsH != H || w.wsW != W) {
     w.wsH = H; w.wsW = W;
@@ -305,6 +310,8 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
   // ConvSta rides in the epilogue of the layer that produces out4 (tcgen05 modes)
   const bool fuse_sta = tc && p->use_stability && g_fuse_sta;
+  // single-pass descriptor head (`mixed`, `fast`): evaluate it after selection, only where descriptors are sampled
+  const bool sparse_d = tc && split_d == 1 && g_sparse_desc && w.drows != nullptr;
   auto conv = [&](const char* name, int in, int out, int res, int sp = 0, bool with_sta = false) -> int {
     const Layer& L = c->L(name);
     // the fused ConvSta accumulates with atomicAdd (two epilogue warps per pixel): start from zero
@@ -336,7 +343,7 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
     // head epilogues fused: the detector head writes the exp-normalised 64 cell scores straight into `semi`,
     // the descriptor head writes L2-normalised rows (no softmax65 / l2norm128 launches in the tcgen05 modes)
     RUNP("tc_conv:headP", launch_conv_tc(A[PA], c->L("headP"), logit_act, nullptr, w.map_semi, split, c->num_sms, st, 2));
-    RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split_d, c->num_sms, st, 1));
+    if (!sparse_d) RUNP("tc_conv:headD", launch_conv_tc(A[DA], c->L("headD"), desc_act, nullptr, w.map_desc, split_d, c->num_sms, st, 1));
   } else {
     RUNP("conv_f32:headP", launch_conv_simt(A[PA], c->L("headP"), logit_act, nullptr, st));
     RUNP("conv_f32:headD", launch_conv_simt(A[DA], c->L("headD"), desc_act, nullptr, st));
@@ -351,7 +358,10 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
                          (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
                  w.counter, st));
   RUNP("select", launch_select(w.cand, w.cap, w.counter, W, p->topk, kpts, scores, count, w.status, w.scratch, st));
-  RUNP("sample", launch_sample(w.descmap, w.H4, w.W4, H, W, kpts, count, p->topk, desc, st));
+  if (sparse_d)   // the descriptor head only at the pixels that are sampled (tc_desc_sparse.cu); bit-identical rows
+    RUNP("tc_conv:headD", launch_desc_sparse(A[DA], c->L("headD"), H, W, kpts, count, p->topk, w.drows, desc, st));
+  else
+    RUNP("sample", launch_sample(w.descmap, w.H4, w.W4, H, W, kpts, count, p->topk, desc, st));
 #undef RUN
 #undef RUNP
   return SFD2_OK;
@@ -386,6 +396,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   SFD2_CUDA(cudaSetDevice(device));
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_PDL")) g_tc_pdl = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_SPARSE_DESC")) g_sparse_desc = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_NSPLIT")) g_tc_nsplit = atoi(e) != 0;
   if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;
@@ -471,7 +482,7 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
   int ns = ((n > 1 || ready) && c->nstreams > 1 && !c->prof_on) ? std::min(c->nstreams, (int)sfd2_ctx::kMaxStreams) : 1;
   if (ns > n && n > 1) ns = n;
   for (int k = 0; k < ns; ++k) {
-    rc = ensure_workspace(c, c->ws[k], h, w, p->precision);
+    rc = ensure_workspace(c, c->ws[k], h, w, p->precision, p->topk);
     if (rc) return rc;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

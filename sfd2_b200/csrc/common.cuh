@@ -93,6 +93,9 @@ int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, in
 // sta / sta_out: fuse ConvSta (1x1 256 -> 3) on this layer's output into the epilogue (fp16-plane outputs only)
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
                    int num_sms, cudaStream_t st, int epi_fn = 0, const Layer* sta = nullptr, float* sta_out = nullptr);
+// tc_desc_sparse.cu
+int launch_desc_sparse(const Act& in, const Layer& L, int H, int W, const float* kpts, const int32_t* count, int topk,
+                       float* rows, float* desc_out, cudaStream_t st);
 // post.cu
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st);
@@ -126,7 +129,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_tc_pdl, g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_diagcat, g_tc_split1x1;
+extern int g_sparse_desc, g_tc_pdl, g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_diagcat, g_tc_split1x1;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

@@ -747,3 +747,33 @@ def test_matcher_fuzz_against_fp64():
             assert gap[i] < 2e-6 or cgap[nn12[i]] < 2e-6, (k, ia, ib, int(i))
         assert (m[k, counts[ia]:] == -1).all()
     assert ncase == 72
+
+
+@pytest.mark.parametrize("prec", ["mixed", "fast"])
+def test_sparse_descriptor_head_equals_dense(golden, monkeypatch, prec):
+    """Single-pass modes evaluate the descriptor head only at the sampled tap pixels (tc_desc_sparse.cu): every output must
+    be bit-identical to the dense head + sample_kernel path (SFD2_SPARSE_DESC=0), incl. odd sizes, K > candidates, 0 keypoints
+    and the batched path."""
+    from gpu_util import WEIGHTS
+    from sfd2_b200 import get_model, extract_resnet_return, Extractor
+    monkeypatch.setenv("SFD2_SPARSE_DESC", "0")
+    dense, _ = get_model("ressegnetv2", WEIGHTS, use_stability=True, precision=prec)
+    dense.cuda()
+    exd = Extractor(WEIGHTS, precision=prec, topk=700)
+    monkeypatch.delenv("SFD2_SPARSE_DESC")
+    sparse, _ = get_model("ressegnetv2", WEIGHTS, use_stability=True, precision=prec)
+    sparse.cuda()
+    exs = Extractor(WEIGHTS, precision=prec, topk=700)
+    imgs = [_img(golden("c1_640x480")), _img(golden("odd_100x141")), synth_image(33, 250, 333), synth_image(34, 64, 80, sigma=1.5)]
+    for im in imgs:
+        for K in (300, 5000, -1):
+            a = extract_resnet_return(dense, torch.from_numpy(im), topK=K, conf_th=0.001, scales=[1.0])
+            b = extract_resnet_return(sparse, torch.from_numpy(im), topK=K, conf_th=0.001, scales=[1.0])
+            for k in a:
+                assert np.array_equal(a[k], b[k]), (im.shape, K, k, float(np.abs(a[k] - b[k]).max()) if a[k].shape == b[k].shape else None)
+    z = extract_resnet_return(sparse, torch.zeros(1, 3, 64, 80), topK=100, conf_th=0.5, scales=[1.0])
+    assert z["descriptors"].shape == (0, 128)
+    batch = torch.from_numpy(np.concatenate([synth_image(40 + i, 240, 320) for i in range(5)])).cuda()
+    od, os_ = exd(batch), exs(batch)
+    for k in od:
+        assert torch.equal(od[k], os_[k]), k
