@@ -159,9 +159,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   pdl_wait();                          // everything above touched only weights / parameters; activations from here on
   const uint32_t tmem_base = *tmem_slot;
   const int nkb = a.taps * a.kchunks;
-  // tile of iteration `it`; a cluster whose FIRST tile is out of range skips the iteration as a whole,
-  // otherwise an out-of-range tile is processed as an all-padding dummy so that peers stay in lock step
-  const int cl_first = (int)blockIdx.x - (int)crank;
+  // Unit of iteration `it` = (tile, channel pass nh).  Units are dealt round-robin to the CLUSTERS: cluster-unit
+  // v = cluster + it * #clusters covers tile pair v / nsplit (tile = pair * mc + rank: cluster peers consume the same weight
+  // slabs in lock step, which is what the multicast needs) and channel pass v % nsplit.  With the two passes of a wide
+  // exact-mode layer as separate units, 950 tiles on 74 clusters take 13 half-tile rounds instead of 7 whole ones.  A
+  // cluster whose FIRST tile is out of range stops; otherwise an out-of-range tile is processed as an all-padding dummy.
+  const int ncl = (int)gridDim.x / a.mc, cl = ((int)blockIdx.x - (int)crank) / a.mc;
+  auto unit = [&](int it, int& tile, int& nh) -> bool {
+    const int v = cl + it * ncl;
+    const int tp = (a.nsplit == 2) ? (v >> 1) : v;
+    nh = (a.nsplit == 2) ? (v & 1) : 0;
+    tile = tp * a.mc + (int)crank;
+    return tp * a.mc < a.num_tiles;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -171,10 +181,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int sa = 0, sb = 0, nb_loaded = 0;
       uint32_t pha = 0, phb = 0;
       for (int it = 0; it < a.iters; ++it) {
-        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
-        const int tile = blockIdx.x + it * gridDim.x;
+        int tile, nh;
+        if (!unit(it, tile, nh)) break;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        for (int nh = 0; nh < a.nsplit; ++nh)
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
@@ -216,8 +225,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < a.iters; ++it) {
-        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
-        const int tile = blockIdx.x + it * gridDim.x;
+        int tile, nh;
+        if (!unit(it, tile, nh)) break;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
         for (int tap = 0; tap < a.taps; ++tap) {
           const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
@@ -260,14 +269,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     // (whole warp runs the loops; tcgen05.mma / commit come from the one lane elect.sync picks - always the same)
     if (a.halo) {
-      const uint32_t idesc = make_idesc_f16(128, a.cat ? 64 : a.n_mma);
-      const uint32_t idesc_cat = make_idesc_f16(128, 128);
+      const int dbg_n = (a.dbg_nob & 32) ? 16 : ((a.dbg_nob & 64) ? 32 : 64);   // EXPERIMENT: narrower grouped MMAs (timing only)
+      const uint32_t idesc = make_idesc_f16(128, a.cat ? dbg_n : a.n_mma);
+      const uint32_t idesc_cat = make_idesc_f16(128, 2 * dbg_n);
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
       int sa = 0, sb = 0, buf = 0;
       uint32_t pha = 0, phb = 0, bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
-        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
-        for (int nh = 0; nh < a.nsplit; ++nh) {
+        int tile, nh;
+        if (!unit(it, tile, nh)) break;
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
@@ -338,7 +348,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (elect_one()) umma_commit(&tfull[buf]);
         __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
-        }
       }
     } else {
       const uint32_t idesc = make_idesc_f16(128, a.n_mma);
@@ -348,7 +357,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int buf = 0;
       uint32_t bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
-        if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
+        int tile, nh;
+        if (!unit(it, tile, nh)) break;
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
@@ -415,15 +425,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
     const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
     const int r = lane;                          // row of this warp's 32-pixel box (2 tile rows x 16 px)
-    auto tile_xy = [&](int it, int& x0, int& y0) {
-      const int tile = blockIdx.x + it * gridDim.x;
+    auto tile_xy = [&](int it, int& x0, int& y0, int& nh) -> bool {
+      int tile;
+      const bool ok = unit(it, tile, nh);
       x0 = (tile % a.tiles_x) * a.tile_w;
       y0 = (tile / a.tiles_x) * a.tile_h + a.epi_rows * q;
+      return ok;
     };
-    auto issue_res = [&](int it, int ch) {        // lane 0 only
-      if (ch >= nstore || it >= a.iters || cl_first + it * (int)gridDim.x >= a.num_tiles) return;
-      int x0, y0;
-      tile_xy(it, x0, y0);
+    auto issue_res = [&](int it, int ch) {        // lane 0 only (layers with a residual run a single channel pass)
+      int x0, y0, nh;
+      if (ch >= nstore || it >= a.iters || !tile_xy(it, x0, y0, nh)) return;
       if (a.dbg_nob & 8) { mbar_arrive(wres); return; }
       mbar_expect_tx(wres, a.has_res == 2 ? 4096u : 2048u);
       tma_load_3d(st, &tmR_hi, wres, ch * 32, x0, y0);
@@ -432,10 +443,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t rphase = 0u;
     if (a.has_res && lane == 0) issue_res(0, h);  // the residual of this warp's first chunk
     for (int it = 0; it < a.iters; ++it) {
-      if (cl_first + it * (int)gridDim.x >= a.num_tiles) break;
-      int x0, y0;
-      tile_xy(it, x0, y0);
-      for (int nh = 0; nh < a.nsplit; ++nh) {
+      int x0, y0, nh;
+      if (!tile_xy(it, x0, y0, nh)) break;
       const int cbase = nh * a.n_mma;             // first output channel of this pass (0 unless nsplit > 1)
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
@@ -621,7 +630,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           float* o = a.sta_out + ((size_t)py * a.Wo + px) * 3;
           atomicAdd(o, sta0); atomicAdd(o + 1, sta1); atomicAdd(o + 2, sta2);
         }
-      }
       }
     }
     if (lane == 0) bulk_wait_all();               // all output bytes are in global memory before the CTA exits
@@ -901,12 +909,14 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     if (nob == 4) a.dbg_nob = 2;
     if (nob == 8) a.dbg_nob = 4;                              // 8: epilogue computes but issues no output stores (timing only)
     if (nob == 16) a.dbg_nob = 8;
+    if (nob == 64 && a.cat) a.dbg_nob = 32;                  // 64 / 128: grouped layers issue N = 32|16 / 64|32 MMAs instead of 128|64 (WRONG results, timing only)
+    if (nob == 128 && a.cat) a.dbg_nob = 64;
     if (nob == 32) a.dbg_nob = 16 | 8;                        // 32: null epilogue - accumulators are handed back untouched (timing only)                             // 16: residual tiles are not loaded (timing only)                              // 4: epilogue does not wait for its TMA stores to drain (RACY, timing only)
   }
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
   if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
   if (a.mc > 1 && grid > num_sms) grid -= 2;
-  a.iters = cdiv(a.num_tiles, grid);
+  a.iters = cdiv(cdiv(a.num_tiles, a.mc) * a.nsplit, grid / a.mc);   // cluster-units per cluster (see `unit` in the kernel)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TC_THREADS);
