@@ -269,9 +269,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     // (whole warp runs the loops; tcgen05.mma / commit come from the one lane elect.sync picks - always the same)
     if (a.halo) {
-      const int dbg_n = (a.dbg_nob & 32) ? 16 : ((a.dbg_nob & 64) ? 32 : 64);   // EXPERIMENT: narrower grouped MMAs (timing only)
-      const uint32_t idesc = make_idesc_f16(128, a.cat ? dbg_n : a.n_mma);
-      const uint32_t idesc_cat = make_idesc_f16(128, 2 * dbg_n);
+      const uint32_t idesc = make_idesc_f16(128, a.cat ? 16 : a.n_mma);
+      const uint32_t idesc_cat = make_idesc_f16(128, 32);
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
       int sa = 0, sb = 0, buf = 0;
       uint32_t pha = 0, phb = 0, bphase = 0;
@@ -292,18 +291,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint64_t da_lo = make_desc_sw128_sbo(abase + (uint32_t)a.a_plane_off + off, (uint32_t)a.hw * 128);
             const bool first = (tap == 0) && (a.diag || kc == 0);
             if (a.cat) {
-              // one [w_hi | w_lo] slab: a_hi x both (N = 128: main | correction), then a_lo x w_hi (N = 64) into the
-              // correction columns - which the N = 128 MMA of this tap has already initialised when tap == 0
+              // K step k of the chunk = input channels 16k.. = two whole groups, whose 16 outputs are the only non-zero rows
+              // of the block-diagonal slab: rows [32k, 32k+32) of the slab hold [w_hi 16 | w_lo 16] of exactly those.
+              // a_hi x both (N = 32: main | correction columns of the 16 channels), then a_lo x w_hi (N = 16) into the
+              // correction columns - which the N = 32 MMA of this tap has already initialised when tap == 0
               mbar_wait(&full[sb], phb);
               tc_fence_after();
               const uint64_t dbc = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
               if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(dbc, k), idesc_cat, (first && k == 0) ? 0u : 1u);
+                for (int k = 0; k < 4; ++k)       // 32 slab rows = 4096 B further on; + the K offset inside the 128-byte rows
+                  umma_f16(dcol + 32u * k, desc_advance_k(da_hi, k), desc_advance_k(dbc, k) + (uint64_t)(k * (4096 >> 4)), idesc_cat, first ? 0u : 1u);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(dbc, k), idesc, 1u);
+                  umma_f16(dcol + 32u * k + 16u, desc_advance_k(da_lo, k), desc_advance_k(dbc, k) + (uint64_t)(k * (4096 >> 4)), idesc, 1u);
                 if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
               }
               __syncwarp();
@@ -521,9 +522,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       for (int ch = h; ch < nstore; ch += 2) {
         if (a.dbg_nob & 16) break;                 // experiment: null epilogue (timing only)
         const int c0 = ch * 32;
-        // accumulator column of channel c0: diag-cat keeps [main 64 | correction 64] per 64-channel chunk
-        const uint32_t tcol = a.cat ? (uint32_t)((c0 >> 6) * 128 + (c0 & 63)) : (uint32_t)c0;
-        const uint32_t coff = a.cat ? 64u : (uint32_t)a.acc_cols;
+        // accumulator column of channel c0: diag-cat keeps [main 16 | correction 16] per 16 channels, 2 columns per channel
+        const uint32_t tcol = a.cat ? (uint32_t)(2 * c0) : (uint32_t)c0;
+        const uint32_t coff = (uint32_t)a.acc_cols;
         uint32_t v[32];
         float x[32];
         tmem_ld32(taddr + tcol, v);
@@ -532,6 +533,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           __syncwarp();
         }
         tmem_ld_wait();
+        if (a.cat) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v[j + 16]);
+          tmem_ld32(taddr + tcol + 32u, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[16 + j] = __uint_as_float(v[j]) + __uint_as_float(v[j + 16]);
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
         if (a.corr) {
@@ -539,6 +548,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] += __uint_as_float(v[j]);
+        }
         }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -709,13 +719,14 @@ int tc_encode_weights(Layer& L) {
   SFD2_CUDA(cudaMalloc(&L.w_lo, lo.size() * sizeof(__half)));
   SFD2_CUDA(cudaMemcpy(L.w_hi, hi.data(), hi.size() * sizeof(__half), cudaMemcpyHostToDevice));
   SFD2_CUDA(cudaMemcpy(L.w_lo, lo.data(), lo.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  if (diag) {   // diag-cat slabs: row (tap*4 + kc)*128 + r = w_hi row (tap, kc*64 + r) for r < 64, w_lo row (.., r - 64) else
+  if (diag) {   // diag-cat slabs: row (tap*4 + kc)*128 + k*32 + j = w_hi row (tap, kc*64 + 16k + j) for j < 16, w_lo row (.., 16k + j - 16) else
     std::vector<__half> cat((size_t)taps * 4 * 128 * 64);
     for (int t = 0; t < taps; ++t)
       for (int kc = 0; kc < 4; ++kc)
         for (int r = 0; r < 128; ++r) {
-          const std::vector<__half>& src = r < 64 ? hi : lo;
-          memcpy(&cat[(((size_t)t * 4 + kc) * 128 + r) * 64], &src[((size_t)t * 256 + kc * 64 + (r & 63)) * 64], 64 * sizeof(__half));
+          const int k = r >> 5, j = r & 31;
+          const std::vector<__half>& src = j < 16 ? hi : lo;
+          memcpy(&cat[(((size_t)t * 4 + kc) * 128 + r) * 64], &src[((size_t)t * 256 + kc * 64 + 16 * k + (j & 15)) * 64], 64 * sizeof(__half));
         }
     SFD2_CUDA(cudaMalloc(&L.w_cat, cat.size() * sizeof(__half)));
     SFD2_CUDA(cudaMemcpy(L.w_cat, cat.data(), cat.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -909,8 +920,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     if (nob == 4) a.dbg_nob = 2;
     if (nob == 8) a.dbg_nob = 4;                              // 8: epilogue computes but issues no output stores (timing only)
     if (nob == 16) a.dbg_nob = 8;
-    if (nob == 64 && a.cat) a.dbg_nob = 32;                  // 64 / 128: grouped layers issue N = 32|16 / 64|32 MMAs instead of 128|64 (WRONG results, timing only)
-    if (nob == 128 && a.cat) a.dbg_nob = 64;
     if (nob == 32) a.dbg_nob = 16 | 8;                        // 32: null epilogue - accumulators are handed back untouched (timing only)                             // 16: residual tiles are not loaded (timing only)                              // 4: epilogue does not wait for its TMA stores to drain (RACY, timing only)
   }
   int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
