@@ -14,6 +14,8 @@ namespace sfd2 {
 
 static thread_local char g_err[1024] = "";
 thread_local long long g_launches = 0;
+int g_band_layers = 2;    // SFD2_BAND_LAYERS: how many of conv1b / conv2a / conv2b follow conv1a band by band (0..3)
+int g_host_bands = 4;     // SFD2_HOST_BANDS: row bands of a single host image's upload (<= 1: one copy, conv1a after it)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -294,9 +296,17 @@ static inline void prof_end(sfd2_ctx* c, cudaStream_t st) {
   cudaEventRecord(c->prof.back().b, st);
 }
 
+// A single host image arrives in row bands (sfd2_extract_host, n == 1): ev[b] fires on the copy stream when rows
+// [.., row_end[b]) are in HBM, and conv1a runs band by band behind the copy instead of after all of it.
+struct Bands {
+  int n = 0;
+  int row_end[8];
+  cudaEvent_t ev[8];
+};
+
 // one image through network + post-processing, all on `st`
 static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H, int W, const sfd2_extract_params* p,
-                       float* kpts, float* scores, float* desc, int32_t* count, cudaStream_t st) {
+                       float* kpts, float* scores, float* desc, int32_t* count, cudaStream_t st, const Bands* bands = nullptr) {
   const int prec = p->precision;
   const bool tc = prec != SFD2_PREC_FP32;
   const int split = (prec == SFD2_PREC_TC_EXACT || prec == SFD2_PREC_TC_MIXED) ? 3 : 1;
@@ -307,7 +317,39 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
   if (rc) return rc;
 #define RUN(x) do { rc = (x); if (rc) return rc; } while (0)
 #define RUNP(label, x) do { prof_begin(c, label, st); rc = (x); prof_end(c, st); if (rc) return rc; } while (0)
-  RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
+  // the first layers can run band by band behind a banded upload: {layer, input, output, stride, output rows done}
+  struct BandLayer { const char* name; int in, out, stride, done; };
+  BandLayer bl[3] = {{"conv1b", A1A, A1B, 2, 0}, {"conv2a", A1B, A2A, 1, 0}, {"conv2b", A2A, A2B, 2, 0}};
+  int nbl = 0;               // layers of bl[] completed inside the band loop
+  if (bands && bands->n > 0) {
+    const bool by_band = conv1a_bands_ok(tc ? split : 0);
+    if (by_band) nbl = std::max(0, std::min(g_band_layers, 3));
+    int y0 = 0;
+    for (int b = 0; b < bands->n; ++b) {
+      if (cudaStreamWaitEvent(st, bands->ev[b], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent(band %d) failed", b); return SFD2_ERR_CUDA; }
+      // output row y reads input rows y-1 .. y+1: with rows < row_end[b] uploaded, rows < row_end[b] - 1 can be computed
+      const int y1 = (b == bands->n - 1) ? H : bands->row_end[b] - 1;
+      if (by_band && y1 > y0) {
+        RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], split, w.nimg, w.map_1a, c->num_sms, st, y0, y1));
+        y0 = y1;
+        // the layers behind it follow as far as their inputs reach: a 3x3 output row y reads input rows s*y-1 .. s*y+1
+        int in_done = y1, in_h = H;
+        for (int l = 0; l < nbl; ++l) {
+          const int out_h = A[bl[l].out].H;
+          const int avail = in_done >= in_h ? out_h : (bl[l].stride == 2 ? (in_done >= 2 ? (in_done - 2) / 2 + 1 : 0) : std::max(in_done - 1, 0));
+          prof_begin(c, (std::string("tc_conv:") + bl[l].name).c_str(), st);
+          rc = launch_conv_tc(A[bl[l].in], c->L(bl[l].name), A[bl[l].out], nullptr, nullptr, split, c->num_sms, st, 0, nullptr, nullptr,
+                              &bl[l].done, avail);
+          prof_end(c, st);
+          if (rc) return rc;
+          in_done = bl[l].done; in_h = out_h;
+        }
+      }
+    }
+    if (!by_band) RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
+  } else {
+    RUNP("conv1a", launch_conv1a(img, img_dtype, H, W, c->L("conv1a"), A[A1A], tc ? split : 0, w.nimg, tc ? w.map_1a : nullptr, c->num_sms, st));
+  }
   // ConvSta rides in the epilogue of the layer that produces out4 (tcgen05 modes)
   const bool fuse_sta = tc && p->use_stability && g_fuse_sta;
   // single-pass descriptor head (`mixed`, `fast`): evaluate it after selection, only where descriptors are sampled
@@ -326,9 +368,9 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
     prof_end(c, st);
     return r;
   };
-  RUN(conv("conv1b", A1A, A1B, -1));
-  RUN(conv("conv2a", A1B, A2A, -1));
-  RUN(conv("conv2b", A2A, A2B, -1));
+  if (nbl < 1) RUN(conv("conv1b", A1A, A1B, -1));
+  if (nbl < 2) RUN(conv("conv2a", A1B, A2A, -1));
+  if (nbl < 3) RUN(conv("conv2b", A2A, A2B, -1));
   RUN(conv("conv3a", A2B, A3A, -1));
   RUN(conv("conv3b", A3A, A3B, -1));
   RUN(conv("rb0c1", A3B, T1, -1)); RUN(conv("rb0c2", T1, T2, -1)); RUN(conv("rb0c3", T2, BA, A3B));
@@ -397,6 +439,8 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_MULTICAST")) g_tc_multicast = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_PDL")) g_tc_pdl = atoi(e) != 0;
   if (const char* e = getenv("SFD2_SPARSE_DESC")) g_sparse_desc = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_HOST_BANDS")) g_host_bands = atoi(e);
+  if (const char* e = getenv("SFD2_BAND_LAYERS")) g_band_layers = atoi(e);
   if (const char* e = getenv("SFD2_TC_HALO")) g_tc_halo = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_NSPLIT")) g_tc_nsplit = atoi(e) != 0;
   if (const char* e = getenv("SFD2_CONV1A_MMA")) g_conv1a_mma = atoi(e) != 0;
@@ -468,7 +512,8 @@ SFD2_API int sfd2_destroy(sfd2_ctx* c) {
 
 // `ready`: optional per-image events (recorded on another stream when that image's bytes are in HBM)
 static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int h, int w, const sfd2_extract_params* p,
-                         float* kpts, float* scores, float* desc, int32_t* counts, void* stream, const cudaEvent_t* ready) {
+                         float* kpts, float* scores, float* desc, int32_t* counts, void* stream, const cudaEvent_t* ready,
+                         const Bands* bands = nullptr) {
   SFD2_CHECK(c && img && kpts && scores && desc && counts, SFD2_ERR_ARG, "sfd2_extract_dev: NULL argument");
   SFD2_CHECK(!c->layers.empty(), SFD2_ERR_WEIGHTS, "this context was created without network weights (matcher only)");
   int rc = check_params(p, n, h, w);
@@ -505,7 +550,7 @@ static int extract_batch(sfd2_ctx* c, const void* img, int img_dtype, int n, int
     if (ready && cudaStreamWaitEvent(si, ready[i], 0) != cudaSuccess) { set_error("cudaStreamWaitEvent(image %d) failed", i); rc = SFD2_ERR_CUDA; break; }
     rc = extract_one(c, c->ws[k], static_cast<const uint8_t*>(img) + i * img_stride, img_dtype, h, w, p,
                      kpts + (size_t)i * p->topk * 2, scores + (size_t)i * p->topk,
-                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, si);
+                     desc + (size_t)i * p->topk * SFD2_DESC_DIM, counts + i, si, n == 1 ? bands : nullptr);
   }
   // join the internal streams to the caller's stream also when an image failed: whatever was launched must
   // be ordered before the caller's next work (and before the workspaces are reused)
@@ -548,7 +593,40 @@ SFD2_API int sfd2_extract_host(sfd2_ctx* c, const void* img, int img_dtype, int 
     c->out_cap = rows;
   }
   cudaStream_t st = c->stream;
-  if (n == 1) {
+  if (n == 1 && img_bytes >= (4u << 20) && h >= 64 && g_host_bands > 1) {
+    // one large image: the upload goes out in row bands on the copy stream and conv1a follows it band by band, so only
+    // the last band's share of conv1a is left on the critical path behind the 23 MB copy (1600 x 1200 float32)
+    if (!c->copy_stream) SFD2_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    Bands bands;
+    bands.n = std::min(g_host_bands, 8);
+    while ((int)c->img_ready.size() < bands.n) {
+      cudaEvent_t e = nullptr;
+      SFD2_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->img_ready.push_back(e);
+    }
+    SFD2_CUDA(cudaEventRecord(c->img_ready[0], st));               // previous users of img_dev on st are done
+    SFD2_CUDA(cudaStreamWaitEvent(c->copy_stream, c->img_ready[0], 0));
+    const uint8_t* src = static_cast<const uint8_t*>(img);
+    uint8_t* dst = static_cast<uint8_t*>(c->img_dev);
+    int r0 = 0;
+    for (int b = 0; b < bands.n; ++b) {
+      const int r1 = (int)((long long)h * (b + 1) / bands.n);
+      if (img_dtype == SFD2_IMG_F32_NCHW) {
+        // the band's rows of the three channel planes: one strided copy (3 "rows" of band bytes, pitch = one plane)
+        const size_t off = (size_t)r0 * w * sizeof(float), plane = (size_t)h * w * sizeof(float);
+        SFD2_CUDA(cudaMemcpy2DAsync(dst + off, plane, src + off, plane, (size_t)(r1 - r0) * w * sizeof(float), 3,
+                                    cudaMemcpyHostToDevice, c->copy_stream));
+      } else {
+        const size_t off = (size_t)r0 * w * 3;
+        SFD2_CUDA(cudaMemcpyAsync(dst + off, src + off, (size_t)(r1 - r0) * w * 3, cudaMemcpyHostToDevice, c->copy_stream));
+      }
+      SFD2_CUDA(cudaEventRecord(c->img_ready[b], c->copy_stream));
+      bands.row_end[b] = r1;
+      bands.ev[b] = c->img_ready[b];
+      r0 = r1;
+    }
+    rc = extract_batch(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st, nullptr, &bands);
+  } else if (n == 1) {
     SFD2_CUDA(cudaMemcpyAsync(c->img_dev, img, img_bytes, cudaMemcpyHostToDevice, st));
     rc = extract_batch(c, c->img_dev, img_dtype, n, h, w, p, c->kp_dev, c->sc_dev, c->de_dev, c->cnt_dev, st, nullptr);
   } else {

@@ -73,12 +73,14 @@ struct TcConvLaunch;  // tc_conv.cu
 
 // ---- kernels' host-side launchers (each returns a sfd2_status) -------------------
 // simt_conv.cu
+// [y_begin, y_end): output rows of this launch (y_end < 0 = H); row bands need the tcgen05 kernel (conv1a_bands_ok)
 int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out, float4* nimg,
-                  const CUtensorMap* tm1a, int num_sms, cudaStream_t st);
+                  const CUtensorMap* tm1a, int num_sms, cudaStream_t st, int y_begin = 0, int y_end = -1);
+bool conv1a_bands_ok(int tc_out);
 // tc_conv1a.cu
 int conv1a_mma_encode(Layer& L);
 int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
-                      int num_sms, cudaStream_t st);
+                      int num_sms, cudaStream_t st, int y_begin = 0, int y_end = -1);
 int launch_conv_simt(const Act& in, const Layer& L, Act out, const Act* res, cudaStream_t st);
 // tc_in: 0 = fp32 input, 1 = fp16 hi+lo, 2 = fp16 hi only
 int launch_sta(const Act& in, int tc_in, const Layer& L, float* logits, cudaStream_t st);
@@ -91,8 +93,11 @@ int tc_make_act_maps(const Act& t, const __half* base, CUtensorMap* s1, CUtensor
 int tc_make_store_map(CUtensorMap* tm, const void* base, int C, int W, int H, int Wp, int is_f32, int box_w);
 // epi_fn (fp32 outputs only): 0 raw, 1 L2-normalised channels, 2 exp-normalised (softmax-with-eps) channels 0..63
 // sta / sta_out: fuse ConvSta (1x1 256 -> 3) on this layer's output into the epilogue (fp16-plane outputs only)
+// rows_done / rows_avail (row-band launches behind a banded upload): compute only the whole TILE rows inside output rows
+// [*rows_done, rows_avail) - up to the last row when rows_avail >= out.H - and advance *rows_done; nothing to do = no launch
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st, int epi_fn = 0, const Layer* sta = nullptr, float* sta_out = nullptr);
+                   int num_sms, cudaStream_t st, int epi_fn = 0, const Layer* sta = nullptr, float* sta_out = nullptr,
+                   int* rows_done = nullptr, int rows_avail = 0);
 // tc_desc_sparse.cu
 int launch_desc_sparse(const Act& in, const Layer& L, int H, int W, const float* kpts, const int32_t* count, int topk,
                        float* rows, float* desc_out, cudaStream_t st);

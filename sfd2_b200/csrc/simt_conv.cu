@@ -208,12 +208,15 @@ int g_conv1a_mma = 1;   // SFD2_CONV1A_MMA=0: keep conv1a on the CUDA cores in t
 // tm1a: store maps of the conv1a output (tcgen05 modes only): [hi, lo] with box {64 ch, 256 px, 1 row} for the
 // CUDA-core kernel, then [hi, lo] with box {64 ch, 128 px, 1 row} for the tensor-core kernel.
 // tc_out: 0 = fp32 output (FP32 mode), else the split of the tcgen05 mode (1 or 3).
+bool conv1a_bands_ok(int tc_out) { return tc_out && g_conv1a_mma; }
+
 int launch_conv1a(const void* img, int img_dtype, int H, int W, const Layer& L, Act out, int tc_out, float4* nimg,
-                  const CUtensorMap* tm1a, int num_sms, cudaStream_t st) {
+                  const CUtensorMap* tm1a, int num_sms, cudaStream_t st, int y_begin, int y_end) {
   SFD2_CHECK(L.cin == 3 && L.cout == 64 && L.k == 3, SFD2_ERR_WEIGHTS, "conv1a: unexpected layer shape");
   SFD2_CHECK(img_dtype == SFD2_IMG_F32_NCHW || img_dtype == SFD2_IMG_U8_NHWC, SFD2_ERR_ARG, "unknown image dtype %d", img_dtype);
   // tcgen05 modes: one kernel normalises, builds the im2col operand and runs the MMAs (tc_conv1a.cu)
-  if (tc_out && g_conv1a_mma) return launch_conv1a_mma(img, img_dtype, H, W, L, tm1a + 2, tc_out, num_sms, st);
+  if (tc_out && g_conv1a_mma) return launch_conv1a_mma(img, img_dtype, H, W, L, tm1a + 2, tc_out, num_sms, st, y_begin, y_end);
+  SFD2_CHECK(y_begin == 0 && (y_end < 0 || y_end == H), SFD2_ERR_ARG, "conv1a: row bands need the tcgen05 kernel");
   if (img_dtype == SFD2_IMG_F32_NCHW) norm_kernel<SFD2_IMG_F32_NCHW><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
   else norm_kernel<SFD2_IMG_U8_NHWC><<<cdiv(H * W, 256), 256, 0, st>>>(img, H, W, nimg);
   // L.w_simt is [tap][ci][cout_pad = 64] fp32 = exactly the [27][64] table the kernels stage in smem

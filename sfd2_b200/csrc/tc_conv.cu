@@ -48,7 +48,8 @@ constexpr int TC_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int TC_EPI_WARPS = 8;
 
 struct TcConvArgs {
-  int Ho, Wo, tiles_x, num_tiles;
+  int Ho, Wo, tiles_x, num_tiles;   // this launch covers tiles [tile_begin, num_tiles) (row-major over the tile grid)
+  int tile_begin, oob_tile;         // oob_tile: a tile index below the image (all padding), for the odd tile of a cluster
   int taps, stride, kchunks, diag;
   int n_mma, acc_cols, tmem_cols, cout, relu, split;
   int nsplit;      // halo mode: the output channels are processed in nsplit passes of n_mma channels each, so that
@@ -169,8 +170,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int v = cl + it * ncl;
     const int tp = (a.nsplit == 2) ? (v >> 1) : v;
     nh = (a.nsplit == 2) ? (v & 1) : 0;
-    tile = tp * a.mc + (int)crank;
-    return tp * a.mc < a.num_tiles;
+    tile = a.tile_begin + tp * a.mc + (int)crank;
+    const bool ok = a.tile_begin + tp * a.mc < a.num_tiles;
+    if (tile >= a.num_tiles) tile = a.oob_tile;
+    return ok;
   };
 
   if (warp == 0) {
@@ -808,7 +811,7 @@ int g_tc_halo = 1;        // SFD2_TC_HALO=0 falls back to per-tap A loads for th
 
 // out_f32_map: NULL for fp16 hi/lo outputs, else two maps {16x2 boxes, 8x4 boxes} of the fp32 output
 int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const CUtensorMap* out_f32_map, int split,
-                   int num_sms, cudaStream_t st, int epi_fn, const Layer* sta, float* sta_out) {
+                   int num_sms, cudaStream_t st, int epi_fn, const Layer* sta, float* sta_out, int* rows_done, int rows_avail) {
   SFD2_CHECK(in.tm != nullptr && in.hi != nullptr, SFD2_ERR_ARG, "conv_tc(%s): input has no tensor maps", L.name.c_str());
   SFD2_CHECK(in.C == L.cin && in.C % 64 == 0, SFD2_ERR_ARG, "conv_tc(%s): cin %d", L.name.c_str(), in.C);
   SFD2_CHECK(split == 1 || split == 3, SFD2_ERR_ARG, "conv_tc: split must be 1 or 3");
@@ -826,6 +829,17 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.epi_rows = a.halo ? 4 : 2;
   a.tiles_x = cdiv(out.W, a.tile_w);
   a.num_tiles = a.tiles_x * cdiv(out.H, a.tile_h);
+  a.oob_tile = a.num_tiles;
+  if (rows_done) {
+    SFD2_CHECK(*rows_done % a.tile_h == 0 && !sta_out, SFD2_ERR_ARG, "conv_tc(%s): bad row band", L.name.c_str());
+    const int tr0 = *rows_done / a.tile_h;
+    const int tr1 = rows_avail >= out.H ? cdiv(out.H, a.tile_h) : rows_avail / a.tile_h;
+    if (tr1 <= tr0) return SFD2_OK;
+    a.tile_begin = tr0 * a.tiles_x;
+    a.num_tiles = tr1 * a.tiles_x;
+    *rows_done = tr1 * a.tile_h;
+  }
+  const int n_range = a.num_tiles - a.tile_begin;
   a.taps = L.k * L.k; a.stride = L.stride; a.diag = diag ? 1 : 0;
   a.kchunks = L.cin / 64;
   a.tap_rows = L.cout_tc;
@@ -912,7 +926,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
-  a.mc = (g_tc_multicast && a.num_tiles >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
+  a.mc = (g_tc_multicast && n_range >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
   {
     static const int nob = getenv("SFD2_TC_DEBUG_NOB") ? atoi(getenv("SFD2_TC_DEBUG_NOB")) : 0;
     a.dbg_nob = (nob == 1 && a.cat) || nob == 2 ? 1 : 0;     // 1: grouped layers only, 2: every halo-mode layer
@@ -922,10 +936,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     if (nob == 16) a.dbg_nob = 8;
     if (nob == 32) a.dbg_nob = 16 | 8;                        // 32: null epilogue - accumulators are handed back untouched (timing only)                             // 16: residual tiles are not loaded (timing only)                              // 4: epilogue does not wait for its TMA stores to drain (RACY, timing only)
   }
-  int grid = a.num_tiles < num_sms ? a.num_tiles : num_sms;
+  int grid = n_range < num_sms ? n_range : num_sms;
   if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
   if (a.mc > 1 && grid > num_sms) grid -= 2;
-  a.iters = cdiv(cdiv(a.num_tiles, a.mc) * a.nsplit, grid / a.mc);   // cluster-units per cluster (see `unit` in the kernel)
+  a.iters = cdiv(cdiv(n_range, a.mc) * a.nsplit, grid / a.mc);   // cluster-units per cluster (see `unit` in the kernel)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(TC_THREADS);

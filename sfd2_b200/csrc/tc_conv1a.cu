@@ -36,6 +36,7 @@ constexpr int C1M_PITCH = 132;                 // words per (row slot, channel)
 struct Conv1aMmaArgs {
   int H, W, split, img_dtype;
   int rows_per_block;      // output rows a block walks through
+  int y_begin, y_end;      // output rows of this launch (a row band of the image; the whole image = [0, H))
   const void* img;         // raw image: f32 NCHW in [0,1] or u8 NHWC
   const __half* w_hi;      // [64 co][64 k] fp16, k = tap*3 + c (27 used)
   const __half* w_lo;
@@ -75,7 +76,7 @@ conv1a_mma_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_consta
   const uint32_t idesc = make_idesc_f16(128, 64);
   const int segs_x = (a.W + C1M_SEG - 1) / C1M_SEG;
   const int x0 = ((int)blockIdx.x % segs_x) * C1M_SEG;
-  const int ya = ((int)blockIdx.x / segs_x) * a.rows_per_block, yb = min(ya + a.rows_per_block, a.H);
+  const int ya = a.y_begin + ((int)blockIdx.x / segs_x) * a.rows_per_block, yb = min(ya + a.rows_per_block, a.y_end);
   const size_t plane = (size_t)a.H * a.W;
   uint32_t phase = 0;
   const int r = tid;                                        // pixel of the segment = A row = TMEM lane
@@ -238,14 +239,17 @@ int conv1a_mma_encode(Layer& L) {
 
 // tm1a: [hi, lo] store maps of the conv1a output with box {64 ch, 128 px, 1 row}
 int launch_conv1a_mma(const void* img, int img_dtype, int H, int W, const Layer& L, const CUtensorMap* tm1a, int split,
-                      int num_sms, cudaStream_t st) {
+                      int num_sms, cudaStream_t st, int y_begin, int y_end) {
   SFD2_CHECK(L.w_hi && L.w_lo && tm1a, SFD2_ERR_ARG, "conv1a_mma: weights / store maps missing");
+  if (y_end < 0) y_end = H;
+  SFD2_CHECK(0 <= y_begin && y_begin < y_end && y_end <= H, SFD2_ERR_ARG, "conv1a_mma: bad row band [%d, %d)", y_begin, y_end);
   // one wave of 4 resident blocks per SM: column strips x row ranges
   const int segs_x = cdiv(W, C1M_SEG);
-  int rows_per_block = cdiv(H * segs_x, 4 * num_sms);
-  if (rows_per_block < 4) rows_per_block = std::min(4, H);   // the two extra rows a block loads amortise over its range
-  const int blocks = segs_x * cdiv(H, rows_per_block);
-  Conv1aMmaArgs a{H, W, split, img_dtype, rows_per_block, img, L.w_hi, L.w_lo, L.b_dev};
+  const int band = y_end - y_begin;
+  int rows_per_block = cdiv(band * segs_x, 4 * num_sms);
+  if (rows_per_block < 4) rows_per_block = std::min(4, band);   // the two extra rows a block loads amortise over its range
+  const int blocks = segs_x * cdiv(band, rows_per_block);
+  Conv1aMmaArgs a{H, W, split, img_dtype, rows_per_block, y_begin, y_end, img, L.w_hi, L.w_lo, L.b_dev};
   const int smem = 1024 + 49152 + (9 * C1M_PITCH + 64) * 4 + 64;
   SFD2_CUDA(cudaFuncSetAttribute(conv1a_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   // per device: set on every launch (cheap)
   conv1a_mma_kernel<<<blocks, 128, smem, st>>>(tm1a[0], tm1a[1], a);

@@ -777,3 +777,25 @@ def test_sparse_descriptor_head_equals_dense(golden, monkeypatch, prec):
     od, os_ = exd(batch), exs(batch)
     for k in od:
         assert torch.equal(od[k], os_[k]), k
+
+
+def test_single_host_image_band_upload_equals_device_path():
+    """sfd2_extract_host with one large image uploads it in row bands and runs conv1a band by band behind the copy
+    (api.cu: Bands).  Results must equal the device-input path bit for bit, for float32 NCHW and uint8 NHWC, odd heights."""
+    from gpu_util import WEIGHTS
+    from sfd2_b200 import get_model, extract_resnet_return, Extractor
+    from sfd2_b200.synth import synth_image_u8
+    model, _ = get_model("ressegnetv2", WEIGHTS, use_stability=True, precision="mixed")
+    model.cuda()
+    for (H, W) in ((1063, 1600), (1200, 1600), (771, 1029)):
+        u8 = synth_image_u8(70 + H, H, W)
+        f = torch.from_numpy(np.ascontiguousarray(u8.transpose(2, 0, 1))[None].astype(np.float32) / 255.0)
+        a = extract_resnet_return(model, f.pin_memory(), topK=2000, conf_th=0.001)          # host path: banded
+        b = extract_resnet_return(model, f.cuda(), topK=2000, conf_th=0.001)                # device path: one conv1a launch
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (H, W, k)
+        ex = Extractor(WEIGHTS, precision="mixed", topk=2000)
+        hu = ex.extract_host(torch.from_numpy(u8[None]).pin_memory())
+        du = ex(torch.from_numpy(u8[None]).cuda())
+        for k in hu:
+            assert np.array_equal(hu[k], du[k].cpu().numpy()), (H, W, k, "u8")
