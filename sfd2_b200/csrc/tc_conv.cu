@@ -82,6 +82,13 @@ struct TcConvArgs {
   int tile_w, tile_h, epi_rows, ring_bytes;
   int dbg_nob;     // experiment: skip weight reloads (timing only)
   int mc;          // cluster size (1 or 2): with 2, each CTA loads half of every weight slab and multicasts it
+  int cg2;         // per-tap ring only: the cluster is a CTA PAIR running tcgen05.mma.cta_group::2 (M = 256 = both CTAs' tiles):
+                   // each CTA keeps only ITS half of every weight slab (no multicast), so a stage is A + B/2 - a third less
+                   // shared-memory fill per tile for the 256-wide 1x1 layers and three stages instead of two.  The even CTA
+                   // issues for both; loads of both CTAs complete on its `full` barriers, its commits arrive on both CTAs'
+                   // `empty` / `tfull`, and both CTAs' epilogue warps arrive on its `tempty`
+  int stiles;      // staging tiles per epilogue warp (1; CTA-pair layers have the room for 2, or 3 with a residual: the TMA
+                   // store of chunk i drains - and the residual of chunk i+1 arrives - while chunk i+1 is converted)
   int iters;       // tiles per CTA (same for every CTA so cluster peers stay in lock step)
   const float* bias;
   int out_mode;    // 0: fp16 hi plane only, 1: fp16 hi + lo planes, 2: fp32
@@ -109,6 +116,9 @@ constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-co
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
 constexpr int TC_EXCH_BYTES = 2 * TC_EPI_WARPS * 32 * 4;   // head epilogues: partial-sum exchange between paired warps
 
+// PAIR: the instantiation that contains the cta_group::2 instructions - such a kernel can only be launched as clusters of two
+// (a cluster-of-one launch fails with "cluster misconfiguration"), so the single-CTA / multicast path is its own instantiation
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -121,8 +131,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + (size_t)a.ring_bytes;                        // 1024-aligned
-  float* sbias = reinterpret_cast<float*>(staging + TC_STAGING_BYTES);
-  uint64_t* full = reinterpret_cast<uint64_t*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES);
+  const int staging_bytes = a.stiles * TC_STAGING_BYTES;
+  float* sbias = reinterpret_cast<float*>(staging + staging_bytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(staging + staging_bytes + TC_BIAS_BYTES);
   uint64_t* empty = full + TC_MAX_STAGES;
   uint64_t* tfull = empty + TC_MAX_STAGES;
   uint64_t* tempty = tfull + 2;
@@ -130,7 +141,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* fullA = resbar + 8;                                          // halo mode: A-tile ring
   uint64_t* emptyA = fullA + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyA + 4);
-  float* exch = reinterpret_cast<float*>(staging + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
+  uint64_t* resbar_x = emptyA + 5;                                       // [8 warps][2]: residual barriers of staging tiles 1, 2
+  float* exch = reinterpret_cast<float*>(staging + staging_bytes + TC_BIAS_BYTES + TC_BAR_BYTES);   // heads only: [2][8 warps][32]
 
   // The warp index goes through a shuffle so that the compiler KNOWS it is warp-uniform: the producer and MMA-issuer
   // loops below are run by the whole warp (ring indices, phases, descriptors stay in uniform registers) and only the
@@ -144,13 +156,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (a.split == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (uint32_t)a.mc); }
+    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (PAIR && a.cg2) ? 1u : (uint32_t)a.mc); }
     for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], TC_EPI_WARPS); }
-    for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(&resbar[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR && a.cg2) ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int i = 0; i < TC_EPI_WARPS; ++i) { mbar_init(&resbar[i], 1); mbar_init(&resbar_x[2 * i], 1); mbar_init(&resbar_x[2 * i + 1], 1); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
+  if (warp == 2) { if ((PAIR && a.cg2)) tmem_alloc_cg2(tmem_slot, (uint32_t)a.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols); }
   for (int i = threadIdx.x; i < (int)(TC_BIAS_BYTES / sizeof(float)); i += blockDim.x)
     sbias[i] = (i < ((a.cout + 31) / 32) * 32) ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
@@ -238,6 +250,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
             uint8_t* sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
             const int c0 = kc * 64;
+            if ((PAIR && a.cg2)) {
+              if (elect_one()) {
+                // both CTAs' bytes complete on the leader's barrier (its own arrival is this expect_tx)
+                if (crank == 0) mbar_expect_tx(&full[stage], 2u * (uint32_t)a.stage_bytes);
+                if (a.stride == 1) {
+                  const int cx = x0 + kx - 1, cy = y0 + ky - 1;
+                  tma_load_3d_cg2(sa, &tmA_hi, &full[stage], c0, cx, cy);
+                  if (a.split == 3) tma_load_3d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, cx, cy);
+                } else {
+                  const int xp = (kx + 1) & 1, yp = (ky + 1) & 1;
+                  const int cx = x0 + (kx - 1 - xp) / 2, cy = y0 + (ky - 1 - yp) / 2;
+                  tma_load_5d_cg2(sa, &tmA_hi, &full[stage], c0, xp, cx, yp, cy);
+                  if (a.split == 3) tma_load_5d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
+                }
+                const int brow2 = tap * a.tap_rows + (int)crank * (a.n_mma / 2);   // my half of the slab's rows, kept here
+                tma_load_2d_cg2(sb, &tmB_hi, &full[stage], c0, brow2);
+                if (a.split == 3) tma_load_2d_cg2(sb + a.b_bytes, &tmB_lo, &full[stage], c0, brow2);
+              }
+              __syncwarp();
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             if (elect_one()) {
             mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
             if (a.stride == 1) {
@@ -354,7 +388,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
     } else {
-      const uint32_t idesc = make_idesc_f16(128, a.n_mma);
+      const uint32_t idesc = make_idesc_f16((PAIR && a.cg2) ? 256 : 128, a.n_mma);
       const uint32_t idesc_ncat = make_idesc_f16(128, 2 * a.n_mma);
       int stage = 0;
       uint32_t phase = 0;
@@ -362,7 +396,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
         int tile, nh;
-        if (!unit(it, tile, nh)) break;
+        if (!unit(it, tile, nh) || ((PAIR && a.cg2) && crank != 0)) break;     // CTA pair: the even CTA issues for both
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
@@ -396,17 +430,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const bool to_corr = a.corr && pass > 0;
             const uint32_t d = to_corr ? dcol + (uint32_t)a.acc_cols : dcol;
             const int first_pass = to_corr ? 1 : 0;
+            if ((PAIR && a.cg2)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_f16_cg2(d, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (first && pass == first_pass && k == 0) ? 0u : 1u);
+            } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16(d, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (first && pass == first_pass && k == 0) ? 0u : 1u);
+            }
           }
-          // smem slot free once these MMAs have read it (in both CTAs when the slab is multicast)
-          if (a.mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
+          // smem slot free once these MMAs have read it (in both CTAs when the slab is multicast / the MMA spans the pair)
+          if ((PAIR && a.cg2)) umma_commit_cg2(&empty[stage], cmask);
+          else if (a.mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
           }
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[buf]);   // accumulator complete -> epilogue
+        if (elect_one()) { if ((PAIR && a.cg2)) umma_commit_cg2(&tfull[buf], cmask); else umma_commit(&tfull[buf]); }   // accumulator complete -> epilogue
         __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
@@ -422,8 +463,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int ew = warp - 2;
     const int q = warp & 3;
     const int h = ew >> 2;
-    uint8_t* st = staging + ew * 4096;
+    const int nst = a.stiles;
+    uint8_t* st = staging + ew * nst * 4096;     // this warp's staging tile(s); `st` = the tile of the current chunk
+    uint8_t* const st0 = st;
+    auto wres_of = [&](int ti) -> uint64_t* { return ti == 0 ? resbar + ew : resbar_x + 2 * ew + (ti - 1); };
     uint64_t* wres = resbar + ew;
+    int ti = 0;                                  // staging tile of the current chunk (rotates when nst > 1)
+    uint32_t rph = 0u;                           // residual-barrier phase per tile (bit ti)
     int buf = 0;
     uint32_t bphase = 0;
     const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
@@ -436,16 +482,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       y0 = (tile / a.tiles_x) * a.tile_h + a.epi_rows * q;
       return ok;
     };
-    auto issue_res = [&](int it, int ch) {        // lane 0 only (layers with a residual run a single channel pass)
+    auto issue_res = [&](int it, int ch, int tdst) {  // lane 0 only (layers with a residual run a single channel pass)
       int x0, y0, nh;
       if (ch >= nstore || it >= a.iters || !tile_xy(it, x0, y0, nh)) return;
-      if (a.dbg_nob & 8) { mbar_arrive(wres); return; }
-      mbar_expect_tx(wres, a.has_res == 2 ? 4096u : 2048u);
-      tma_load_3d(st, &tmR_hi, wres, ch * 32, x0, y0);
-      if (a.has_res == 2) tma_load_3d(st + 2048, &tmR_lo, wres, ch * 32, x0, y0);
+      uint64_t* wr = wres_of(tdst);
+      uint8_t* sd = st0 + tdst * 4096;
+      if (a.dbg_nob & 8) { mbar_arrive(wr); return; }
+      mbar_expect_tx(wr, a.has_res == 2 ? 4096u : 2048u);
+      tma_load_3d(sd, &tmR_hi, wr, ch * 32, x0, y0);
+      if (a.has_res == 2) tma_load_3d(sd + 2048, &tmR_lo, wr, ch * 32, x0, y0);
     };
-    uint32_t rphase = 0u;
-    if (a.has_res && lane == 0) issue_res(0, h);  // the residual of this warp's first chunk
+    if (a.has_res && lane == 0) issue_res(0, h, 0);  // the residual of this warp's first chunk
     for (int it = 0; it < a.iters; ++it) {
       int x0, y0, nh;
       if (!tile_xy(it, x0, y0, nh)) break;
@@ -486,7 +533,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[buf]);   // this warp's share of the accumulator is in registers
+        if (lane == 0) { if ((PAIR && a.cg2)) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }   // this warp's share of the accumulator is in registers
         float* ex = exch + ((it & 1) * TC_EPI_WARPS + ew) * 32;    // double-buffered by tile parity
         ex[lane] = part;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this lane quarter
@@ -530,9 +577,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const uint32_t coff = (uint32_t)a.acc_cols;
         uint32_t v[32];
         float x[32];
+        st = st0 + ti * 4096;
+        wres = wres_of(ti);
+        if (a.has_res && nst == 3 && lane == 0) {
+          // three tiles: the store of the previous chunk may still be draining, the one before it has been read - its
+          // tile takes the residual of the NEXT chunk now, a whole chunk ahead of its use
+          bulk_wait_read<1>();
+          if (ch + 2 < nstore) issue_res(it, ch + 2, (ti + 1) % 3); else issue_res(it + 1, h, (ti + 1) % 3);
+        }
         tmem_ld32(taddr + tcol, v);
-        if (!a.has_res) {                         // this warp's previous store must have finished reading the
-          if (lane == 0 && !(a.dbg_nob & 2)) bulk_wait_read<0>();     // staging tile (with a residual, issue_res waited already)
+        if (!a.has_res) {                         // the store that last used this tile must have finished reading it
+          if (lane == 0 && !(a.dbg_nob & 2)) { if (nst > 1) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // (with a residual, issue_res waited already)
           __syncwarp();
         }
         tmem_ld_wait();
@@ -560,8 +615,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         const int sw64 = (r >> 1) & 3;            // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,9)
         if (a.has_res) {
-          mbar_wait(wres, rphase);
-          rphase ^= 1u;
+          mbar_wait(wres, (rph >> ti) & 1u);
+          rph ^= 1u << ti;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 h = *reinterpret_cast<const uint4*>(st + r * 64 + ((g ^ sw64) << 4));
@@ -627,15 +682,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           }
           bulk_commit();
-          if (a.has_res) {                        // refill the tile with the residual of this warp's next chunk
+          if (a.has_res && nst != 3) {            // one tile: refill it with the residual of this warp's next chunk
             if (!(a.dbg_nob & 2)) bulk_wait_read<0>();
-            if (ch + 2 < nstore) issue_res(it, ch + 2); else issue_res(it + 1, h);
+            if (ch + 2 < nstore) issue_res(it, ch + 2, 0); else issue_res(it + 1, h, 0);
           }
         }
+        if (nst > 1 && ++ti == nst) ti = 0;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
+      if (lane == 0) { if ((PAIR && a.cg2)) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }
       if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       if (a.sta_out) {                            // (nsplit == 1 here) this lane's pixel: TMEM lane q*32 + r of the tile
         const int py = y0 + r / a.tile_w, px = x0 + r % a.tile_w;
@@ -650,12 +706,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   if (a.mc > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
-  if (warp == 2) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == 2) { if ((PAIR && a.cg2)) tmem_dealloc_cg2(tmem_base, (uint32_t)a.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------ host side
 int g_fuse_sta = 1;       // SFD2_FUSE_STA=0: run ConvSta as its own kernel (sta_kernel) instead of in rb2c3's epilogue
 int g_tc_multicast = 1;   // SFD2_TC_MULTICAST=0 in the environment disables the 2-CTA weight multicast
+int g_tc_stiles = 1;      // SFD2_TC_STILES=0: one staging tile per epilogue warp also in the CTA-pair layers
+int g_tc_cg2 = 2;         // SFD2_TC_CG2: 0 = no CTA-pair MMAs, 1 = the 1x1 layers, 2 = every per-tap-ring layer that qualifies
 int g_tc_pdl = 1;         // SFD2_TC_PDL=0: launch the conv layers without programmatic dependent launch
 
 PFN_encodeTiled get_encode_tiled() {
@@ -872,14 +930,20 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   while (tc < a.nbuf * a.buf_stride + over) tc <<= 1;
   a.tmem_cols = tc;
   a.cout = L.cout; a.relu = L.relu; a.split = split;
-  a.b_bytes = a.n_mma * 128;
+  // CTA pair (see TcConvArgs::cg2): per-tap-ring layers whose slab halves are whole swizzle atoms, enough tiles for a cluster
+  const bool can_mc = g_tc_multicast && n_range >= 2 && (a.n_mma / 2) % 8 == 0;
+  a.cg2 = (g_tc_cg2 && split == 3 && can_mc && !a.halo && !diag && !a.ncat && a.n_mma % 32 == 0 && (g_tc_cg2 > 1 || L.k == 1)) ? 1 : 0;
+  a.b_bytes = (a.cg2 ? a.n_mma / 2 : a.n_mma) * 128;
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;
   const bool fuse_sta = sta && sta_out;
   SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w.size() == 768),
              SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
   // alignment slack, staging, bias, barriers
-  const int smem_fixed = 1024 + TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
+  // CTA-pair 1x1 layers are bound by their epilogue, not by the operand ring: two 64 KB stages, and the shared memory the
+  // halved weight slabs free goes to extra staging tiles (TcConvArgs::stiles)
+  a.stiles = (a.cg2 && L.k == 1 && !out_f32_map && g_tc_stiles) ? (res ? 3 : 2) : 1;
+  const int smem_fixed = 1024 + a.stiles * TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   SFD2_CHECK(stages >= 2, SFD2_ERR_ARG, "conv_tc(%s): stage too large", L.name.c_str());
@@ -923,13 +987,14 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& r_hi = res ? res->tm_st[so] : o_hi;       // residual boxes have the epilogue warps' pixel shape
   const CUtensorMap& r_lo = res ? res->tm_st[so + 1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
-  SFD2_CUDA(cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = a.cg2 ? tc_conv_kernel<true> : tc_conv_kernel<false>;
+  SFD2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
-  a.mc = (g_tc_multicast && n_range >= 2 && (a.n_mma / 2) % 8 == 0) ? 2 : 1;
+  a.mc = can_mc ? 2 : 1;
   {
     static const int nob = getenv("SFD2_TC_DEBUG_NOB") ? atoi(getenv("SFD2_TC_DEBUG_NOB")) : 0;
-    a.dbg_nob = (nob == 1 && a.cat) || nob == 2 ? 1 : 0;     // 1: grouped layers only, 2: every halo-mode layer
+    a.dbg_nob = (nob == 1 && a.cat) || (nob == 2 && a.halo) ? 1 : 0;     // 1: grouped layers only, 2: every halo-mode layer
     if (a.dbg_nob) a.mc = 1;
     if (nob == 4) a.dbg_nob = 2;
     if (nob == 8) a.dbg_nob = 4;                              // 8: epilogue computes but issues no output stores (timing only)
@@ -963,7 +1028,18 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& wb_hi = a.cat ? (mi == 0 ? L.tm_w_cat : L.tm_w_cat_half)
                                    : (mi == 0 ? L.tm_w_hi : (mi == 1 ? L.tm_w_hi_half : L.tm_w_hi_quarter));
   const CUtensorMap& wb_lo = mi == 0 ? L.tm_w_lo : (mi == 1 ? L.tm_w_lo_half : L.tm_w_lo_quarter);
-  SFD2_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a, sw));
+  if (getenv("SFD2_DEBUG_LAUNCH"))
+    fprintf(stderr, "conv_tc %-8s out %dx%d halo %d tiles %d grid %d mc %d cg2 %d stiles %d stages %d/%d smem %zu iters %d nsplit %d\n", L.name.c_str(), out.H, out.W,
+            a.halo, n_range, grid, a.mc, a.cg2, a.stiles, a.stages, a.b_stages, smem, a.iters, a.nsplit);
+  {
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA[0], tmA[1], wb_hi, wb_lo, o_hi, o_lo, r_hi, r_lo, a, sw);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      set_error("conv_tc(%s): launch failed: %s (grid %d, cluster %d, pair %d, %zu B smem, %d tiles)", L.name.c_str(), cudaGetErrorString(e),
+                grid, a.mc, a.cg2, smem, n_range);
+      return SFD2_ERR_CUDA;
+    }
+  }
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
