@@ -203,9 +203,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
           if (elect_one()) {
+            if (PAIR && a.cg2) {    // both CTAs' halo tiles complete on the leader's barrier
+              if (crank == 0) mbar_expect_tx(&fullA[sa], 2u * (uint32_t)(planes * a.a_plane_bytes));
+              tma_load_3d_cg2(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+              if (planes == 2) tma_load_3d_cg2(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+            } else {
             mbar_expect_tx(&fullA[sa], (uint32_t)(planes * a.a_plane_bytes));
             tma_load_3d(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
             if (planes == 2) tma_load_3d(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
+            }
           }
           __syncwarp();
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
@@ -220,11 +226,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 if (a.dbg_nob && nb_loaded >= a.b_stages) {
                   mbar_arrive(&full[sb]);            // EXPERIMENT (SFD2_TC_DEBUG_NOB): no weight traffic after the first fill
                 } else {
-                mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
-                if (a.mc > 1) {
+                if (PAIR && a.cg2) {     // my half of the slab's rows stays here; the pair's MMA reads both halves
+                  if (crank == 0) mbar_expect_tx(&full[sb], 2u * (uint32_t)a.b_bytes);
+                  tma_load_2d_cg2(bs, tb, &full[sb], bcol, brow + (int)crank * (a.n_mma / 2));
+                } else if (a.mc > 1) {
+                  mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
                   const int ro = (int)crank * (a.n_mma / 2);
                   tma_load_2d_mc(bs + ro * 128, tb, &full[sb], bcol, brow + ro, cmask);
                 } else {
+                  mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
                   tma_load_2d(bs, tb, &full[sb], bcol, brow);
                 }
                 }
@@ -306,14 +316,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ------------------------------------------------------------------ MMA issuer
     // (whole warp runs the loops; tcgen05.mma / commit come from the one lane elect.sync picks - always the same)
     if (a.halo) {
-      const uint32_t idesc = make_idesc_f16(128, a.cat ? 16 : a.n_mma);
+      const bool pair = PAIR && a.cg2;
+      const uint32_t idesc = make_idesc_f16(pair ? 256 : 128, a.cat ? 16 : a.n_mma);
       const uint32_t idesc_cat = make_idesc_f16(128, 32);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
+        if (PAIR && a.cg2) umma_f16_cg2(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+      };
+      auto commit = [&](uint64_t* bar, bool both) {     // both: the barrier exists in both CTAs of a multicast / pair cluster
+        if (PAIR && a.cg2) umma_commit_cg2(bar, cmask);
+        else if (both && a.mc > 1) umma_commit_mc(bar, cmask);
+        else umma_commit(bar);
+      };
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
       int sa = 0, sb = 0, buf = 0;
       uint32_t pha = 0, phb = 0, bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
         int tile, nh;
-        if (!unit(it, tile, nh)) break;
+        if (!unit(it, tile, nh) || (pair && crank != 0)) break;      // CTA pair: the even CTA issues for both
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
@@ -355,13 +374,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma_f16(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, (first && k == 0) ? 0u : 1u);
+                mma(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), (first && k == 0) ? 0u : 1u);
               if (a.split == 3) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), idesc, (a.corr && first && k == 0) ? 0u : 1u);
+                  mma(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), (a.corr && first && k == 0) ? 0u : 1u);
               }
-              if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+              commit(&empty[sb], true);
             }
             __syncwarp();
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
@@ -372,18 +391,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_f16(ccol, desc_advance_k(da_hi, k), desc_advance_k(db, k), idesc, 1u);
-                if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+                  mma(ccol, desc_advance_k(da_hi, k), desc_advance_k(db, k), 1u);
+                commit(&empty[sb], true);
               }
               __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
             }
           }
-          if (elect_one()) umma_commit(&emptyA[sa]);   // halo tile free once all nine taps have read it
+          if (elect_one()) commit(&emptyA[sa], false);   // halo tile free once all nine taps have read it
           __syncwarp();
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
         }
-        if (elect_one()) umma_commit(&tfull[buf]);
+        if (elect_one()) commit(&tfull[buf], false);
         __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
@@ -932,7 +951,7 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   a.cout = L.cout; a.relu = L.relu; a.split = split;
   // CTA pair (see TcConvArgs::cg2): per-tap-ring layers whose slab halves are whole swizzle atoms, enough tiles for a cluster
   const bool can_mc = g_tc_multicast && n_range >= 2 && (a.n_mma / 2) % 8 == 0;
-  a.cg2 = (g_tc_cg2 && split == 3 && can_mc && !a.halo && !diag && !a.ncat && a.n_mma % 32 == 0 && (g_tc_cg2 > 1 || L.k == 1)) ? 1 : 0;
+  a.cg2 = (g_tc_cg2 && split == 3 && can_mc && (!a.halo || g_tc_cg2 > 2) && !diag && !a.ncat && a.n_mma % 32 == 0 && (g_tc_cg2 > 1 || L.k == 1)) ? 1 : 0;
   a.b_bytes = (a.cg2 ? a.n_mma / 2 : a.n_mma) * 128;
   a.stage_bytes = (TC_A_BYTES + a.b_bytes) * (split == 3 ? 2 : 1);
   const int smem_max = 227 * 1024;

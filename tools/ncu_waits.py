@@ -12,7 +12,11 @@ import collections, csv, io, re, subprocess, sys
 
 rep, first, count, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 names = sys.argv[5].split(",") if len(sys.argv) > 5 else []
-OFFS = [("0x8480", "full"), ("0x84e0", "empty"), ("0x8540", "tfull"), ("0x8550", "tempty"), ("0x85a0", "fullA"), ("0x85c0", "emptyA")]
+# offsets behind the staging tiles: 1, 2 or 3 tiles of 4 KB per epilogue warp (TcConvArgs::stiles) + 1152 bytes of bias
+REL = [(0x0, "full"), (0x60, "empty"), (0xc0, "tfull"), (0xd0, "tempty"), (0x120, "fullA"), (0x140, "emptyA")]
+BASES = [0x8480, 0x10480, 0x18480]
+OFFS = [(hex(BASES[0] + r), n) for r, n in REL]
+ALIAS = {hex(b + r): hex(BASES[0] + r) for b in BASES for r, _ in REL}
 lines = ["| # | layer | time us | " + " | ".join(n for _, n in OFFS) + " | reading |", "|---|---|---|" + "---|" * (len(OFFS) + 1)]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -26,9 +30,9 @@ for k in range(count):
     ai, ei = hdr.index("Source"), hdr.index("Instructions Executed")
     cnt = collections.Counter()
     for d in data:
-        m = re.search(r"TRYWAIT.*\+(0x8[0-9a-f]{3})\]", d[ai])
-        if m:
-            cnt[m.group(1)] += int(d[ei] or 0)
+        m = re.search(r"TRYWAIT.*\+(0x[0-9a-f]{4,5})\]", d[ai])
+        if m and m.group(1) in ALIAS:
+            cnt[ALIAS[m.group(1)]] += int(d[ei] or 0)
     c = {n: cnt[o] for o, n in OFFS}
     if c["tempty"] > 20 * 950:
         reading = "MMA issuer waits for a free accumulator: epilogue-bound"
