@@ -3,7 +3,7 @@
 # reference arm, the ncu launch list of the default bench command, ncu --set full captures of the extract path and of the
 # matcher, and SASS listings of the tensor-core kernels.  Everything lands in gpurun_out/<tag>_*.
 tag=${1:-final}
-KREGEX='regex:conv|nms|select|sample|heat|match|preprocess'
+KREGEX='regex:conv|nms|select|sample|heat|match|preprocess|desc'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${tag}_smi.txt 2>&1
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/${tag}_pytest.log
