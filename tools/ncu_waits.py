@@ -12,9 +12,9 @@ import collections, csv, io, re, subprocess, sys
 
 rep, first, count, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
 names = sys.argv[5].split(",") if len(sys.argv) > 5 else []
-# offsets behind the staging tiles: 1, 2 or 3 tiles of 4 KB per epilogue warp (TcConvArgs::stiles) + 1152 bytes of bias
+# offsets behind the staging tiles (1, 2 or 3 tiles of 4 KB per epilogue warp, TcConvArgs::stiles) + 1152 bytes of bias
 REL = [(0x0, "full"), (0x60, "empty"), (0xc0, "tfull"), (0xd0, "tempty"), (0x120, "fullA"), (0x140, "emptyA")]
-BASES = [0x8480, 0x10480, 0x18480]
+BASES = [0x8480, 0x480]      # captures before / after the staging size became a runtime value (the constant part is the 1152 bias bytes)
 OFFS = [(hex(BASES[0] + r), n) for r, n in REL]
 ALIAS = {hex(b + r): hex(BASES[0] + r) for b in BASES for r, _ in REL}
 lines = ["| # | layer | time us | " + " | ".join(n for _, n in OFFS) + " | reading |", "|---|---|---|" + "---|" * (len(OFFS) + 1)]
@@ -30,7 +30,7 @@ for k in range(count):
     ai, ei = hdr.index("Source"), hdr.index("Instructions Executed")
     cnt = collections.Counter()
     for d in data:
-        m = re.search(r"TRYWAIT.*\+(0x[0-9a-f]{4,5})\]", d[ai])
+        m = re.search(r"TRYWAIT.*\+(0x[0-9a-f]{3,5})\]", d[ai])
         if m and m.group(1) in ALIAS:
             cnt[ALIAS[m.group(1)]] += int(d[ei] or 0)
     c = {n: cnt[o] for o, n in OFFS}
