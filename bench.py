@@ -261,6 +261,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # torchrun exports OMP_NUM_THREADS=1; the host side of the plugin calls (float64 packing of the results) is threaded
+        # in a normal single-process run - give every rank its share of the host cores
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     B, K, Wm = args.batch, args.steps, args.warmup
     pool_n = max(args.pool, B)
