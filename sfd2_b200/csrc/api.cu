@@ -440,6 +440,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_PDL")) g_tc_pdl = atoi(e) != 0;
   if (const char* e = getenv("SFD2_TC_CG2")) g_tc_cg2 = atoi(e);
   if (const char* e = getenv("SFD2_TC_STILES")) g_tc_stiles = atoi(e);
+  if (const char* e = getenv("SFD2_TC_SLIM")) g_tc_slim = atoi(e) != 0;
   if (const char* e = getenv("SFD2_SPARSE_DESC")) g_sparse_desc = atoi(e) != 0;
   if (const char* e = getenv("SFD2_HOST_BANDS")) g_host_bands = atoi(e);
   if (const char* e = getenv("SFD2_BAND_LAYERS")) g_band_layers = atoi(e);

@@ -134,7 +134,7 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
-extern int g_sparse_desc, g_tc_stiles, g_tc_cg2, g_tc_pdl, g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_diagcat, g_tc_split1x1;
+extern int g_sparse_desc, g_tc_slim, g_tc_stiles, g_tc_cg2, g_tc_pdl, g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_diagcat, g_tc_split1x1;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 
 }  // namespace sfd2

@@ -116,9 +116,9 @@ constexpr int TC_BIAS_BYTES = 1024 + 128;       // up to 288 floats (256 + 32-co
 constexpr int TC_BAR_BYTES = 512;               // mbarriers + TMEM slot
 constexpr int TC_EXCH_BYTES = 2 * TC_EPI_WARPS * 32 * 4;   // head epilogues: partial-sum exchange between paired warps
 
-// PAIR: the instantiation that contains the cta_group::2 instructions - such a kernel can only be launched as clusters of two
+// PAIR: the instantiations that contain the cta_group::2 instructions - such a kernel can only be launched as clusters of two
 // (a cluster-of-one launch fails with "cluster misconfiguration"), so the single-CTA / multicast path is its own instantiation
-template <bool PAIR>
+template <bool PAIR, bool SLIM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -126,8 +126,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                const __grid_constant__ CUtensorMap tmR_hi, const __grid_constant__ CUtensorMap tmR_lo,
                const __grid_constant__ TcConvArgs a, const __grid_constant__ TcStaW sw) {
   pdl_launch_dependents();       // the next layer's prologue may overlap this layer's last wave (it waits below)
-  const uint32_t crank = (a.mc > 1) ? cluster_ctarank() : 0u;
-  const uint16_t cmask = (uint16_t)((1u << a.mc) - 1u);
+  // SLIM: the instantiation for the exact-mode 1x1 pair layers (6 of the 17 launches of an image, all epilogue-bound).  Its
+  // configuration is fixed at compile time, so the halo path, the grouped / head / fp32 epilogues and the single-CTA variants
+  // drop out: the generic kernel is ~5800 instructions and a quarter of the epilogue warps' stall samples in these layers
+  // were instruction-fetch misses (`no_inst`) on the branches around the variants they never take
+  const int k_halo = SLIM ? 0 : a.halo, k_taps = SLIM ? 1 : a.taps, k_stride = SLIM ? 1 : a.stride, k_split = SLIM ? 3 : a.split;
+  const int k_diag = SLIM ? 0 : a.diag, k_cat = SLIM ? 0 : a.cat, k_ncat = SLIM ? 0 : a.ncat, k_nsplit = SLIM ? 1 : a.nsplit;
+  const int k_corr = SLIM ? 0 : a.corr, k_epi_fn = SLIM ? 0 : a.epi_fn, k_out_mode = SLIM ? 1 : a.out_mode;
+  const int k_dbg_nob = SLIM ? 0 : a.dbg_nob, k_mc = SLIM ? 2 : a.mc;
+  const bool k_cg2 = SLIM ? true : (PAIR && a.cg2);
+  const uint32_t crank = (k_mc > 1) ? cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << k_mc) - 1u);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* staging = smem + (size_t)a.ring_bytes;                        // 1024-aligned
@@ -153,45 +162,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA_hi);
     prefetch_tmap(&tmB_hi);
-    if (a.split == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
+    if (k_split == 3) { prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB_lo); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], (PAIR && a.cg2) ? 1u : (uint32_t)a.mc); }
+    for (int i = 0; i < TC_MAX_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], k_cg2 ? 1u : (uint32_t)k_mc); }
     for (int i = 0; i < 4; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], (PAIR && a.cg2) ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], k_cg2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) { mbar_init(&resbar[i], 1); mbar_init(&resbar_x[2 * i], 1); mbar_init(&resbar_x[2 * i + 1], 1); }
     fence_barrier_init();
   }
-  if (warp == 2) { if ((PAIR && a.cg2)) tmem_alloc_cg2(tmem_slot, (uint32_t)a.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols); }
+  if (warp == 2) { if (k_cg2) tmem_alloc_cg2(tmem_slot, (uint32_t)a.tmem_cols); else tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols); }
   for (int i = threadIdx.x; i < (int)(TC_BIAS_BYTES / sizeof(float)); i += blockDim.x)
     sbias[i] = (i < ((a.cout + 31) / 32) * 32) ? __ldg(a.bias + i) : 0.f;
   tc_fence_before();
   __syncthreads();
-  if (a.mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
+  if (k_mc > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   pdl_wait();                          // everything above touched only weights / parameters; activations from here on
   const uint32_t tmem_base = *tmem_slot;
-  const int nkb = a.taps * a.kchunks;
+  const int nkb = k_taps * a.kchunks;
   // Unit of iteration `it` = (tile, channel pass nh).  Units are dealt round-robin to the CLUSTERS: cluster-unit
   // v = cluster + it * #clusters covers tile pair v / nsplit (tile = pair * mc + rank: cluster peers consume the same weight
   // slabs in lock step, which is what the multicast needs) and channel pass v % nsplit.  With the two passes of a wide
   // exact-mode layer as separate units, 950 tiles on 74 clusters take 13 half-tile rounds instead of 7 whole ones.  A
   // cluster whose FIRST tile is out of range stops; otherwise an out-of-range tile is processed as an all-padding dummy.
-  const int ncl = (int)gridDim.x / a.mc, cl = ((int)blockIdx.x - (int)crank) / a.mc;
+  const int ncl = (int)gridDim.x / k_mc, cl = ((int)blockIdx.x - (int)crank) / k_mc;
   auto unit = [&](int it, int& tile, int& nh) -> bool {
     const int v = cl + it * ncl;
-    const int tp = (a.nsplit == 2) ? (v >> 1) : v;
-    nh = (a.nsplit == 2) ? (v & 1) : 0;
-    tile = a.tile_begin + tp * a.mc + (int)crank;
-    const bool ok = a.tile_begin + tp * a.mc < a.num_tiles;
+    const int tp = (k_nsplit == 2) ? (v >> 1) : v;
+    nh = (k_nsplit == 2) ? (v & 1) : 0;
+    tile = a.tile_begin + tp * k_mc + (int)crank;
+    const bool ok = a.tile_begin + tp * k_mc < a.num_tiles;
     if (tile >= a.num_tiles) tile = a.oob_tile;
     return ok;
   };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (a.halo) {
-      const int planes = (a.split == 3) ? 2 : 1;
+    if (k_halo) {
+      const int planes = (k_split == 3) ? 2 : 1;
       uint8_t* bring = smem + (size_t)a.a_slots * a.a_slot_bytes;
       int sa = 0, sb = 0, nb_loaded = 0;
       uint32_t pha = 0, phb = 0;
@@ -199,11 +208,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int tile, nh;
         if (!unit(it, tile, nh)) break;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
+        for (int kc = k_cat ? nh * 2 : 0; kc < (k_cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           uint8_t* slot = smem + (size_t)sa * a.a_slot_bytes;
           if (elect_one()) {
-            if (PAIR && a.cg2) {    // both CTAs' halo tiles complete on the leader's barrier
+            if (k_cg2) {    // both CTAs' halo tiles complete on the leader's barrier
               if (crank == 0) mbar_expect_tx(&fullA[sa], 2u * (uint32_t)(planes * a.a_plane_bytes));
               tma_load_3d_cg2(slot, &tmA_hi, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
               if (planes == 2) tma_load_3d_cg2(slot + a.a_plane_off, &tmA_lo, &fullA[sa], kc * 64, x0 - a.hoff, y0 - a.hoff);
@@ -215,21 +224,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           }
           __syncwarp();
           if (++sa == a.a_slots) { sa = 0; pha ^= 1; }
-          for (int tap = 0; tap < a.taps; ++tap) {
-            const int brow = a.cat ? (tap * 4 + kc) * 128 : (a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
-            const int bcol = a.diag ? 0 : kc * 64;
-            for (int pl = 0; pl < (a.cat ? 1 : planes); ++pl) {
+          for (int tap = 0; tap < k_taps; ++tap) {
+            const int brow = k_cat ? (tap * 4 + kc) * 128 : (k_diag ? tap * 256 + kc * 64 : tap * a.tap_rows + nh * a.n_mma);
+            const int bcol = k_diag ? 0 : kc * 64;
+            for (int pl = 0; pl < (k_cat ? 1 : planes); ++pl) {
               mbar_wait(&empty[sb], phb ^ 1);
               uint8_t* bs = bring + (size_t)sb * a.b_bytes;
               const CUtensorMap* tb = pl ? &tmB_lo : &tmB_hi;
               if (elect_one()) {
-                if (a.dbg_nob && nb_loaded >= a.b_stages) {
+                if (k_dbg_nob && nb_loaded >= a.b_stages) {
                   mbar_arrive(&full[sb]);            // EXPERIMENT (SFD2_TC_DEBUG_NOB): no weight traffic after the first fill
                 } else {
-                if (PAIR && a.cg2) {     // my half of the slab's rows stays here; the pair's MMA reads both halves
+                if (k_cg2) {     // my half of the slab's rows stays here; the pair's MMA reads both halves
                   if (crank == 0) mbar_expect_tx(&full[sb], 2u * (uint32_t)a.b_bytes);
                   tma_load_2d_cg2(bs, tb, &full[sb], bcol, brow + (int)crank * (a.n_mma / 2));
-                } else if (a.mc > 1) {
+                } else if (k_mc > 1) {
                   mbar_expect_tx(&full[sb], (uint32_t)a.b_bytes);
                   const int ro = (int)crank * (a.n_mma / 2);
                   tma_load_2d_mc(bs + ro * 128, tb, &full[sb], bcol, brow + ro, cmask);
@@ -253,30 +262,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         int tile, nh;
         if (!unit(it, tile, nh)) break;
         const int y0 = (tile / a.tiles_x) * a.tile_h, x0 = (tile % a.tiles_x) * a.tile_w;
-        for (int tap = 0; tap < a.taps; ++tap) {
-          const int ky = (a.taps == 9) ? tap / 3 : 1, kx = (a.taps == 9) ? tap % 3 : 1;
+        for (int tap = 0; tap < k_taps; ++tap) {
+          const int ky = (k_taps == 9) ? tap / 3 : 1, kx = (k_taps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < a.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * a.stage_bytes;
-            uint8_t* sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
+            uint8_t* sb = sa + (k_split == 3 ? 2 : 1) * TC_A_BYTES;
             const int c0 = kc * 64;
-            if ((PAIR && a.cg2)) {
+            if (k_cg2) {
               if (elect_one()) {
                 // both CTAs' bytes complete on the leader's barrier (its own arrival is this expect_tx)
                 if (crank == 0) mbar_expect_tx(&full[stage], 2u * (uint32_t)a.stage_bytes);
-                if (a.stride == 1) {
+                if (k_stride == 1) {
                   const int cx = x0 + kx - 1, cy = y0 + ky - 1;
                   tma_load_3d_cg2(sa, &tmA_hi, &full[stage], c0, cx, cy);
-                  if (a.split == 3) tma_load_3d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, cx, cy);
+                  if (k_split == 3) tma_load_3d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, cx, cy);
                 } else {
                   const int xp = (kx + 1) & 1, yp = (ky + 1) & 1;
                   const int cx = x0 + (kx - 1 - xp) / 2, cy = y0 + (ky - 1 - yp) / 2;
                   tma_load_5d_cg2(sa, &tmA_hi, &full[stage], c0, xp, cx, yp, cy);
-                  if (a.split == 3) tma_load_5d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
+                  if (k_split == 3) tma_load_5d_cg2(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
                 }
                 const int brow2 = tap * a.tap_rows + (int)crank * (a.n_mma / 2);   // my half of the slab's rows, kept here
                 tma_load_2d_cg2(sb, &tmB_hi, &full[stage], c0, brow2);
-                if (a.split == 3) tma_load_2d_cg2(sb + a.b_bytes, &tmB_lo, &full[stage], c0, brow2);
+                if (k_split == 3) tma_load_2d_cg2(sb + a.b_bytes, &tmB_lo, &full[stage], c0, brow2);
               }
               __syncwarp();
               if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -284,26 +293,26 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             if (elect_one()) {
             mbar_expect_tx(&full[stage], (uint32_t)a.stage_bytes);
-            if (a.stride == 1) {
+            if (k_stride == 1) {
               const int cx = x0 + kx - 1, cy = y0 + ky - 1;
               tma_load_3d(sa, &tmA_hi, &full[stage], c0, cx, cy);
-              if (a.split == 3) tma_load_3d(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, cx, cy);
+              if (k_split == 3) tma_load_3d(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, cx, cy);
             } else {
               const int xp = (kx + 1) & 1, yp = (ky + 1) & 1;
               const int cx = x0 + (kx - 1 - xp) / 2, cy = y0 + (ky - 1 - yp) / 2;
               tma_load_5d(sa, &tmA_hi, &full[stage], c0, xp, cx, yp, cy);
-              if (a.split == 3) tma_load_5d(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
+              if (k_split == 3) tma_load_5d(sa + TC_A_BYTES, &tmA_lo, &full[stage], c0, xp, cx, yp, cy);
             }
-            const int brow = a.diag ? tap * 256 + kc * 64 : tap * a.tap_rows;
-            const int bcol = a.diag ? 0 : c0;
-            if (a.mc > 1) {   // my half of the slab, delivered to both CTAs
+            const int brow = k_diag ? tap * 256 + kc * 64 : tap * a.tap_rows;
+            const int bcol = k_diag ? 0 : c0;
+            if (k_mc > 1) {   // my half of the slab, delivered to both CTAs
               const int hrows = a.n_mma / 2;
               const int ro = (int)crank * hrows;
               tma_load_2d_mc(sb + ro * 128, &tmB_hi, &full[stage], bcol, brow + ro, cmask);
-              if (a.split == 3) tma_load_2d_mc(sb + a.b_bytes + ro * 128, &tmB_lo, &full[stage], bcol, brow + ro, cmask);
+              if (k_split == 3) tma_load_2d_mc(sb + a.b_bytes + ro * 128, &tmB_lo, &full[stage], bcol, brow + ro, cmask);
             } else {
               tma_load_2d(sb, &tmB_hi, &full[stage], bcol, brow);
-              if (a.split == 3) tma_load_2d(sb + a.b_bytes, &tmB_lo, &full[stage], bcol, brow);
+              if (k_split == 3) tma_load_2d(sb + a.b_bytes, &tmB_lo, &full[stage], bcol, brow);
             }
             }
             __syncwarp();
@@ -315,16 +324,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // (whole warp runs the loops; tcgen05.mma / commit come from the one lane elect.sync picks - always the same)
-    if (a.halo) {
-      const bool pair = PAIR && a.cg2;
-      const uint32_t idesc = make_idesc_f16(pair ? 256 : 128, a.cat ? 16 : a.n_mma);
+    if (k_halo) {
+      const bool pair = k_cg2;
+      const uint32_t idesc = make_idesc_f16(pair ? 256 : 128, k_cat ? 16 : a.n_mma);
       const uint32_t idesc_cat = make_idesc_f16(128, 32);
       auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t acc) {
-        if (PAIR && a.cg2) umma_f16_cg2(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
+        if (k_cg2) umma_f16_cg2(d, da, db, idesc, acc); else umma_f16(d, da, db, idesc, acc);
       };
       auto commit = [&](uint64_t* bar, bool both) {     // both: the barrier exists in both CTAs of a multicast / pair cluster
-        if (PAIR && a.cg2) umma_commit_cg2(bar, cmask);
-        else if (both && a.mc > 1) umma_commit_mc(bar, cmask);
+        if (k_cg2) umma_commit_cg2(bar, cmask);
+        else if (both && k_mc > 1) umma_commit_mc(bar, cmask);
         else umma_commit(bar);
       };
       const uint32_t bring = smem_u32(smem + (size_t)a.a_slots * a.a_slot_bytes);
@@ -335,18 +344,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (!unit(it, tile, nh) || (pair && crank != 0)) break;      // CTA pair: the even CTA issues for both
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
-        for (int kc = a.cat ? nh * 2 : 0; kc < (a.cat ? nh * 2 + 2 : a.kchunks); ++kc) {
+        for (int kc = k_cat ? nh * 2 : 0; kc < (k_cat ? nh * 2 + 2 : a.kchunks); ++kc) {
           mbar_wait(&fullA[sa], pha);
           tc_fence_after();
           const uint32_t abase = smem_u32(smem + (size_t)sa * a.a_slot_bytes);
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.cat ? (kc & 1) * 128 : (a.diag ? kc * 64 : 0)));
-          const uint32_t ccol = a.cat ? dcol + 64u : (a.corr ? dcol + (uint32_t)a.acc_cols : dcol);
-          for (int tap = 0; tap < a.taps; ++tap) {
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (k_cat ? (kc & 1) * 128 : (k_diag ? kc * 64 : 0)));
+          const uint32_t ccol = k_cat ? dcol + 64u : (k_corr ? dcol + (uint32_t)a.acc_cols : dcol);
+          for (int tap = 0; tap < k_taps; ++tap) {
             const uint32_t off = (uint32_t)(((tap / 3) * a.hw + (tap % 3)) * 128);
             const uint64_t da_hi = make_desc_sw128_sbo(abase + off, (uint32_t)a.hw * 128);
             const uint64_t da_lo = make_desc_sw128_sbo(abase + (uint32_t)a.a_plane_off + off, (uint32_t)a.hw * 128);
-            const bool first = (tap == 0) && (a.diag || kc == 0);
-            if (a.cat) {
+            const bool first = (tap == 0) && (k_diag || kc == 0);
+            if (k_cat) {
               // K step k of the chunk = input channels 16k.. = two whole groups, whose 16 outputs are the only non-zero rows
               // of the block-diagonal slab: rows [32k, 32k+32) of the slab hold [w_hi 16 | w_lo 16] of exactly those.
               // a_hi x both (N = 32: main | correction columns of the 16 channels), then a_lo x w_hi (N = 16) into the
@@ -361,7 +370,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                   umma_f16(dcol + 32u * k + 16u, desc_advance_k(da_lo, k), desc_advance_k(dbc, k) + (uint64_t)(k * (4096 >> 4)), idesc, 1u);
-                if (a.mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
+                if (k_mc > 1) umma_commit_mc(&empty[sb], cmask); else umma_commit(&empty[sb]);
               }
               __syncwarp();
               if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
@@ -375,16 +384,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 mma(dcol, desc_advance_k(da_hi, k), desc_advance_k(db, k), (first && k == 0) ? 0u : 1u);
-              if (a.split == 3) {
+              if (k_split == 3) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  mma(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), (a.corr && first && k == 0) ? 0u : 1u);
+                  mma(ccol, desc_advance_k(da_lo, k), desc_advance_k(db, k), (k_corr && first && k == 0) ? 0u : 1u);
               }
               commit(&empty[sb], true);
             }
             __syncwarp();
             if (++sb == a.b_stages) { sb = 0; phb ^= 1; }
-            if (a.split == 3) {                 // weight slab, lo plane: a_hi * w_lo
+            if (k_split == 3) {                 // weight slab, lo plane: a_hi * w_lo
               mbar_wait(&full[sb], phb);
               tc_fence_after();
               db = make_desc_sw128(bring + (uint32_t)(sb * a.b_bytes));
@@ -407,7 +416,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
     } else {
-      const uint32_t idesc = make_idesc_f16((PAIR && a.cg2) ? 256 : 128, a.n_mma);
+      const uint32_t idesc = make_idesc_f16(k_cg2 ? 256 : 128, a.n_mma);
       const uint32_t idesc_ncat = make_idesc_f16(128, 2 * a.n_mma);
       int stage = 0;
       uint32_t phase = 0;
@@ -415,20 +424,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       uint32_t bphase = 0;
       for (int it = 0; it < a.iters; ++it) {
         int tile, nh;
-        if (!unit(it, tile, nh) || ((PAIR && a.cg2) && crank != 0)) break;     // CTA pair: the even CTA issues for both
+        if (!unit(it, tile, nh) || (k_cg2 && crank != 0)) break;     // CTA pair: the even CTA issues for both
         mbar_wait(&tempty[buf], bphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * a.stage_bytes);
-          const uint32_t sb = sa + (a.split == 3 ? 2 : 1) * TC_A_BYTES;
+          const uint32_t sb = sa + (k_split == 3 ? 2 : 1) * TC_A_BYTES;
           const uint64_t da_hi = make_desc_sw128(sa), da_lo = make_desc_sw128(sa + TC_A_BYTES);
           const uint64_t db_hi = make_desc_sw128(sb), db_lo = make_desc_sw128(sb + a.b_bytes);
-          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (a.diag ? (kb % a.kchunks) * 64 : 0));
-          const bool first = a.diag ? (kb < a.kchunks) : (kb == 0);
+          const uint32_t dcol = tmem_base + (uint32_t)(buf * a.buf_stride + (k_diag ? (kb % a.kchunks) * 64 : 0));
+          const bool first = k_diag ? (kb < a.kchunks) : (kb == 0);
           if (elect_one()) {
-          if (a.ncat) {
+          if (k_ncat) {
             // narrow layers (N <= 64): an SMEM-operand MMA at M = 128 costs >= 53 cycles whatever N is and 64 at N = 128
             // (tools/mma_rate_probe.py), so a_hi x w_hi and a_hi x w_lo go out as ONE MMA over the adjacent [w_hi | w_lo]
             // slabs of the stage - it fills the main columns and, right behind them, the correction columns
@@ -440,16 +449,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
               umma_f16(dcol + (uint32_t)a.acc_cols, desc_advance_k(da_lo, k), desc_advance_k(db_hi, k), idesc, 1u);
           } else
 #pragma unroll 1
-          for (int pass = 0; pass < a.split; ++pass) {
+          for (int pass = 0; pass < k_split; ++pass) {
             const uint64_t da = (pass == 2) ? da_lo : da_hi;
             const uint64_t db = (pass == 1) ? db_lo : db_hi;
             // the tensor core truncates (round-toward-zero) every time it adds into the fp32 accumulator, so
             // the two small correction passes go to their own accumulator: truncation there is relative to a
             // ~2^-11 smaller magnitude, and the main accumulator sees 3x fewer additions.
-            const bool to_corr = a.corr && pass > 0;
+            const bool to_corr = k_corr && pass > 0;
             const uint32_t d = to_corr ? dcol + (uint32_t)a.acc_cols : dcol;
             const int first_pass = to_corr ? 1 : 0;
-            if ((PAIR && a.cg2)) {
+            if (k_cg2) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_f16_cg2(d, desc_advance_k(da, k), desc_advance_k(db, k), idesc, (first && pass == first_pass && k == 0) ? 0u : 1u);
@@ -460,13 +469,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
           }
           // smem slot free once these MMAs have read it (in both CTAs when the slab is multicast / the MMA spans the pair)
-          if ((PAIR && a.cg2)) umma_commit_cg2(&empty[stage], cmask);
-          else if (a.mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
+          if (k_cg2) umma_commit_cg2(&empty[stage], cmask);
+          else if (k_mc > 1) umma_commit_mc(&empty[stage], cmask); else umma_commit(&empty[stage]);
           }
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        if (elect_one()) { if ((PAIR && a.cg2)) umma_commit_cg2(&tfull[buf], cmask); else umma_commit(&tfull[buf]); }   // accumulator complete -> epilogue
+        if (elect_one()) { if (k_cg2) umma_commit_cg2(&tfull[buf], cmask); else umma_commit(&tfull[buf]); }   // accumulator complete -> epilogue
         __syncwarp();
         if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       }
@@ -491,8 +500,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint32_t rph = 0u;                           // residual-barrier phase per tile (bit ti)
     int buf = 0;
     uint32_t bphase = 0;
-    const int nchunks = (a.nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
-    const int nstore = (a.epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
+    const int nchunks = (k_nsplit > 1) ? a.n_mma / 32 : (a.cout + 31) / 32;   // per channel pass
+    const int nstore = (k_epi_fn == 2) ? 2 : nchunks;   // the softmax head writes channels 0..63 only
     const int r = lane;                          // row of this warp's 32-pixel box (2 tile rows x 16 px)
     auto tile_xy = [&](int it, int& x0, int& y0, int& nh) -> bool {
       int tile;
@@ -506,7 +515,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (ch >= nstore || it >= a.iters || !tile_xy(it, x0, y0, nh)) return;
       uint64_t* wr = wres_of(tdst);
       uint8_t* sd = st0 + tdst * 4096;
-      if (a.dbg_nob & 8) { mbar_arrive(wr); return; }
+      if (k_dbg_nob & 8) { mbar_arrive(wr); return; }
       mbar_expect_tx(wr, a.has_res == 2 ? 4096u : 2048u);
       tma_load_3d(sd, &tmR_hi, wr, ch * 32, x0, y0);
       if (a.has_res == 2) tma_load_3d(sd + 2048, &tmR_lo, wr, ch * 32, x0, y0);
@@ -519,7 +528,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(&tfull[buf], bphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * a.buf_stride);
-      if (a.epi_fn) {
+      if (k_epi_fn) {
         // Head epilogues (fp32 output, <= 128 channels = at most two own chunks per warp): every pixel needs a reduction
         // over ALL its channels before anything can be written (sum x^2 for F.normalize, sfd2.py:342; sum_65 exp for the
         // detector, sfd2.py:330-333).  Each warp reads only its own chunks, keeps them in registers, and the two warps
@@ -536,7 +545,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) xo[ci][j] = __uint_as_float(v[j]);
-            if (a.corr) {
+            if (k_corr) {
               tmem_ld32(taddr + a.acc_cols + ch * 32, v);
               tmem_ld_wait();
 #pragma unroll
@@ -546,19 +555,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 32; ++j) {
               const float t = xo[ci][j] + sbias[ch * 32 + j];
               xo[ci][j] = t;
-              if (ch * 32 + j < a.cout) part += (a.epi_fn == 1) ? t * t : expf(t);
+              if (ch * 32 + j < a.cout) part += (k_epi_fn == 1) ? t * t : expf(t);
             }
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if ((PAIR && a.cg2)) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }   // this warp's share of the accumulator is in registers
+        if (lane == 0) { if (k_cg2) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }   // this warp's share of the accumulator is in registers
         float* ex = exch + ((it & 1) * TC_EPI_WARPS + ew) * 32;    // double-buffered by tile parity
         ex[lane] = part;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the two warps of this lane quarter
         const float acc = part + exch[((it & 1) * TC_EPI_WARPS + (ew ^ 4)) * 32 + lane];
         // one reciprocal per pixel, then multiplies (<= 1 ulp from the reference's per-element division)
-        const float row_scale = __frcp_rn((a.epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
+        const float row_scale = __frcp_rn((k_epi_fn == 1) ? fmaxf(sqrtf(acc), 1e-12f) : (acc + 0.00001f));
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           const int ch = h + 2 * ci;
@@ -567,7 +576,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              float t = (a.epi_fn == 1) ? xo[ci][j] * row_scale : expf(xo[ci][j]) * row_scale;
+              float t = (k_epi_fn == 1) ? xo[ci][j] * row_scale : expf(xo[ci][j]) * row_scale;
               xo[ci][j] = a.relu ? fmaxf(t, 0.f) : t;
             }
 #pragma unroll
@@ -589,10 +598,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // (atomicAdd on a zeroed map: two addends, so the result does not depend on their order)
       float sta0 = h ? 0.f : a.sta_b[0], sta1 = h ? 0.f : a.sta_b[1], sta2 = h ? 0.f : a.sta_b[2];
       for (int ch = h; ch < nstore; ch += 2) {
-        if (a.dbg_nob & 16) break;                 // experiment: null epilogue (timing only)
+        if (k_dbg_nob & 16) break;                 // experiment: null epilogue (timing only)
         const int c0 = ch * 32;
         // accumulator column of channel c0: diag-cat keeps [main 16 | correction 16] per 16 channels, 2 columns per channel
-        const uint32_t tcol = a.cat ? (uint32_t)(2 * c0) : (uint32_t)c0;
+        const uint32_t tcol = k_cat ? (uint32_t)(2 * c0) : (uint32_t)c0;
         const uint32_t coff = (uint32_t)a.acc_cols;
         uint32_t v[32];
         float x[32];
@@ -606,11 +615,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
         tmem_ld32(taddr + tcol, v);
         if (!a.has_res) {                         // the store that last used this tile must have finished reading it
-          if (lane == 0 && !(a.dbg_nob & 2)) { if (nst > 1) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // (with a residual, issue_res waited already)
+          if (lane == 0 && !(k_dbg_nob & 2)) { if (nst > 1) bulk_wait_read<1>(); else bulk_wait_read<0>(); }   // (with a residual, issue_res waited already)
           __syncwarp();
         }
         tmem_ld_wait();
-        if (a.cat) {
+        if (k_cat) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + __uint_as_float(v[j + 16]);
           tmem_ld32(taddr + tcol + 32u, v);
@@ -620,7 +629,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
-        if (a.corr) {
+        if (k_corr) {
           tmem_ld32(taddr + tcol + coff, v);
           tmem_ld_wait();
 #pragma unroll
@@ -658,7 +667,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
         }
-        if (a.out_mode == 2) {                    // fp32 rows of 128 B, SWIZZLE_128B
+        if (k_out_mode == 2) {                    // fp32 rows of 128 B, SWIZZLE_128B
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             *reinterpret_cast<float4*>(st + r * 128 + ((g ^ (r & 7)) << 4)) =
@@ -670,7 +679,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int g = 0; g < 4; ++g)
             *reinterpret_cast<uint4*>(st + r * 64 + ((g ^ sw64) << 4)) = reinterpret_cast<const uint4*>(hi)[g];
-          if (a.out_mode == 1) {
+          if (k_out_mode == 1) {
             __align__(16) __half lo[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) lo[j] = __float2half_rn(x[j] - __half2float(hi[j]));
@@ -696,13 +705,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         fence_proxy_async();                      // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
         if (lane == 0) {
-          if (!(a.dbg_nob & 4)) {
+          if (!(k_dbg_nob & 4)) {
           tma_store_3d(&tmO_hi, st, cbase + c0, x0, y0);
-          if (a.out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
+          if (k_out_mode == 1) tma_store_3d(&tmO_lo, st + 2048, cbase + c0, x0, y0);
           }
           bulk_commit();
           if (a.has_res && nst != 3) {            // one tile: refill it with the residual of this warp's next chunk
-            if (!(a.dbg_nob & 2)) bulk_wait_read<0>();
+            if (!(k_dbg_nob & 2)) bulk_wait_read<0>();
             if (ch + 2 < nstore) issue_res(it, ch + 2, 0); else issue_res(it + 1, h, 0);
           }
         }
@@ -710,7 +719,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) { if ((PAIR && a.cg2)) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }
+      if (lane == 0) { if (k_cg2) mbar_arrive_cluster(&tempty[buf], 0); else mbar_arrive(&tempty[buf]); }
       if (++buf == a.nbuf) { buf = 0; bphase ^= 1; }
       if (a.sta_out) {                            // (nsplit == 1 here) this lane's pixel: TMEM lane q*32 + r of the tile
         const int py = y0 + r / a.tile_w, px = x0 + r % a.tile_w;
@@ -724,13 +733,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (a.mc > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
-  if (warp == 2) { if ((PAIR && a.cg2)) tmem_dealloc_cg2(tmem_base, (uint32_t)a.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols); }
+  if (k_mc > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
+  if (warp == 2) { if (k_cg2) tmem_dealloc_cg2(tmem_base, (uint32_t)a.tmem_cols); else tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols); }
 }
 
 // ------------------------------------------------------------------------------------ host side
 int g_fuse_sta = 1;       // SFD2_FUSE_STA=0: run ConvSta as its own kernel (sta_kernel) instead of in rb2c3's epilogue
 int g_tc_multicast = 1;   // SFD2_TC_MULTICAST=0 in the environment disables the 2-CTA weight multicast
+int g_tc_slim = 1;        // SFD2_TC_SLIM=0: the 1x1 pair layers run the generic pair instantiation
 int g_tc_stiles = 1;      // SFD2_TC_STILES=0: one staging tile per epilogue warp also in the CTA-pair layers
 int g_tc_cg2 = 2;         // SFD2_TC_CG2: 0 = no CTA-pair MMAs, 1 = the 1x1 layers, 2 = every per-tap-ring layer that qualifies
 int g_tc_pdl = 1;         // SFD2_TC_PDL=0: launch the conv layers without programmatic dependent launch
@@ -959,9 +969,11 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   SFD2_CHECK(!fuse_sta || (!out_f32_map && L.cout == 256 && sta->cin == 256 && sta->cout == 3 && sta->k == 1 && sta->w.size() == 768),
              SFD2_ERR_ARG, "conv_tc(%s): ConvSta can only be fused into a 256-channel fp16-plane layer", L.name.c_str());
   // alignment slack, staging, bias, barriers
-  // CTA-pair 1x1 layers are bound by their epilogue, not by the operand ring: two 64 KB stages, and the shared memory the
-  // halved weight slabs free goes to extra staging tiles (TcConvArgs::stiles)
-  a.stiles = (a.cg2 && L.k == 1 && !out_f32_map && g_tc_stiles) ? (res ? 3 : 2) : 1;
+  // CTA-pair 1x1 layers with a residual are bound by their epilogue, not by the operand ring: two 64 KB stages, and the shared
+  // memory the halved weight slabs free goes to extra staging tiles (TcConvArgs::stiles)
+  // (measured with the slim instantiation: without a residual, three operand stages + one staging tile beat two + two,
+  //  rb.c1 49-50 us against 56-57; with a residual two stages + three staging tiles win, rb.c3 70-72 against 78-85)
+  a.stiles = (a.cg2 && L.k == 1 && !out_f32_map && g_tc_stiles && res) ? 3 : 1;
   const int smem_fixed = 1024 + a.stiles * TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + ((out_f32_map && epi_fn) ? TC_EXCH_BYTES : 0);
   int stages = (smem_max - smem_fixed) / a.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -1006,8 +1018,6 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
   const CUtensorMap& r_hi = res ? res->tm_st[so] : o_hi;       // residual boxes have the epilogue warps' pixel shape
   const CUtensorMap& r_lo = res ? res->tm_st[so + 1] : o_lo;
   const size_t smem = (size_t)a.ring_bytes + smem_fixed;
-  auto kern = a.cg2 ? tc_conv_kernel<true> : tc_conv_kernel<false>;
-  SFD2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const CUtensorMap* tmA = in.tm + (a.halo ? (split1 ? 6 : 4) : (L.stride == 2 ? 2 : 0));
   // multicast needs an even number of 1024-byte-aligned half slabs and at least one full cluster of work
   a.mc = can_mc ? 2 : 1;
@@ -1020,6 +1030,10 @@ int launch_conv_tc(const Act& in, const Layer& L, Act out, const Act* res, const
     if (nob == 16) a.dbg_nob = 8;
     if (nob == 32) a.dbg_nob = 16 | 8;                        // 32: null epilogue - accumulators are handed back untouched (timing only)                             // 16: residual tiles are not loaded (timing only)                              // 4: epilogue does not wait for its TMA stores to drain (RACY, timing only)
   }
+  const bool slim = g_tc_slim && a.cg2 && a.mc == 2 && !a.halo && L.k == 1 && L.stride == 1 && split == 3 && !diag && !a.cat && !a.ncat &&
+                    a.nsplit == 1 && !a.corr && a.epi_fn == 0 && a.out_mode == 1 && a.dbg_nob == 0;
+  auto kern = slim ? tc_conv_kernel<true, true> : (a.cg2 ? tc_conv_kernel<true, false> : tc_conv_kernel<false, false>);
+  SFD2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = n_range < num_sms ? n_range : num_sms;
   if (a.mc > 1) grid = (grid / 2) * 2 > 0 ? ((grid + 1) / 2) * 2 : 2;
   if (a.mc > 1 && grid > num_sms) grid -= 2;

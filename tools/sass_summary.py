@@ -12,7 +12,7 @@ for f in funcs:
     short = next((k for k in ("tc_conv_kernel", "tc_match_kernel", "tc_desc_sparse_kernel", "conv1a_mma_kernel", "match_prep_kernel", "preprocess_kernel") if k in name), None)
     if not short:
         continue
-    variant = "_sub2" if "ILi2E" in name else ("_sub1" if "ILi1E" in name else ("_pair" if "ILb1E" in name else ""))
+    variant = "_sub2" if "ILi2E" in name else ("_sub1" if "ILi1E" in name else ("_pair_slim" if "ILb1ELb1E" in name else ("_pair" if "ILb1ELb0E" in name else "")))
     lines = [l for l in f.split("\n") if re.search(r"/\*[0-9a-f]{4,}\*/", l)]
     hist = collections.Counter()
     keep = []
