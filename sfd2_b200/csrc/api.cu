@@ -15,6 +15,7 @@ namespace sfd2 {
 static thread_local char g_err[1024] = "";
 thread_local long long g_launches = 0;
 int g_band_layers = 2;    // SFD2_BAND_LAYERS: how many of conv1b / conv2a / conv2b follow conv1a band by band (0..3)
+int g_post_pdl = 1;       // SFD2_POST_PDL=0: heat / nms / select / descriptor kernels launched without programmatic stream serialization
 int g_host_bands = 4;     // SFD2_HOST_BANDS: row bands of a single host image's upload (<= 1: one copy, conv1a after it)
 
 void set_error(const char* fmt, ...) {
@@ -395,10 +396,11 @@ static int extract_one(sfd2_ctx* c, Ws& w, const void* img, int img_dtype, int H
     RUNP("l2norm128", launch_l2norm128(w.descmap, w.H4 * w.W4, st));
   }
   if (p->use_stability && !fuse_sta) RUNP("sta", launch_sta(A[BA], tc ? (split == 3 ? 1 : 2) : 0, c->L("sta"), w.sta, st));
+  if (cudaMemsetAsync(w.counter, 0, sizeof(int), st) != cudaSuccess) { set_error("cudaMemsetAsync(counter) failed"); return SFD2_ERR_CUDA; }
   RUNP("heat", launch_heat(w.semi, w.H8, w.W8, w.sta, w.H4, w.W4, p->use_stability, w.heat, H, W, st));
   RUNP("nms", launch_nms(w.heat, H, W, p->conf_th, p->border, p->border_w > 0 ? p->border_w : W, p->border_h > 0 ? p->border_h : H,
                          (c->debug_flags & 1) ? w.nmsdbg : nullptr, w.cand, w.cap,
-                 w.counter, st));
+                 w.counter, st, /*zero_counter=*/false));
   RUNP("select", launch_select(w.cand, w.cap, w.counter, W, p->topk, kpts, scores, count, w.status, w.scratch, st));
   if (sparse_d)   // the descriptor head only at the pixels that are sampled (tc_desc_sparse.cu); bit-identical rows
     RUNP("tc_conv:headD", launch_desc_sparse(A[DA], c->L("headD"), H, W, kpts, count, p->topk, w.drows, desc, st));
@@ -441,6 +443,7 @@ SFD2_API int sfd2_create(const void* blob, size_t nbytes, int device, sfd2_ctx**
   if (const char* e = getenv("SFD2_TC_CG2")) g_tc_cg2 = atoi(e);
   if (const char* e = getenv("SFD2_TC_STILES")) g_tc_stiles = atoi(e);
   if (const char* e = getenv("SFD2_TC_SLIM")) g_tc_slim = atoi(e) != 0;
+  if (const char* e = getenv("SFD2_POST_PDL")) g_post_pdl = atoi(e) != 0;
   if (const char* e = getenv("SFD2_SPARSE_DESC")) g_sparse_desc = atoi(e) != 0;
   if (const char* e = getenv("SFD2_HOST_BANDS")) g_host_bands = atoi(e);
   if (const char* e = getenv("SFD2_BAND_LAYERS")) g_band_layers = atoi(e);

@@ -105,7 +105,7 @@ int launch_desc_sparse(const Act& in, const Layer& L, int H, int W, const float*
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st);
 int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out,
-               unsigned long long* cand, int cap, int* counter, cudaStream_t st);
+               unsigned long long* cand, int cap, int* counter, cudaStream_t st, bool zero_counter = true);
 int launch_select(unsigned long long* cand, int cap, const int* counter, int W, int topk, float* kpts,
                   float* scores, int32_t* count_out, int* status, unsigned long long* scratch,
                   cudaStream_t st);
@@ -134,6 +134,19 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* d
 int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, int is_f32, int swizzle);
 
+// Launch with programmatic stream serialization (SFD2_POST_PDL=0 disables): the kernel may be scheduled while its
+// predecessor in the stream drains; every kernel launched this way executes griddepcontrol.wait before it touches global memory.
+extern int g_post_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_post_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 extern int g_sparse_desc, g_tc_slim, g_tc_stiles, g_tc_cg2, g_tc_pdl, g_tc_multicast, g_tc_halo, g_tc_nsplit, g_conv1a_mma, g_fuse_sta, g_tc_diagcat, g_tc_split1x1;
 extern thread_local long long g_launches;  // kernels launched by this thread (for sfd2_launch_count)
 

@@ -4,6 +4,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace sfd2 {
 
@@ -35,6 +36,8 @@ __device__ __forceinline__ float score_at(const float* __restrict__ semi, int W8
 //              * {0.1, 0.5, 1.0}[argmax_c bilinear(sta_logits)[c]]   (sfd2.py:345-347, extractor.py:141)
 __global__ void heat_kernel(const float* __restrict__ semi, int H8, int W8, const float* __restrict__ sta, int H4,
                             int W4, int use_sta, float* __restrict__ heat, int H, int W) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();                      // (launch_pdl) the head's maps are complete from here on
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= W || y >= H) return;
   const int HS = H8 * 8, WS = W8 * 8;
@@ -73,7 +76,7 @@ __global__ void heat_kernel(const float* __restrict__ semi, int H8, int W8, cons
 int launch_heat(const float* semi, int H8, int W8, const float* sta, int H4, int W4, int use_sta, float* heat,
                 int H, int W, cudaStream_t st) {
   dim3 block(32, 8), grid(cdiv(W, 32), cdiv(H, 8));
-  heat_kernel<<<grid, block, 0, st>>>(semi, H8, W8, sta, H4, W4, use_sta, heat, H, W);
+  SFD2_CUDA(launch_pdl(heat_kernel, grid, block, 0, st, semi, H8, W8, sta, H4, W4, use_sta, heat, H, W));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
@@ -160,6 +163,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 2)
 nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int border, int bw, int bh,
            float* __restrict__ nms_out,
            unsigned long long* __restrict__ cand, int cap, int* __restrict__ counter) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float sm[];
   float* s = sm;             // scores (-inf outside the image)
   float* u = sm + NP_N;      // row-pass scratch of the float pools
@@ -225,13 +230,14 @@ nms_kernel(const float* __restrict__ heat, int H, int W, float conf_th, int bord
 
 // bw / bh: the extents the border test uses (the reference tests scaled coordinates against the ORIGINAL
 // image size in its multi-scale loop, nets/extractor.py:181-182); pass W / H for the single-scale case
+// zero_counter = false: the caller has zeroed `counter` earlier on the stream (so that no memset sits between heat_kernel and this launch)
 int launch_nms(const float* heat, int H, int W, float conf_th, int border, int bw, int bh, float* nms_out, unsigned long long* cand,
-               int cap, int* counter, cudaStream_t st) {
+               int cap, int* counter, cudaStream_t st, bool zero_counter) {
   const size_t smem = (size_t)2 * NP_N * sizeof(float) + 3 * NP_N;
   SFD2_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch (cheap)
-  SFD2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+  if (zero_counter) SFD2_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
   dim3 grid(cdiv(W, NT_W), cdiv(H, NT_H));
-  nms_kernel<<<grid, NMS_THREADS, smem, st>>>(heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter);
+  SFD2_CUDA(launch_pdl(nms_kernel, grid, dim3(NMS_THREADS), smem, st, heat, H, W, conf_th, border, bw, bh, nms_out, cand, cap, counter));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
@@ -258,6 +264,8 @@ select_kernel(const unsigned long long* __restrict__ cand, int cap, const int* _
               int* __restrict__ status, int* __restrict__ rank_buf, int* __restrict__ arrive) {
   __shared__ unsigned long long keys[SEL_CHUNK];
   __shared__ int is_last;
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   int n = *counter;
   if (n > cap) {                       // more candidates than the workspace holds: report, keep what fits
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *status = SFD2_ERR_OVERFLOW;
@@ -314,7 +322,7 @@ int launch_select(unsigned long long* cand, int cap, const int* counter, int W, 
   int* rank_buf = reinterpret_cast<int*>(scratch);
   int* arrive = rank_buf + cap;
   dim3 grid(cdiv(cap, SEL_THREADS), SEL_Y);
-  select_kernel<<<grid, SEL_THREADS, 0, st>>>(cand, cap, counter, W, topk, kpts, scores, count_out, status, rank_buf, arrive);
+  SFD2_CUDA(launch_pdl(select_kernel, grid, dim3(SEL_THREADS), 0, st, cand, cap, counter, W, topk, kpts, scores, count_out, status, rank_buf, arrive));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
@@ -326,6 +334,8 @@ int launch_select(unsigned long long* cand, int cap, const int* counter, int W, 
 __global__ void sample_kernel(const float* __restrict__ desc_map, int H4, int W4, int H, int W,
                               const float* __restrict__ kpts, const int32_t* __restrict__ count, int topk,
                               float* __restrict__ out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= topk) return;
   float4* o = reinterpret_cast<float4*>(out + (size_t)warp * 128) + lane;
@@ -360,7 +370,7 @@ __global__ void sample_kernel(const float* __restrict__ desc_map, int H4, int W4
 int launch_sample(const float* desc_map, int H4, int W4, int H, int W, const float* kpts, const int32_t* count,
                   int topk, float* desc_out, cudaStream_t st) {
   if (topk <= 0) return SFD2_OK;
-  sample_kernel<<<cdiv(topk * 32, 256), 256, 0, st>>>(desc_map, H4, W4, H, W, kpts, count, topk, desc_out);
+  SFD2_CUDA(launch_pdl(sample_kernel, dim3(cdiv(topk * 32, 256)), dim3(256), 0, st, desc_map, H4, W4, H, W, kpts, count, topk, desc_out));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;

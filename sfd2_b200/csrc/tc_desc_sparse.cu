@@ -70,6 +70,8 @@ tc_desc_sparse_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
   float* sbias = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();                                                  // (launch_pdl) the selection's count / keypoints are final from here on
   const int n = min(max(*a.count, 0), a.topk);
   const int row0 = blockIdx.x * 128;
   if (row0 >= 4 * n) return;                                   // (uniform) nothing sampled in this tile
@@ -186,6 +188,8 @@ tc_desc_sparse_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
 // bilinear blend of a keypoint's four tap rows + L2 normalisation: sample_kernel's arithmetic on the gathered rows
 __global__ void sample_rows_kernel(const float* __restrict__ rows, int H4, int W4, int H, int W, const float* __restrict__ kpts,
                                    const int32_t* __restrict__ count, int topk, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= topk) return;
   float4* o = reinterpret_cast<float4*>(out + (size_t)warp * 128) + lane;
@@ -226,9 +230,9 @@ int launch_desc_sparse(const Act& in, const Layer& L, int H, int W, const float*
   a.bias = L.b_dev; a.rows = rows;
   const size_t smem = 1024 + (size_t)DS_STAGES * DS_STAGE_BYTES + 256 + 512;
   SFD2_CUDA(cudaFuncSetAttribute(tc_desc_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_desc_sparse_kernel<<<cdiv(4 * topk, 128), DS_THREADS, smem, st>>>(L.tm_w_hi, a);
+  SFD2_CUDA(launch_pdl(tc_desc_sparse_kernel, dim3(cdiv(4 * topk, 128)), dim3(DS_THREADS), smem, st, L.tm_w_hi, a));
   ++g_launches;
-  sample_rows_kernel<<<cdiv(topk * 32, 256), 256, 0, st>>>(rows, in.H, in.W, H, W, kpts, count, topk, desc_out);
+  SFD2_CUDA(launch_pdl(sample_rows_kernel, dim3(cdiv(topk * 32, 256)), dim3(256), 0, st, rows, in.H, in.W, H, W, kpts, count, topk, desc_out));
   ++g_launches;
   SFD2_CUDA(cudaGetLastError());
   return SFD2_OK;
