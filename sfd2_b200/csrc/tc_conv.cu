@@ -18,12 +18,17 @@
 //   layers accumulate in their own TMEM columns (TcConvArgs::corr) and are added in the epilogue.
 // * grouped 3x3 (groups=32, 8 ch/group): "diag" mode - for each 64-channel chunk the weight slab is
 //   the 64x64 block-diagonal piece, one N=64 MMA per chunk into its own 64 accumulator columns; in exact
-//   mode the slab is [w_hi | w_lo] and a_hi meets both halves in one N=128 MMA (TcConvArgs::cat).
+//   mode the slab is [w_hi 16 | w_lo 16] per K step and the MMAs are N = 32 / N = 16 on the non-zero blocks
+//   only (TcConvArgs::cat).
+// * work units = (tile pair, channel pass), dealt round-robin to the clusters (`unit` in the kernel).
 //
 // * weight multicast: CTAs run as clusters of 2 neighbouring tiles; each CTA fetches HALF of every
 //   weight slab and TMA-multicasts it into both CTAs' shared memory, halving the L2->SM traffic of
 //   the B operand (the kernel is L2-bandwidth bound otherwise).  A stage is released to the
 //   producers only when BOTH CTAs' MMAs have consumed it (multicast tcgen05.commit).
+// * CTA pairs (template PAIR, TcConvArgs::cg2): the exact-mode per-tap-ring layers run ONE
+//   tcgen05.mma.cta_group::2 of M = 256 over the cluster instead - each CTA keeps only its half of the slab.
+//   SLIM is the compile-time-specialised instantiation of that for the 1x1 layers.
 //
 // Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = MMA
 // issuer (one elected lane), warps 2..9 = epilogue: TMEM lane quarter = warp % 4, and the two warps
